@@ -1,0 +1,200 @@
+"""nct_b200 -- Python host-side mirror of the reference's operator surface over libnct.so.
+
+The product is `libnct.so` (hand-written sm_100a CUDA behind the C ABI of include/nct.h)
+and the `neural_color_transfer` CLI built on it.  This module is the ctypes binding used
+by tests/ and bench.py; method names follow the reference's functions
+(NCT/GeneralizedPatchMatch.cuh:18-50, NCT/main.cu:47-454) so the parity tests read like
+the reference's call sites.  torch is used only for device memory, streams and
+torch.distributed plumbing.
+
+There is no CPU fallback: importing works without a GPU (so the ABI can be checked), but
+`Context()` raises if libnct.so is missing or no sm_100 device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnct.so")
+
+c_ctx_p = C.c_void_p
+_i, _f, _d, _p, _ll = C.c_int, C.c_float, C.c_double, C.c_void_p, C.c_longlong
+
+# name -> (restype, argtypes); every symbol include/nct.h declares must be listed here
+# (tests/test_abi.py cross-checks this table against the header).
+ABI = {
+    "nct_create": (_i, [_i, C.POINTER(c_ctx_p)]),
+    "nct_destroy": (_i, [c_ctx_p]),
+    "nct_last_error": (C.c_char_p, [c_ctx_p]),
+    "nct_set_stream": (_i, [c_ctx_p, _p]),
+    "nct_get_stream": (_p, [c_ctx_p]),
+    "nct_synchronize": (_i, [c_ctx_p]),
+    "nct_version": (_i, []),
+    "nct_launch_count": (_ll, [c_ctx_p]),
+    "nct_reset_launch_count": (None, [c_ctx_p]),
+    "nct_chw_to_hwc": (_i, [c_ctx_p, _p, _p, _i, _i, _i]),
+    "nct_hwc_to_chw": (_i, [c_ctx_p, _p, _p, _i, _i, _i]),
+    "nct_l2norm": (_i, [c_ctx_p, _p, _p, _i, _i, _i]),
+    "nct_nnf_init": (_i, [c_ctx_p, _p, _i, _i, _i, _i]),
+    "nct_nnf_upsample": (_i, [c_ctx_p, _p, _i, _i, _p, _i, _i, _i, _i]),
+    "nct_patchmatch": (_i, [c_ctx_p, _p, _p, _p, _p, C.POINTER(_i)]),
+    "nct_patchmatch_bidir": (_i, [c_ctx_p, _p, _p, _p, _p, _p, _p, C.POINTER(_i)]),
+    "nct_xorwow_table": (_i, [c_ctx_p, _p, _i, _i]),
+    "nct_patchmatch_stats": (_i, [c_ctx_p, C.POINTER(_ll)]),
+    "nct_patchmatch_count_evals": (_i, [c_ctx_p, _i]),
+}
+
+_lib = None
+
+
+class NctError(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen libnct.so and bind every ABI symbol; raises NctError when the CUDA extension
+    is missing (the product path never falls back to anything else)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise NctError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). libnct has no CPU fallback."
+        )
+    lib = C.CDLL(path)
+    for name, (res, args) in ABI.items():
+        fn = getattr(lib, name)  # AttributeError => symbol missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def make_params(C_, ah, aw, bh, bw, iters=10, rs_max=32, patch=3):
+    """The reference's 11-int PatchMatch parameter block (NCT/main.cu:204-214)."""
+    return (_i * 11)(C_, ah, aw, bh, bw, patch, iters, rs_max, 0, 10, 1)
+
+
+def level_sizes(n: int, levels: int = 5):
+    """Feature-map side lengths conv1_1..conv5_1 of an n-pixel side under Caffe's ceil-mode
+    2x2/2 pooling (caffe/layers/pooling_layer.cpp:90-93): n -> ceil((n-2)/2)+1."""
+    out = [n]
+    for _ in range(levels - 1):
+        n = -(-(n - 2) // 2) + 1
+        out.append(n)
+    return out
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """One libnct context = one GPU + one stream (reference: the process-wide CUDA device
+    of NCT/main.cu:562-570)."""
+
+    def __init__(self, gpu_id: int = 0, stream=None):
+        self.lib = load_library()
+        h = c_ctx_p()
+        rc = self.lib.nct_create(gpu_id, C.byref(h))
+        if rc != 0:
+            raise NctError(f"nct_create({gpu_id}) failed with {rc} (no CUDA sm_100 device? libnct has no CPU fallback)")
+        self.h = h
+        self.gpu_id = gpu_id
+        if stream is not None:
+            self.set_stream(stream)
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise NctError(f"libnct error {rc}: {self.lib.nct_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nct_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream):
+        """stream: torch.cuda.Stream, raw cudaStream_t int, or None (ctx-owned stream)."""
+        handle = getattr(stream, "cuda_stream", stream) or 0
+        self._check(self.lib.nct_set_stream(self.h, C.c_void_p(handle)))
+
+    def synchronize(self):
+        self._check(self.lib.nct_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.nct_launch_count(self.h))
+
+    def reset_launch_count(self):
+        self.lib.nct_reset_launch_count(self.h)
+
+    # -- feature helpers
+    def chw_to_hwc(self, src, dst=None):
+        import torch
+        Cn, H, W = src.shape
+        dst = dst if dst is not None else torch.empty((H, W, Cn), dtype=torch.float32, device=src.device)
+        self._check(self.lib.nct_chw_to_hwc(self.h, _ptr(src), _ptr(dst), Cn, H, W))
+        return dst
+
+    def hwc_to_chw(self, src, dst=None):
+        import torch
+        H, W, Cn = src.shape
+        dst = dst if dst is not None else torch.empty((Cn, H, W), dtype=torch.float32, device=src.device)
+        self._check(self.lib.nct_hwc_to_chw(self.h, _ptr(src), _ptr(dst), Cn, H, W))
+        return dst
+
+    def norm(self, src_hwc, dst=None):
+        """norm(dst, src, NULL, dim) of NCT/GeneralizedPatchMatch.cu:237-283 (HWC layout)."""
+        import torch
+        H, W, Cn = src_hwc.shape
+        dst = dst if dst is not None else torch.empty_like(src_hwc)
+        self._check(self.lib.nct_l2norm(self.h, _ptr(src_hwc), _ptr(dst), Cn, H, W))
+        return dst
+
+    # -- NNF
+    def init_ann(self, ann, ah, aw, bh, bw):
+        """init_Ann_kernel (NCT/GeneralizedPatchMatch.cu:527-544); ann: int32/uint32 [ah*aw] cuda tensor."""
+        self._check(self.lib.nct_nnf_init(self.h, _ptr(ann), ah, aw, bh, bw))
+        return ann
+
+    def upsample(self, ann_half, ah_half, aw_half, ann, ah, aw, bh, bw):
+        """upSample_kernel + D2D copy (NCT/GeneralizedPatchMatch.cu:546-580, NCT/main.cu:238-250)."""
+        self._check(self.lib.nct_nnf_upsample(self.h, _ptr(ann_half), ah_half, aw_half, _ptr(ann), ah, aw, bh, bw))
+        return ann
+
+    def patchmatch_single(self, a, b, ann, annd, params):
+        """patchmatch_single<<<>>> (NCT/GeneralizedPatchMatch.cu:677-831); a, b L2-normalised HWC."""
+        self._check(self.lib.nct_patchmatch(self.h, _ptr(a), _ptr(b), _ptr(ann), _ptr(annd), params))
+
+    def patchmatch_bidir(self, a, b, ann, annd, bnn, bnnd, params_ab):
+        """Both launches of NCT/main.cu:283-284 fused."""
+        self._check(
+            self.lib.nct_patchmatch_bidir(self.h, _ptr(a), _ptr(b), _ptr(ann), _ptr(annd), _ptr(bnn), _ptr(bnnd), params_ab)
+        )
+
+    def xorwow_table(self, ncols, ndraws):
+        import torch
+        out = torch.empty((ncols, ndraws), dtype=torch.float32, device=f"cuda:{self.gpu_id}")
+        self._check(self.lib.nct_xorwow_table(self.h, _ptr(out), ncols, ndraws))
+        return out
+
+    def count_evals(self, enable=True):
+        self._check(self.lib.nct_patchmatch_count_evals(self.h, 1 if enable else 0))
+
+    def patchmatch_stats(self):
+        st = (_ll * 2)()
+        self._check(self.lib.nct_patchmatch_stats(self.h, st))
+        return int(st[0]), int(st[1])

@@ -1,0 +1,123 @@
+// Context, error reporting and workspace arena of libnct.
+// Replaces the device setup of NCT/main.cu:562-570 (cudaSetDevice/cudaDeviceReset/
+// cudaMemGetInfo) and the per-level cudaMalloc/cudaFree churn of NCT/main.cu:238-326.
+#include "nct_internal.h"
+
+int nct_fail(nct_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->last_error = buf;
+    else fprintf(stderr, "libnct: %s\n", buf);
+    return code;
+}
+
+void *nct_scratch(nct_ctx *ctx, const char *name, size_t bytes)
+{
+    NctBuffer &b = ctx->scratch[name];
+    if (b.bytes >= bytes && b.ptr) return b.ptr;
+    if (b.ptr) {
+        // the old buffer may still be in use by queued work on the stream
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(b.ptr);
+        b.ptr = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    void *p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        nct_fail(ctx, NCT_ERR_NOMEM, "cudaMalloc(%zu) for scratch '%s' failed", want, name);
+        return nullptr;
+    }
+    b.ptr = p;
+    b.bytes = want;
+    return p;
+}
+
+extern "C" {
+
+int nct_version(void) { return 100; }
+
+int nct_create(int gpu_id, nct_ctx **out)
+{
+    if (!out) return NCT_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return nct_fail(nullptr, NCT_ERR_CUDA, "no CUDA device available (%s); libnct has no CPU fallback",
+                        cudaGetErrorString(e));
+    if (gpu_id < 0 || gpu_id >= count)
+        return nct_fail(nullptr, NCT_ERR_ARG, "gpu_id %d out of range (device count %d)", gpu_id, count);
+    if (cudaSetDevice(gpu_id) != cudaSuccess) return nct_fail(nullptr, NCT_ERR_CUDA, "cudaSetDevice(%d) failed", gpu_id);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, gpu_id) != cudaSuccess)
+        return nct_fail(nullptr, NCT_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return nct_fail(nullptr, NCT_ERR_CUDA, "device %d is sm_%d%d; libnct is built for sm_100a only", gpu_id,
+                        prop.major, prop.minor);
+    nct_ctx *ctx = new nct_ctx();
+    ctx->device = gpu_id;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return nct_fail(nullptr, NCT_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    ctx->stream = ctx->own_stream;
+    if (cudaMalloc(&ctx->pm_counters, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return nct_fail(nullptr, NCT_ERR_NOMEM, "cudaMalloc failed");
+    }
+    cudaMemset(ctx->pm_counters, 0, 2 * sizeof(unsigned long long));
+    *out = ctx;
+    return NCT_OK;
+}
+
+// defined by vgg19.cu / pipeline.cu
+void nct_vgg_free(nct_ctx *ctx);
+void nct_pipe_free(nct_ctx *ctx);
+
+int nct_destroy(nct_ctx *ctx)
+{
+    if (!ctx) return NCT_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    nct_pipe_free(ctx);
+    nct_vgg_free(ctx);
+    for (auto &kv : ctx->scratch)
+        if (kv.second.ptr) cudaFree(kv.second.ptr);
+    if (ctx->pm_counters) cudaFree(ctx->pm_counters);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return NCT_OK;
+}
+
+const char *nct_last_error(const nct_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null ctx"; }
+
+int nct_set_stream(nct_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return NCT_ERR_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return NCT_OK;
+}
+
+void *nct_get_stream(const nct_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int nct_synchronize(nct_ctx *ctx)
+{
+    if (!ctx) return NCT_ERR_ARG;
+    NCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NCT_OK;
+}
+
+long long nct_launch_count(const nct_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void nct_reset_launch_count(nct_ctx *ctx)
+{
+    if (ctx) ctx->launches = 0;
+}
+
+}  // extern "C"

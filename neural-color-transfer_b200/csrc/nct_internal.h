@@ -1,0 +1,65 @@
+// Internal definitions shared by the libnct translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/nct.h"
+
+struct NctBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct nct_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    long long launches = 0;
+
+    // named, grow-only device scratch buffers ("workspace arena"): no per-level
+    // cudaMalloc/cudaFree on the hot path (the reference does ~12 per level,
+    // NCT/main.cu:238-257,293-299).
+    std::map<std::string, NctBuffer> scratch;
+
+    // PatchMatch bookkeeping
+    int pm_count_evals = 0;
+    unsigned long long *pm_counters = nullptr;  // device, 2 x u64
+
+    // opaque sub-module states (owned, freed in nct_destroy)
+    struct VggState *vgg = nullptr;
+    struct PipeState *pipe = nullptr;
+};
+
+int nct_fail(nct_ctx *ctx, int code, const char *fmt, ...);
+// returns device pointer of at least `bytes` bytes, stable until a larger request under the same name
+void *nct_scratch(nct_ctx *ctx, const char *name, size_t bytes);
+
+#define NCT_CUDA(ctx, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return nct_fail((ctx), NCT_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,        \
+                            cudaGetErrorString(e__));                                                \
+    } while (0)
+
+#define NCT_CHECK_LAUNCH(ctx)                                                                        \
+    do {                                                                                             \
+        (ctx)->launches++;                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                                        \
+        if (e__ != cudaSuccess)                                                                      \
+            return nct_fail((ctx), NCT_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__,    \
+                            cudaGetErrorString(e__));                                                \
+    } while (0)
+
+#define NCT_REQUIRE(ctx, cond, ...)                                                                  \
+    do {                                                                                             \
+        if (!(cond)) return nct_fail((ctx), NCT_ERR_ARG, __VA_ARGS__);                               \
+    } while (0)
+
+static inline int nct_div_up(int a, int b) { return (a + b - 1) / b; }

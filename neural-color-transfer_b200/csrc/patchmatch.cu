@@ -1,0 +1,538 @@
+// Dense correspondence kernels: NNF init / upsample, XORWOW table, PatchMatch.
+//
+// Replaces init_Ann_kernel, upSample_kernel and patchmatch_single of
+// NCT/GeneralizedPatchMatch.cu:527-580, 677-831 (launched from NCT/main.cu:230-284).
+//
+// Design:
+//   * features are pixel-major (HWC) FP32, so one candidate patch pixel is one contiguous
+//     C*4-byte row: a warp reads it with coalesced LDG.128 (32 lanes x float4 = 512 B / instr);
+//   * one warp per query pixel; the query's own 3x3xC patch lives in registers (C <= 256) for
+//     the whole step, candidates' patches are streamed from L2/HBM with all loads of a
+//     candidate in flight at once; the distance is a 32-lane FMA chain + XOR-shuffle butterfly;
+//   * the reference runs 10 iterations in ONE racy launch; here each (iter, jump) step is a
+//     launch reading the previous step's NNF (double buffered) => deterministic and bit-exact
+//     against oracle/pm_oracle.c.  Random search is fused into the jump==1 step and the initial
+//     distance into the first step, both directions (A->B, B->A) share each launch.
+//   * per-column XORWOW streams are materialised once per call into a small table.
+#include "nct_internal.h"
+#include <cfloat>
+
+namespace {
+
+__host__ __device__ __forceinline__ uint32_t xy_to_int(int x, int y) { return ((uint32_t)y << 12) | (uint32_t)x; }
+__host__ __device__ __forceinline__ int int_to_x(uint32_t v) { return (int)(v & 0xFFFu); }
+__host__ __device__ __forceinline__ int int_to_y(uint32_t v) { return (int)((v >> 12) & 0xFFFu); }
+
+// ------------------------------------------------------------------ NNF init / upsample
+__global__ void nnf_init_kernel(uint32_t *__restrict__ ann, int ah, int aw, int bh, int bw)
+{
+    int ax = blockIdx.x * blockDim.x + threadIdx.x;
+    int ay = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ax < aw && ay < ah) {
+        float fx = __fmul_rn(__fdiv_rn((float)ax, (float)(aw - 1)), (float)(bw - 1));
+        float fy = __fmul_rn(__fdiv_rn((float)ay, (float)(ah - 1)), (float)(bh - 1));
+        int bx = min((int)fx, bw - 1);
+        int by = min((int)fy, bh - 1);
+        ann[ay * aw + ax] = xy_to_int(bx, by);
+    }
+}
+
+__device__ __forceinline__ int clampi(int x, int hi, int lo) { return x > hi ? hi : (x < lo ? lo : x); }
+
+__global__ void nnf_upsample_kernel(const uint32_t *__restrict__ ann_half, int ah_half, int aw_half,
+                                    uint32_t *__restrict__ ann, int ah, int aw, int bh, int bw)
+{
+    int ax = blockIdx.x * blockDim.x + threadIdx.x;
+    int ay = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ax >= aw || ay >= ah) return;
+    float rx = __fdiv_rn((float)aw, (float)aw_half);
+    float ry = __fdiv_rn((float)ah, (float)ah_half);
+    int axh = (int)(__ddiv_rn((double)ax + 0.5, (double)rx));
+    int ayh = (int)(__ddiv_rn((double)ay + 0.5, (double)ry));
+    axh = clampi(axh, aw_half - 1, 0);
+    ayh = clampi(ayh, ah_half - 1, 0);
+    uint32_t v = ann_half[ayh * aw_half + axh];
+    int bxh = int_to_x(v), byh = int_to_y(v);
+    int bx = (int)((double)__fmaf_rn((float)(bxh - axh), rx, (float)ax) + 0.5);
+    int by = (int)((double)__fmaf_rn((float)(byh - ayh), ry, (float)ay) + 0.5);
+    bx = clampi(bx, bw - 1, 0);
+    by = clampi(by, bh - 1, 0);
+    ann[ay * aw + ax] = xy_to_int(bx, by);
+}
+
+// ------------------------------------------------------------------ XORWOW table
+// curand_init(seed = column, 0, 0) + curand_uniform, restated from CUDA's curand_kernel.h
+// (no skip-ahead is needed for subsequence = offset = 0).
+__global__ void xorwow_table_kernel(float *__restrict__ out, int ncols, int ndraws)
+{
+    int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    unsigned long long seed = (unsigned long long)col;
+    uint32_t s0 = ((uint32_t)seed) ^ 0xaad26b49u;
+    uint32_t s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;
+    uint32_t t0 = 1099087573u * s0;
+    uint32_t t1 = 2591861531u * s1;
+    uint32_t d = 6615241u + t1 + t0;
+    uint32_t v0 = 123456789u + t0, v1 = 362436069u ^ t0, v2 = 521288629u + t1, v3 = 88675123u ^ t1,
+             v4 = 5783321u + t0;
+    for (int k = 0; k < ndraws; ++k) {
+        uint32_t t = v0 ^ (v0 >> 2);
+        v0 = v1; v1 = v2; v2 = v3; v3 = v4;
+        v4 = (v4 ^ (v4 << 4)) ^ (t ^ (t << 1));
+        d += 362437u;
+        uint32_t x = v4 + d;
+        out[(size_t)col * ndraws + k] = __fmaf_rn((float)x, 2.3283064e-10f, 2.3283064e-10f / 2.0f);
+    }
+}
+
+// ------------------------------------------------------------------ PatchMatch step
+struct PMDir {
+    const float *a;          // query features   [ah][aw][C]
+    const float *b;          // target features  [bh][bw][C]
+    const uint32_t *nnf_in;  // NNF at the end of the previous step
+    uint32_t *nnf_out;
+    float *nnd;              // own entry only: read + write in place
+    const float *rng;        // [aw][ndraws]
+    int ah, aw, bh, bw;
+    int rs_start, n_mag, ndraws;
+};
+
+struct PMStep {
+    PMDir d[2];
+    int nq0;        // number of queries of direction 0
+    int nq_total;   // queries of both directions
+    int jump;
+    int iter;
+    int first;      // compute the initial distance instead of reading nnd
+    int do_random;  // jump == 1: fused random search
+    unsigned long long *counters;  // nullptr or 2 x u64 {evaluated, reference-semantics}
+};
+
+template <int C>
+struct PMTraits {
+    static constexpr int V = C / 4;                        // float4 vectors per pixel
+    static constexpr int VPL = (V >= 32) ? V / 32 : 1;     // vectors per lane per pixel
+    static constexpr int GROUPS = (V >= 32) ? 1 : 32 / V;  // patch pixels processed side by side
+    static constexpr int PPL = (9 + GROUPS - 1) / GROUPS;  // patch pixels per lane
+    static constexpr bool A_IN_REGS = (C <= 256);
+};
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+__device__ __forceinline__ float butterfly(float acc)
+{
+    acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 16));
+    acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 8));
+    acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+    acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+    acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+    return acc;
+}
+
+__device__ __forceinline__ float fma4(float4 a, float4 b, float acc)
+{
+    acc = __fmaf_rn(a.x, b.x, acc);
+    acc = __fmaf_rn(a.y, b.y, acc);
+    acc = __fmaf_rn(a.z, b.z, acc);
+    acc = __fmaf_rn(a.w, b.w, acc);
+    return acc;
+}
+
+// 9-bit mask of patch pixels (dy outer, dx inner) that lie inside a h x w image around (x, y)
+__device__ __forceinline__ unsigned patch_mask(int x, int y, int w, int h)
+{
+    unsigned mx = (x > 0 ? 1u : 0u) | 2u | (x + 1 < w ? 4u : 0u);
+    unsigned m = 0;
+    if (y > 0) m |= mx;
+    m |= mx << 3;
+    if (y + 1 < h) m |= mx << 6;
+    return m;
+}
+
+template <int C>
+struct QueryPatch {
+    using T = PMTraits<C>;
+    float4 a[T::A_IN_REGS ? T::PPL * T::VPL : 1];
+    const float *a_base;  // address of the query pixel's own feature row (+ lane offset)
+    int aw;
+    unsigned amask;
+};
+
+// loads the query patch into registers (or records where to find it)
+template <int C>
+__device__ __forceinline__ void load_query(QueryPatch<C> &q, const float *__restrict__ a, int ax, int ay, int aw,
+                                           int ah, int lane)
+{
+    using T = PMTraits<C>;
+    q.aw = aw;
+    q.amask = patch_mask(ax, ay, aw, ah);
+    const int j = (T::GROUPS == 1) ? lane : (lane % T::V);
+    q.a_base = a + ((size_t)ay * aw + ax) * C + j * 4;
+    if (T::A_IN_REGS) {
+        const int g = (T::GROUPS == 1) ? 0 : lane / T::V;
+#pragma unroll
+        for (int i = 0; i < T::PPL; ++i) {
+            const int pi = i * T::GROUPS + g;
+            const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+            const bool ok = pi < 9 && ((q.amask >> pi) & 1u);
+#pragma unroll
+            for (int k = 0; k < T::VPL; ++k) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) v = ldg4(q.a_base + ((ptrdiff_t)dy * aw + dx) * C + k * 128);
+                q.a[i * T::VPL + k] = v;
+            }
+        }
+    }
+}
+
+// canonical-order patch distance (oracle decision D2); all lanes return the same value
+template <int C>
+__device__ __forceinline__ float eval_dist(const QueryPatch<C> &q, const float *__restrict__ b, int bx, int by,
+                                           int bw, int bh, int lane)
+{
+    using T = PMTraits<C>;
+    const unsigned valid = q.amask & patch_mask(bx, by, bw, bh);
+    const int j = (T::GROUPS == 1) ? lane : (lane % T::V);
+    const int g = (T::GROUPS == 1) ? 0 : lane / T::V;
+    const float *b_base = b + ((size_t)by * bw + bx) * C + j * 4;
+    float4 bv[T::PPL * T::VPL];
+#pragma unroll
+    for (int i = 0; i < T::PPL; ++i) {
+        const int pi = i * T::GROUPS + g;
+        const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+        const bool ok = pi < 9 && ((valid >> pi) & 1u);
+#pragma unroll
+        for (int k = 0; k < T::VPL; ++k) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) v = ldg4(b_base + ((ptrdiff_t)dy * bw + dx) * C + k * 128);
+            bv[i * T::VPL + k] = v;
+        }
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < T::PPL; ++i) {
+        const int pi = i * T::GROUPS + g;
+        const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+        const bool ok = pi < 9 && ((valid >> pi) & 1u);
+        if (ok) {
+#pragma unroll
+            for (int k = 0; k < T::VPL; ++k) {
+                float4 av;
+                if (T::A_IN_REGS) av = q.a[i * T::VPL + k];
+                else av = ldg4(q.a_base + ((ptrdiff_t)dy * q.aw + dx) * C + k * 128);
+                acc = fma4(av, bv[i * T::VPL + k], acc);
+            }
+        }
+    }
+    acc = butterfly(acc);
+    const int n = __popc(valid);
+    return __fdiv_rn(-acc, (float)n);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) pm_step_kernel(const PMStep s)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (warp_global >= s.nq_total) return;
+    const int dsel = warp_global >= s.nq0 ? 1 : 0;
+    const PMDir &D = s.d[dsel];
+    const int p = warp_global - (dsel ? s.nq0 : 0);
+    const int aw = D.aw, ah = D.ah, bw = D.bw, bh = D.bh;
+    const int ax = p % aw, ay = p / aw;
+
+    QueryPatch<C> q;
+    load_query<C>(q, D.a, ax, ay, aw, ah, lane);
+
+    const uint32_t v0 = D.nnf_in[p];
+    int xbest = int_to_x(v0), ybest = int_to_y(v0);
+    float dbest;
+    unsigned n_eval = 0, n_ref = 0;
+    if (s.first) {
+        dbest = eval_dist<C>(q, D.b, xbest, ybest, bw, bh, lane);
+        n_eval++;
+        n_ref++;
+    } else {
+        dbest = D.nnd[p];
+    }
+
+    // ---- propagation: L, R, U, D candidates from the previous step's NNF
+    const int jump = s.jump;
+    uint32_t cand[4];
+    bool use[4];
+    {
+        const int qx[4] = {ax - jump, ax + jump, ax, ax};
+        const int qy[4] = {ay, ay, ay - jump, ay + jump};
+        const int sx[4] = {jump, -jump, 0, 0};
+        const int sy[4] = {0, 0, jump, -jump};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            use[k] = false;
+            cand[k] = 0;
+            if (qx[k] >= 0 && qx[k] < aw && qy[k] >= 0 && qy[k] < ah) {
+                uint32_t vp = D.nnf_in[qy[k] * aw + qx[k]];
+                int xp = int_to_x(vp) + sx[k], yp = int_to_y(vp) + sy[k];
+                if (yp >= 0 && yp < bh && xp >= 0 && xp < bw) {
+                    n_ref++;
+                    cand[k] = xy_to_int(xp, yp);
+                    bool dup = (cand[k] == v0);
+#pragma unroll
+                    for (int t = 0; t < k; ++t) dup = dup || (use[t] && cand[t] == cand[k]);
+                    use[k] = !dup;
+                }
+            }
+        }
+    }
+    float dc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        dc[k] = 0.f;
+        if (use[k]) {
+            dc[k] = eval_dist<C>(q, D.b, int_to_x(cand[k]), int_to_y(cand[k]), bw, bh, lane);
+            n_eval++;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (use[k] && dc[k] < dbest) {
+            dbest = dc[k];
+            xbest = int_to_x(cand[k]);
+            ybest = int_to_y(cand[k]);
+        }
+    }
+
+    // ---- random search around the current best (fused into the jump == 1 step)
+    if (s.do_random) {
+        const float *u = D.rng + (size_t)ax * D.ndraws + (size_t)s.iter * 2 * D.n_mag;
+        int m = 0;
+        for (int mag = D.rs_start; mag >= 1; mag /= 2, ++m) {
+            const int xmin = max(xbest - mag, 0), xmax = min(xbest + mag + 1, bw);
+            const int ymin = max(ybest - mag, 0), ymax = min(ybest + mag + 1, bh);
+            const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
+            const int xp = xmin + (int)(__fmul_rn(u1, (float)(xmax - xmin))) % (xmax - xmin);
+            const int yp = ymin + (int)(__fmul_rn(u2, (float)(ymax - ymin))) % (ymax - ymin);
+            n_ref++;
+            if (xp == xbest && yp == ybest) continue;
+            n_eval++;
+            const float d = eval_dist<C>(q, D.b, xp, yp, bw, bh, lane);
+            if (__fadd_rn(d, FLT_MIN) < dbest) {
+                dbest = d;
+                xbest = xp;
+                ybest = yp;
+            }
+        }
+    }
+
+    if (lane == 0) {
+        D.nnf_out[p] = xy_to_int(xbest, ybest);
+        D.nnd[p] = dbest;
+        if (s.counters) {
+            atomicAdd(&s.counters[0], (unsigned long long)n_eval);
+            atomicAdd(&s.counters[1], (unsigned long long)n_ref);
+        }
+    }
+}
+
+// iters == 0: only the initial distance (NCT/GeneralizedPatchMatch.cu:710-712)
+template <int C>
+__global__ void __launch_bounds__(256) pm_init_dist_kernel(const PMStep s)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (warp_global >= s.nq_total) return;
+    const int dsel = warp_global >= s.nq0 ? 1 : 0;
+    const PMDir &D = s.d[dsel];
+    const int p = warp_global - (dsel ? s.nq0 : 0);
+    const int ax = p % D.aw, ay = p / D.aw;
+    QueryPatch<C> q;
+    load_query<C>(q, D.a, ax, ay, D.aw, D.ah, lane);
+    const uint32_t v0 = D.nnf_in[p];
+    float d = eval_dist<C>(q, D.b, int_to_x(v0), int_to_y(v0), D.bw, D.bh, lane);
+    if (lane == 0) D.nnd[p] = d;
+}
+
+template <int C>
+int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1, int ndir)
+{
+    const int warps_per_block = 8;
+    const int blocks = nct_div_up(s.nq_total, warps_per_block);
+    s.counters = ctx->pm_count_evals ? ctx->pm_counters : nullptr;
+    if (iters == 0) {
+        pm_init_dist_kernel<C><<<blocks, 256, 0, ctx->stream>>>(s);
+        NCT_CHECK_LAUNCH(ctx);
+        return NCT_OK;
+    }
+    uint32_t *user[2] = {s.d[0].nnf_out, ndir > 1 ? s.d[1].nnf_out : nullptr};
+    uint32_t *tmp[2] = {tmp0, tmp1};
+    int step = 0;
+    for (int iter = 0; iter < iters; ++iter)
+        for (int jump = 8; jump > 0; jump /= 2, ++step) {
+            s.iter = iter;
+            s.jump = jump;
+            s.first = (step == 0);
+            s.do_random = (jump == 1);
+            for (int d = 0; d < ndir; ++d) {
+                // even steps read the caller's buffer and write scratch; odd steps the reverse.
+                // 4*iters steps is even, so the final NNF lands in the caller's buffer.
+                s.d[d].nnf_in = (step & 1) ? tmp[d] : user[d];
+                s.d[d].nnf_out = (step & 1) ? user[d] : tmp[d];
+            }
+            pm_step_kernel<C><<<blocks, 256, 0, ctx->stream>>>(s);
+            NCT_CHECK_LAUNCH(ctx);
+        }
+    return NCT_OK;
+}
+
+int fill_dir(nct_ctx *ctx, PMDir &D, const float *a, const float *b, uint32_t *ann, float *annd, int ah, int aw,
+             int bh, int bw, int iters, int rs_max, const char *rng_name)
+{
+    D.a = a;
+    D.b = b;
+    D.nnf_in = ann;
+    D.nnf_out = ann;
+    D.nnd = annd;
+    D.ah = ah; D.aw = aw; D.bh = bh; D.bw = bw;
+    int rs = rs_max;
+    if (rs > (bw > bh ? bw : bh)) rs = (bw > bh ? bw : bh);
+    D.rs_start = rs;
+    D.n_mag = 0;
+    for (int mag = rs; mag >= 1; mag /= 2) D.n_mag++;
+    D.ndraws = 2 * D.n_mag * iters;
+    D.rng = nullptr;
+    if (D.ndraws > 0) {
+        float *tab = (float *)nct_scratch(ctx, rng_name, sizeof(float) * (size_t)aw * D.ndraws);
+        if (!tab) return NCT_ERR_NOMEM;
+        xorwow_table_kernel<<<nct_div_up(aw, 128), 128, 0, ctx->stream>>>(tab, aw, D.ndraws);
+        NCT_CHECK_LAUNCH(ctx);
+        D.rng = tab;
+    }
+    return NCT_OK;
+}
+
+int check_params(nct_ctx *ctx, const int *p)
+{
+    NCT_REQUIRE(ctx, p != nullptr, "params is null");
+    const int C = p[0];
+    NCT_REQUIRE(ctx, C == 16 || C == 32 || C == 64 || (C >= 128 && C % 128 == 0 && C <= 512),
+                "unsupported channel count %d (16, 32, 64, 128, 256, 384, 512)", C);
+    NCT_REQUIRE(ctx, C != 384, "unsupported channel count 384");
+    NCT_REQUIRE(ctx, p[1] > 0 && p[2] > 0 && p[3] > 0 && p[4] > 0 && p[1] <= 4096 && p[2] <= 4096 && p[3] <= 4096 &&
+                         p[4] <= 4096,
+                "image sides must be in [1, 4096] (12-bit NNF packing)");
+    NCT_REQUIRE(ctx, p[5] == 3, "patch size %d unsupported (reference uses 3, CT/Config.h:70)", p[5]);
+    NCT_REQUIRE(ctx, p[6] >= 0 && p[6] <= 64, "iters %d out of range", p[6]);
+    NCT_REQUIRE(ctx, p[7] >= 1, "rs_max must be >= 1");
+    NCT_REQUIRE(ctx, p[8] == 0, "flag_constraint must be 0 (the reference never enables it, NCT/main.cu:66)");
+    return NCT_OK;
+}
+
+int dispatch_pm(nct_ctx *ctx, int C, PMStep &s, int iters, uint32_t *t0, uint32_t *t1, int ndir)
+{
+    switch (C) {
+    case 16: return launch_pm<16>(ctx, s, iters, t0, t1, ndir);
+    case 32: return launch_pm<32>(ctx, s, iters, t0, t1, ndir);
+    case 64: return launch_pm<64>(ctx, s, iters, t0, t1, ndir);
+    case 128: return launch_pm<128>(ctx, s, iters, t0, t1, ndir);
+    case 256: return launch_pm<256>(ctx, s, iters, t0, t1, ndir);
+    case 512: return launch_pm<512>(ctx, s, iters, t0, t1, ndir);
+    }
+    return nct_fail(ctx, NCT_ERR_ARG, "unsupported channel count %d", C);
+}
+
+}  // namespace
+
+extern "C" {
+
+int nct_nnf_init(nct_ctx *ctx, uint32_t *ann_dev, int ah, int aw, int bh, int bw)
+{
+    if (!ctx) return NCT_ERR_ARG;
+    NCT_REQUIRE(ctx, ann_dev && ah > 0 && aw > 0 && bh > 0 && bw > 0, "bad arguments");
+    dim3 block(32, 8), grid(nct_div_up(aw, 32), nct_div_up(ah, 8));
+    nnf_init_kernel<<<grid, block, 0, ctx->stream>>>(ann_dev, ah, aw, bh, bw);
+    NCT_CHECK_LAUNCH(ctx);
+    return NCT_OK;
+}
+
+int nct_nnf_upsample(nct_ctx *ctx, const uint32_t *ann_half_dev, int ah_half, int aw_half, uint32_t *ann_dev, int ah,
+                     int aw, int bh, int bw)
+{
+    if (!ctx) return NCT_ERR_ARG;
+    NCT_REQUIRE(ctx, ann_half_dev && ann_dev && ann_half_dev != ann_dev, "bad / aliased NNF buffers");
+    NCT_REQUIRE(ctx, ah_half > 0 && aw_half > 0 && ah > 0 && aw > 0 && bh > 0 && bw > 0, "bad sizes");
+    dim3 block(32, 8), grid(nct_div_up(aw, 32), nct_div_up(ah, 8));
+    nnf_upsample_kernel<<<grid, block, 0, ctx->stream>>>(ann_half_dev, ah_half, aw_half, ann_dev, ah, aw, bh, bw);
+    NCT_CHECK_LAUNCH(ctx);
+    return NCT_OK;
+}
+
+int nct_xorwow_table(nct_ctx *ctx, float *out_dev, int ncols, int ndraws)
+{
+    if (!ctx) return NCT_ERR_ARG;
+    NCT_REQUIRE(ctx, out_dev && ncols > 0 && ndraws > 0, "bad arguments");
+    xorwow_table_kernel<<<nct_div_up(ncols, 128), 128, 0, ctx->stream>>>(out_dev, ncols, ndraws);
+    NCT_CHECK_LAUNCH(ctx);
+    return NCT_OK;
+}
+
+int nct_patchmatch(nct_ctx *ctx, const float *a, const float *b, uint32_t *ann, float *annd, const int params[11])
+{
+    if (!ctx) return NCT_ERR_ARG;
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    NCT_REQUIRE(ctx, a && b && ann && annd, "null device pointer");
+    const int C = params[0], ah = params[1], aw = params[2], bh = params[3], bw = params[4];
+    const int iters = params[6], rs_max = params[7];
+    PMStep s{};
+    rc = fill_dir(ctx, s.d[0], a, b, ann, annd, ah, aw, bh, bw, iters, rs_max, "pm_rng0");
+    if (rc) return rc;
+    s.d[1] = s.d[0];
+    s.nq0 = ah * aw;
+    s.nq_total = s.nq0;
+    uint32_t *t0 = (uint32_t *)nct_scratch(ctx, "pm_nnf_tmp0", sizeof(uint32_t) * (size_t)ah * aw);
+    if (!t0) return NCT_ERR_NOMEM;
+    if (ctx->pm_count_evals) NCT_CUDA(ctx, cudaMemsetAsync(ctx->pm_counters, 0, 16, ctx->stream));
+    return dispatch_pm(ctx, C, s, iters, t0, nullptr, 1);
+}
+
+int nct_patchmatch_bidir(nct_ctx *ctx, const float *a, const float *b, uint32_t *ann, float *annd, uint32_t *bnn,
+                         float *bnnd, const int params[11])
+{
+    if (!ctx) return NCT_ERR_ARG;
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    NCT_REQUIRE(ctx, a && b && ann && annd && bnn && bnnd, "null device pointer");
+    const int C = params[0], ah = params[1], aw = params[2], bh = params[3], bw = params[4];
+    const int iters = params[6], rs_max = params[7];
+    PMStep s{};
+    rc = fill_dir(ctx, s.d[0], a, b, ann, annd, ah, aw, bh, bw, iters, rs_max, "pm_rng0");
+    if (rc) return rc;
+    rc = fill_dir(ctx, s.d[1], b, a, bnn, bnnd, bh, bw, ah, aw, iters, rs_max, "pm_rng1");
+    if (rc) return rc;
+    s.nq0 = ah * aw;
+    s.nq_total = ah * aw + bh * bw;
+    uint32_t *t0 = (uint32_t *)nct_scratch(ctx, "pm_nnf_tmp0", sizeof(uint32_t) * (size_t)ah * aw);
+    uint32_t *t1 = (uint32_t *)nct_scratch(ctx, "pm_nnf_tmp1", sizeof(uint32_t) * (size_t)bh * bw);
+    if (!t0 || !t1) return NCT_ERR_NOMEM;
+    if (ctx->pm_count_evals) NCT_CUDA(ctx, cudaMemsetAsync(ctx->pm_counters, 0, 16, ctx->stream));
+    return dispatch_pm(ctx, C, s, iters, t0, t1, 2);
+}
+
+int nct_patchmatch_count_evals(nct_ctx *ctx, int enable)
+{
+    if (!ctx) return NCT_ERR_ARG;
+    ctx->pm_count_evals = enable ? 1 : 0;
+    return NCT_OK;
+}
+
+int nct_patchmatch_stats(nct_ctx *ctx, long long stats[2])
+{
+    if (!ctx || !stats) return NCT_ERR_ARG;
+    unsigned long long h[2];
+    NCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NCT_CUDA(ctx, cudaMemcpy(h, ctx->pm_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    stats[0] = (long long)h[0];
+    stats[1] = (long long)h[1];
+    return NCT_OK;
+}
+
+}  // extern "C"

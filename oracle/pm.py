@@ -1,0 +1,140 @@
+"""ctypes wrappers over oracle/liboracle_pm.so (built by oracle/Makefile from pm_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liboracle_pm.so")
+_lib = None
+
+_fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_up = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False):
+    """Compile the C restatement (gcc). Building the checker is not using it."""
+    src = os.path.join(_HERE, "pm_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle_pm.so"], stdout=subprocess.DEVNULL)
+    return _LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.orc_xorwow_uniform_table.argtypes = [C.c_int, C.c_int, _fp]
+        L.orc_xorwow_raw.argtypes = [C.c_ulonglong, C.c_int, _up]
+        L.orc_nnf_init.argtypes = [C.c_int] * 4 + [_up]
+        L.orc_nnf_upsample.argtypes = [_up] + [C.c_int] * 6 + [_up]
+        L.orc_dist_canon.argtypes = [_fp, _fp] + [C.c_int] * 9
+        L.orc_dist_canon.restype = C.c_float
+        L.orc_dist_ref_chw.argtypes = [_fp, _fp] + [C.c_int] * 10 + [C.c_float, C.c_int]
+        L.orc_dist_ref_chw.restype = C.c_float
+        L.orc_l2norm_hwc.argtypes = [_fp, _fp, C.c_int, C.c_int]
+        L.orc_chw_to_hwc.argtypes = [_fp, _fp, C.c_int, C.c_int]
+        L.orc_patchmatch.argtypes = [_fp, _fp, _up, _fp, _ip, _lp]
+        L.orc_patchmatch.restype = C.c_int
+        L.orc_patchmatch_ref_serial.argtypes = [_fp, _fp, _up, _fp, _ip]
+        L.orc_patchmatch_ref_serial.restype = C.c_int
+        L.orc_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def make_params(Cn, ah, aw, bh, bw, iters=10, rs_max=32, patch=3):
+    """NCT/main.cu:204-214"""
+    return np.array([Cn, ah, aw, bh, bw, patch, iters, rs_max, 0, 10, 1], dtype=np.int32)
+
+
+def xorwow_uniform_table(ncols, ndraws):
+    out = np.empty((ncols, ndraws), np.float32)
+    lib().orc_xorwow_uniform_table(ncols, ndraws, out)
+    return out
+
+
+def xorwow_raw(seed, ndraws):
+    out = np.empty(ndraws, np.uint32)
+    lib().orc_xorwow_raw(seed, ndraws, out)
+    return out
+
+
+def nnf_init(ah, aw, bh, bw):
+    ann = np.empty(ah * aw, np.uint32)
+    lib().orc_nnf_init(ah, aw, bh, bw, ann)
+    return ann
+
+
+def nnf_upsample(ann_half, ah_half, aw_half, ah, aw, bh, bw):
+    ann = np.empty(ah * aw, np.uint32)
+    lib().orc_nnf_upsample(np.ascontiguousarray(ann_half, np.uint32), ah_half, aw_half, ah, aw, bh, bw, ann)
+    return ann
+
+
+def l2norm_hwc(x):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(x)
+    lib().orc_l2norm_hwc(x, out, x.shape[0] * x.shape[1], x.shape[2])
+    return out
+
+
+def chw_to_hwc(x):
+    x = np.ascontiguousarray(x, np.float32)
+    Cn, H, W = x.shape
+    out = np.empty((H, W, Cn), np.float32)
+    lib().orc_chw_to_hwc(x, out, Cn, H * W)
+    return out
+
+
+def dist_canon(a, b, ax, ay, bx, by):
+    ah, aw, Cn = a.shape
+    bh, bw, _ = b.shape
+    return float(lib().orc_dist_canon(a, b, Cn, ah, aw, bh, bw, ax, ay, bx, by))
+
+
+def dist_ref_chw(a_chw, b_chw, ax, ay, bx, by, cutoff=float(2**31), use_fma=1):
+    Cn, ah, aw = a_chw.shape
+    _, bh, bw = b_chw.shape
+    return float(lib().orc_dist_ref_chw(a_chw, b_chw, Cn, ah, aw, bh, bw, ax, ay, bx, by, 3, cutoff, use_fma))
+
+
+def patchmatch(a_hwc, b_hwc, ann, params):
+    """Deterministic PatchMatch (decisions D1-D3). Returns (ann, annd, (evals_ref, evals_dedup))."""
+    a = np.ascontiguousarray(a_hwc, np.float32)
+    b = np.ascontiguousarray(b_hwc, np.float32)
+    ann = np.array(ann, dtype=np.uint32, copy=True).ravel()
+    annd = np.empty(ann.shape[0], np.float32)
+    stats = np.zeros(2, np.int64)
+    rc = lib().orc_patchmatch(a, b, ann, annd, np.ascontiguousarray(params, np.int32), stats)
+    if rc != 0:
+        raise ValueError(f"orc_patchmatch: unsupported parameters ({rc})")
+    return ann, annd, (int(stats[0]), int(stats[1]))
+
+
+def patchmatch_ref_serial(a_chw, b_chw, ann, params):
+    """Reference-semantics in-place PatchMatch in the reference's layout / summation order."""
+    a = np.ascontiguousarray(a_chw, np.float32)
+    b = np.ascontiguousarray(b_chw, np.float32)
+    ann = np.array(ann, dtype=np.uint32, copy=True).ravel()
+    annd = np.empty(ann.shape[0], np.float32)
+    lib().orc_patchmatch_ref_serial(a, b, ann, annd, np.ascontiguousarray(params, np.int32))
+    return ann, annd
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
+
+
+def unpack(ann):
+    ann = np.asarray(ann, np.uint32)
+    return (ann & 0xFFF).astype(np.int32), ((ann >> 12) & 0xFFF).astype(np.int32)
