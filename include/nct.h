@@ -106,6 +106,25 @@ int nct_patchmatch_stats(nct_ctx *ctx, long long stats[2]);
 /* enable (1) / disable (0) evaluation counting inside the PatchMatch kernels */
 int nct_patchmatch_count_evals(nct_ctx *ctx, int enable);
 
+/* ---------------------------------------------------------------- BDS votes */
+
+/* Replaces the host function reconstruct_bds(a, b, ann, bnn, patch_w=3, wCohen, wComplete),
+ * NCT/GeneralizedPatchMatch.cu:122-235 (called at NCT/main.cu:291 after four D2H copies):
+ * BDS-voted B colours in A's layout.  8-bit BGR images (H x W x 3, device), out has A's size.
+ * Bit-exact vs the oracle (integer sums, IEEE double divide, truncating store). */
+int nct_reconstruct_bds(nct_ctx *ctx, const uint8_t *a_bgr_dev, const uint8_t *b_bgr_dev,
+                        const uint32_t *ann_dev, const uint32_t *bnn_dev, int ah, int aw, int bh, int bw,
+                        double w_cohen, double w_complete, uint8_t *out_bgr_dev);
+
+/* Replaces avg_vote_bds_a + avg_vote_bds_b + avg_vote_bds (NCT/GeneralizedPatchMatch.cu:1074-1202),
+ * norm() of the voted volume and feature_distance (:833-855), i.e. NCT/main.cu:297-318:
+ * err[p] = -< c_norm[p], normalise(BDS vote of s_raw)[p] >.  c_norm: L2-normalised A features,
+ * s_raw: UN-normalised B features, both HWC.  vote_out_dev may be NULL; if given it receives the
+ * voted (weight-divided, un-normalised) features in A's layout (HWC). */
+int nct_bds_feature_error(nct_ctx *ctx, const float *c_norm_hwc_dev, const float *s_raw_hwc_dev,
+                          const uint32_t *ann_dev, const uint32_t *bnn_dev, int C, int ah, int aw, int bh, int bw,
+                          float w_cohen, float w_complete, float *err_dev, float *vote_out_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,8 @@ ABI = {
     "nct_xorwow_table": (_i, [c_ctx_p, _p, _i, _i]),
     "nct_patchmatch_stats": (_i, [c_ctx_p, C.POINTER(_ll)]),
     "nct_patchmatch_count_evals": (_i, [c_ctx_p, _i]),
+    "nct_reconstruct_bds": (_i, [c_ctx_p, _p, _p, _p, _p, _i, _i, _i, _i, _d, _d, _p]),
+    "nct_bds_feature_error": (_i, [c_ctx_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p]),
 }
 
 _lib = None
@@ -198,3 +200,25 @@ class Context:
         st = (_ll * 2)()
         self._check(self.lib.nct_patchmatch_stats(self.h, st))
         return int(st[0]), int(st[1])
+
+    # -- BDS votes
+    def reconstruct_bds(self, a_img, b_img, ann, bnn, w_cohen=1.0, w_complete=2.0):
+        """reconstruct_bds (NCT/GeneralizedPatchMatch.cu:122-235); uint8 BGR cuda tensors (H, W, 3)."""
+        import torch
+        ah, aw, _ = a_img.shape
+        bh, bw, _ = b_img.shape
+        out = torch.empty((ah, aw, 3), dtype=torch.uint8, device=a_img.device)
+        self._check(self.lib.nct_reconstruct_bds(self.h, _ptr(a_img), _ptr(b_img), _ptr(ann), _ptr(bnn), ah, aw, bh, bw,
+                                                 float(w_cohen), float(w_complete), _ptr(out)))
+        return out
+
+    def bds_feature_error(self, c_norm, s_raw, ann, bnn, w_cohen=1.0, w_complete=2.0, want_vote=False):
+        """avg_vote_bds_a/_b/avg_vote_bds + norm + feature_distance (NCT/main.cu:297-318)."""
+        import torch
+        ah, aw, Cn = c_norm.shape
+        bh, bw, _ = s_raw.shape
+        err = torch.empty(ah * aw, dtype=torch.float32, device=c_norm.device)
+        vote = torch.empty((ah, aw, Cn), dtype=torch.float32, device=c_norm.device) if want_vote else None
+        self._check(self.lib.nct_bds_feature_error(self.h, _ptr(c_norm), _ptr(s_raw), _ptr(ann), _ptr(bnn), Cn, ah, aw, bh,
+                                                   bw, float(w_cohen), float(w_complete), _ptr(err), _ptr(vote)))
+        return (err, vote) if want_vote else err

@@ -22,8 +22,8 @@ _lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 
 def build(force: bool = False):
     """Compile the C restatement (gcc). Building the checker is not using it."""
-    src = os.path.join(_HERE, "pm_oracle.c")
-    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("pm_oracle.c", "bds_oracle.c")]
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle_pm.so"], stdout=subprocess.DEVNULL)
     return _LIB
 
@@ -48,6 +48,9 @@ def lib():
         L.orc_patchmatch_ref_serial.argtypes = [_fp, _fp, _up, _fp, _ip]
         L.orc_patchmatch_ref_serial.restype = C.c_int
         L.orc_num_threads.restype = C.c_int
+        _bp = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+        L.orc_reconstruct_bds.argtypes = [_bp, _bp, _up, _up] + [C.c_int] * 4 + [C.c_double, C.c_double, _bp]
+        L.orc_bds_feature_error.argtypes = [_fp, _fp, _up, _up] + [C.c_int] * 5 + [C.c_float, C.c_float, C.c_int, _fp, C.c_void_p]
         _lib = L
     return _lib
 
@@ -138,3 +141,30 @@ def num_threads():
 def unpack(ann):
     ann = np.asarray(ann, np.uint32)
     return (ann & 0xFFF).astype(np.int32), ((ann >> 12) & 0xFFF).astype(np.int32)
+
+
+def reconstruct_bds(a_img, b_img, ann, bnn, w_cohen=1.0, w_complete=2.0):
+    """reconstruct_bds, NCT/GeneralizedPatchMatch.cu:122-235 (uint8 BGR HxWx3)."""
+    a_img = np.ascontiguousarray(a_img, np.uint8)
+    b_img = np.ascontiguousarray(b_img, np.uint8)
+    ah, aw, _ = a_img.shape
+    bh, bw, _ = b_img.shape
+    out = np.empty((ah, aw, 3), np.uint8)
+    lib().orc_reconstruct_bds(a_img, b_img, np.ascontiguousarray(ann, np.uint32), np.ascontiguousarray(bnn, np.uint32),
+                              ah, aw, bh, bw, float(w_cohen), float(w_complete), out)
+    return out
+
+
+def bds_feature_error(c_norm, s_raw, ann, bnn, w_cohen=1.0, w_complete=2.0, mode=0, want_vote=False):
+    """avg_vote_bds_a/_b/avg_vote_bds + norm + feature_distance (NCT/main.cu:297-318).
+    mode 0 = canonical reduction order (GPU parity target), 1 = the reference's sequential order."""
+    c_norm = np.ascontiguousarray(c_norm, np.float32)
+    s_raw = np.ascontiguousarray(s_raw, np.float32)
+    ah, aw, Cn = c_norm.shape
+    bh, bw, _ = s_raw.shape
+    err = np.empty(ah * aw, np.float32)
+    vote = np.empty((ah, aw, Cn), np.float32) if want_vote else None
+    lib().orc_bds_feature_error(c_norm, s_raw, np.ascontiguousarray(ann, np.uint32), np.ascontiguousarray(bnn, np.uint32),
+                                Cn, ah, aw, bh, bw, float(w_cohen), float(w_complete), mode, err,
+                                vote.ctypes.data if want_vote else None)
+    return (err, vote) if want_vote else err
