@@ -125,6 +125,56 @@ int nct_bds_feature_error(nct_ctx *ctx, const float *c_norm_hwc_dev, const float
                           const uint32_t *ann_dev, const uint32_t *bnn_dev, int C, int ah, int aw, int bh, int bw,
                           float w_cohen, float w_complete, float *err_dev, float *vote_out_dev);
 
+/* ---------------------------------------------------------------- colour space / resize
+ * OpenCV 2.4.10 arithmetic (third-party, not in the reference tree), restated bit-exactly
+ * (verified against cv2's plain C++ paths over all 2^24 colours).  8-bit images are H x W x 3. */
+
+/* cvtColor(src, dst, CV_BGR2Lab) on 8UC3: NCT/main.cu:352,371; CT/ColorTransfer.h:58 */
+int nct_bgr2lab_u8(nct_ctx *ctx, const uint8_t *bgr_dev, uint8_t *lab_dev, int npix);
+/* cvtColor(src, dst, CV_Lab2BGR) on 8UC3: CT/ColorTransfer.cpp:1469 */
+int nct_lab2bgr_u8(nct_ctx *ctx, const uint8_t *lab_dev, uint8_t *bgr_dev, int npix);
+/* resize(src, dst, Size(dw, dh), 0, 0, CV_INTER_LINEAR) on 8UC3: NCT/main.cu:106-107, 509, 521 */
+int nct_resize_linear_u8c3(nct_ctx *ctx, const uint8_t *src_dev, int sh, int sw, uint8_t *dst_dev, int dh, int dw);
+/* the same on 64FC3: CT/ColorTransfer.cpp:462-463 */
+int nct_resize_linear_f64c3(nct_ctx *ctx, const double *src_dev, int sh, int sw, double *dst_dev, int dh, int dw);
+
+/* ---------------------------------------------------------------- colour fit (ColorTransfer) */
+
+/* build_accumTable_downsample x2 + the local fit loop of transfer_color_downsample
+ * (CT/ColorTransfer.cpp:425-455, 1194-1265): a = sigma_S / (sigma_C + eps), b = (mu_S - mu_C a)/255 from the
+ * clipped 3x3 window of the 8-bit Lab images.  a_dev / b_dev: h*w*3 doubles (Vec3d layout). */
+int nct_local_fit(nct_ctx *ctx, const uint8_t *cnt_lab_dev, const uint8_t *stl_lab_dev, int h, int w, double eps,
+                  double *a_dev, double *b_dev);
+
+/* m_weight = max(1 - (err - min)/(max - min), 1e-6): CT/ColorTransfer.cpp:1302-1340 */
+int nct_confidence_weights(nct_ctx *ctx, const float *err_dev, int n, double *weight_dev);
+
+/* solve_nonlocal_downsample_gpu_gradient + solve_ls_cg_gpu x3 (CT/ColorTransfer.cpp:548-949,
+ * CT/SparseSolver_GPU.cu:3-198), matrix-free.  a/b in: local fit (start vector), out: refined.  knn_id_dev:
+ * [h*w][8] int pixel ids (-1 = none); knn_w_dev: [h*w][8] NN.w values.  iters_out (host, may be NULL; passing it
+ * synchronises) receives the CG iterations per channel. */
+int nct_solve_nonlocal(nct_ctx *ctx, double *a_dev, double *b_dev, const double *weight_dev,
+                       const uint8_t *cnt_lab_dev, const uint8_t *stl_lab_dev, const int *knn_id_dev,
+                       const double *knn_w_dev, int h, int w, int layer, double local_weight, double alpha,
+                       double nonlocal_weight, int knum, double d_weight, int iters_out[3]);
+
+/* upsample_color_coefficients_bilinear (CT/ColorTransfer.cpp:457-490): level -> full size + roughness map */
+int nct_upsample_coefficients(nct_ctx *ctx, const double *a_lvl_dev, const double *b_lvl_dev, int h, int w,
+                              const uint8_t *cnt_lab_full_dev, int H, int W, double *a_full_dev, double *b_full_dev,
+                              double *rough_dev);
+
+/* solve_WLS_roughness_cpu + solve_direct_cpu (CT/ColorTransfer.cpp:951-1125, CT/SparseSolver_CPU.cpp:104-286):
+ * (diag(rough) + L_g) x = diag(rough) x0 for the six maps, in place.  rel_tol <= 0 -> 1e-10, max_iters <= 0 -> default.
+ * Synchronises the stream (the iteration count is data dependent). */
+int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *rough_dev, const uint8_t *cnt_lab_full_dev,
+                  int H, int W, double lam, double alpha, double rel_tol, int max_iters, int *iters_out,
+                  double *rel_res_out);
+
+/* res = clamp(Lab a + b, 0, 1) -> convertTo(8U, 255) -> Lab2BGR (CT/ColorTransfer.cpp:1436-1469).
+ * out_lab_dev may be NULL. */
+int nct_apply_coefficients(nct_ctx *ctx, const uint8_t *cnt_lab_full_dev, const double *a_dev, const double *b_dev,
+                           int H, int W, uint8_t *out_bgr_dev, uint8_t *out_lab_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,16 @@ ABI = {
     "nct_patchmatch_count_evals": (_i, [c_ctx_p, _i]),
     "nct_reconstruct_bds": (_i, [c_ctx_p, _p, _p, _p, _p, _i, _i, _i, _i, _d, _d, _p]),
     "nct_bds_feature_error": (_i, [c_ctx_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p]),
+    "nct_bgr2lab_u8": (_i, [c_ctx_p, _p, _p, _i]),
+    "nct_lab2bgr_u8": (_i, [c_ctx_p, _p, _p, _i]),
+    "nct_resize_linear_u8c3": (_i, [c_ctx_p, _p, _i, _i, _p, _i, _i]),
+    "nct_resize_linear_f64c3": (_i, [c_ctx_p, _p, _i, _i, _p, _i, _i]),
+    "nct_local_fit": (_i, [c_ctx_p, _p, _p, _i, _i, _d, _p, _p]),
+    "nct_confidence_weights": (_i, [c_ctx_p, _p, _i, _p]),
+    "nct_solve_nonlocal": (_i, [c_ctx_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _d, _d, _d, _i, _d, C.POINTER(_i)]),
+    "nct_upsample_coefficients": (_i, [c_ctx_p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p]),
+    "nct_solve_wls": (_i, [c_ctx_p, _p, _p, _p, _p, _i, _i, _d, _d, _d, _i, C.POINTER(_i), C.POINTER(_d)]),
+    "nct_apply_coefficients": (_i, [c_ctx_p, _p, _p, _p, _i, _i, _p, _p]),
 }
 
 _lib = None
@@ -222,3 +232,78 @@ class Context:
         self._check(self.lib.nct_bds_feature_error(self.h, _ptr(c_norm), _ptr(s_raw), _ptr(ann), _ptr(bnn), Cn, ah, aw, bh,
                                                    bw, float(w_cohen), float(w_complete), _ptr(err), _ptr(vote)))
         return (err, vote) if want_vote else err
+
+    # -- colour space / resize (OpenCV stand-ins)
+    def bgr2lab(self, img):
+        import torch
+        out = torch.empty_like(img)
+        self._check(self.lib.nct_bgr2lab_u8(self.h, _ptr(img), _ptr(out), img.numel() // 3))
+        return out
+
+    def lab2bgr(self, img):
+        import torch
+        out = torch.empty_like(img)
+        self._check(self.lib.nct_lab2bgr_u8(self.h, _ptr(img), _ptr(out), img.numel() // 3))
+        return out
+
+    def resize_linear(self, img, dh, dw):
+        """cv::resize(..., INTER_LINEAR) for uint8 or float64 (H, W, 3) cuda tensors."""
+        import torch
+        sh, sw, _ = img.shape
+        out = torch.empty((dh, dw, 3), dtype=img.dtype, device=img.device)
+        fn = self.lib.nct_resize_linear_u8c3 if img.dtype == torch.uint8 else self.lib.nct_resize_linear_f64c3
+        self._check(fn(self.h, _ptr(img), sh, sw, _ptr(out), dh, dw))
+        return out
+
+    # -- colour fit
+    def local_fit(self, cnt_lab, stl_lab, eps=0.6):
+        import torch
+        h, w, _ = cnt_lab.shape
+        a = torch.empty((h, w, 3), dtype=torch.float64, device=cnt_lab.device)
+        b = torch.empty_like(a)
+        self._check(self.lib.nct_local_fit(self.h, _ptr(cnt_lab), _ptr(stl_lab), h, w, float(eps), _ptr(a), _ptr(b)))
+        return a, b
+
+    def confidence_weights(self, err):
+        import torch
+        wgt = torch.empty(err.numel(), dtype=torch.float64, device=err.device)
+        self._check(self.lib.nct_confidence_weights(self.h, _ptr(err), err.numel(), _ptr(wgt)))
+        return wgt
+
+    def solve_nonlocal(self, a, b, weight, cnt_lab, stl_lab, knn_id, knn_w, layer, local_weight=0.125, alpha=1.2,
+                       nonlocal_weight=2.0, knum=8, d_weight=1.0, want_iters=False):
+        """solve_nonlocal_downsample_gpu_gradient (CT/ColorTransfer.cpp:548-949); a, b updated in place."""
+        h, w, _ = cnt_lab.shape
+        its = (_i * 3)()
+        self._check(self.lib.nct_solve_nonlocal(self.h, _ptr(a), _ptr(b), _ptr(weight), _ptr(cnt_lab), _ptr(stl_lab),
+                                                _ptr(knn_id), _ptr(knn_w), h, w, layer, local_weight, alpha,
+                                                nonlocal_weight, knum, d_weight, its if want_iters else None))
+        return list(its) if want_iters else None
+
+    def upsample_coefficients(self, a_lvl, b_lvl, cnt_lab_full):
+        import torch
+        h, w, _ = a_lvl.shape
+        H, W, _ = cnt_lab_full.shape
+        a = torch.empty((H, W, 3), dtype=torch.float64, device=a_lvl.device)
+        b = torch.empty_like(a)
+        rough = torch.empty((H, W), dtype=torch.float64, device=a_lvl.device)
+        self._check(self.lib.nct_upsample_coefficients(self.h, _ptr(a_lvl), _ptr(b_lvl), h, w, _ptr(cnt_lab_full), H, W,
+                                                       _ptr(a), _ptr(b), _ptr(rough)))
+        return a, b, rough
+
+    def solve_wls(self, a, b, rough, cnt_lab_full, lam, alpha=1.2, rel_tol=0.0, max_iters=0):
+        """solve_WLS_roughness_cpu (CT/ColorTransfer.cpp:951-1125); a, b updated in place. Returns (iters, rel_res)."""
+        H, W, _ = cnt_lab_full.shape
+        it = _i(0)
+        res = _d(0.0)
+        self._check(self.lib.nct_solve_wls(self.h, _ptr(a), _ptr(b), _ptr(rough), _ptr(cnt_lab_full), H, W, lam, alpha,
+                                           rel_tol, max_iters, C.byref(it), C.byref(res)))
+        return it.value, res.value
+
+    def apply_coefficients(self, cnt_lab_full, a, b, want_lab=False):
+        import torch
+        H, W, _ = cnt_lab_full.shape
+        out = torch.empty((H, W, 3), dtype=torch.uint8, device=a.device)
+        lab = torch.empty_like(out) if want_lab else None
+        self._check(self.lib.nct_apply_coefficients(self.h, _ptr(cnt_lab_full), _ptr(a), _ptr(b), H, W, _ptr(out), _ptr(lab)))
+        return (out, lab) if want_lab else out

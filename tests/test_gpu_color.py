@@ -1,0 +1,145 @@
+"""GPU parity tests of the colour stage against oracle/color.py (cv2 plain C++ paths, scipy).
+Bars: bit-exact for the 8-bit / integer work and the closed-form FP64 steps; 1e-4 relative (max-norm, per map)
+for the iterative solves -- the tolerance BASELINE.json's north_star states for the colour least squares."""
+import numpy as np
+import pytest
+
+from oracle import color, synth
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-4
+
+
+def to_dev(x, dev):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def relerr(x, ref):
+    return float(np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-12))
+
+
+def rand_knn(rng, n, k=8, frac_invalid=0.05):
+    ids = rng.integers(0, n, (n, k)).astype(np.int32)
+    ids[ids == np.arange(n)[:, None]] = 0
+    w = np.exp(1.0 - rng.random((n, k)) * 0.3 / 3.0)
+    inval = rng.random((n, k)) < frac_invalid
+    ids[inval] = -1
+    w[inval] = 0.0
+    return ids, w
+
+
+def test_bgr2lab_lab2bgr_exhaustive(ctx, dev):
+    """all 2^24 8-bit colours, both directions, against cv2"""
+    import torch
+
+    v = torch.arange(1 << 24, dtype=torch.int32, device=dev)
+    img = torch.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], dim=1).to(torch.uint8).contiguous().view(4096, 4096, 3)
+    lab = ctx.bgr2lab(img)
+    bgr = ctx.lab2bgr(img)
+    ctx.synchronize()
+    host = img.cpu().numpy()
+    for s in range(0, 4096, 512):
+        assert np.array_equal(lab[s:s + 512].cpu().numpy(), color.bgr2lab_u8(host[s:s + 512]))
+        assert np.array_equal(bgr[s:s + 512].cpu().numpy(), color.lab2bgr_u8(host[s:s + 512]))
+
+
+@pytest.mark.parametrize("sh,sw,dh,dw", [(700, 700, 350, 350), (350, 350, 175, 175), (175, 175, 88, 88), (88, 88, 44, 44),
+                                         (125, 125, 63, 63), (520, 352, 260, 176), (65, 44, 33, 22), (1200, 900, 1000, 750),
+                                         (37, 41, 90, 77)])
+def test_resize_u8_bit_exact(ctx, dev, sh, sw, dh, dw):
+    src = np.random.default_rng(sh + dw).integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+    g = ctx.resize_linear(to_dev(src, dev), dh, dw)
+    ctx.synchronize()
+    assert np.array_equal(g.cpu().numpy(), color.resize_linear(src, dw, dh))
+
+
+@pytest.mark.parametrize("sh,sw,dh,dw", [(44, 44, 700, 700), (88, 88, 700, 700), (175, 175, 700, 700), (350, 350, 700, 700),
+                                         (63, 63, 1000, 1000), (65, 44, 520, 352), (38, 60, 600, 960)])
+def test_resize_f64_bit_exact(ctx, dev, sh, sw, dh, dw):
+    src = np.random.default_rng(sh).standard_normal((sh, sw, 3))
+    g = ctx.resize_linear(to_dev(src, dev), dh, dw)
+    ctx.synchronize()
+    assert np.array_equal(g.cpu().numpy(), color.resize_linear(src, dw, dh))
+
+
+def test_pyramid_matches_reference_chain(pkg, ctx, dev):
+    cnt, _ = synth.pair(0, 700, 700)
+    sizes = pkg.level_sizes(700)[::-1]
+    ref = color.pyramid(cnt, [(s, s) for s in sizes])
+    cur = to_dev(cnt, dev)
+    for l in range(3, -1, -1):
+        cur = ctx.resize_linear(cur, sizes[l], sizes[l])
+        ctx.synchronize()
+        assert np.array_equal(cur.cpu().numpy(), ref[l])
+
+
+@pytest.mark.parametrize("h,w", [(44, 44), (13, 17), (175, 175), (1, 7), (700, 700)])
+def test_local_fit_and_weights_bit_exact(ctx, dev, h, w):
+    cnt, stl = synth.pair(1, h, w)
+    cl, sl = color.bgr2lab_u8(cnt), color.bgr2lab_u8(stl)
+    a, b = ctx.local_fit(to_dev(cl, dev), to_dev(sl, dev), 0.6)
+    err = (np.random.default_rng(0).random(h * w).astype(np.float32) - 1.0)
+    wg = ctx.confidence_weights(to_dev(err, dev))
+    ctx.synchronize()
+    oa, ob = color.local_fit(cl, sl, 0.6)
+    assert np.array_equal(a.cpu().numpy(), oa) and np.array_equal(b.cpu().numpy(), ob)
+    assert np.array_equal(wg.cpu().numpy(), color.confidence_weights(err.reshape(h, w)).ravel())
+
+
+@pytest.mark.parametrize("h,w,layer,dwt", [(44, 44, 0, 253.0), (60, 52, 2, 16.0), (96, 96, 4, 1.0)])
+def test_solve_nonlocal_within_tolerance(ctx, dev, h, w, layer, dwt):
+    rng = np.random.default_rng(h)
+    n = h * w
+    cnt, stl = synth.pair(2, h, w)
+    cl, sl = color.bgr2lab_u8(cnt), color.bgr2lab_u8(stl)
+    ids, kw = rand_knn(rng, n)
+    weight = np.maximum(rng.random((h, w)), 1e-6)
+    a0, b0 = color.local_fit(cl, sl, 0.6)
+    ga, gb = to_dev(a0, dev), to_dev(b0, dev)
+    its = ctx.solve_nonlocal(ga, gb, to_dev(weight.ravel(), dev), to_dev(cl, dev), to_dev(sl, dev), to_dev(ids, dev),
+                             to_dev(kw, dev), layer, d_weight=dwt, want_iters=True)
+    oa, ob, oits = color.solve_nonlocal(a0, b0, weight, cl / 255.0, sl / 255.0, ids, kw, layer, d_weight=dwt)
+    assert its == oits
+    for c in range(3):
+        assert relerr(ga.cpu().numpy()[..., c], oa[..., c]) < REL_TOL
+        assert relerr(gb.cpu().numpy()[..., c], ob[..., c]) < REL_TOL
+
+
+@pytest.mark.parametrize("h,w,H,W", [(44, 44, 700, 700), (30, 25, 120, 100), (64, 64, 64, 64)])
+def test_upsample_roughness_apply_bit_exact(ctx, dev, h, w, H, W):
+    rng = np.random.default_rng(H)
+    cnt, _ = synth.pair(3, H, W)
+    lab = color.bgr2lab_u8(cnt)
+    a = 1.0 + 0.5 * rng.standard_normal((h, w, 3))
+    b = 0.2 * rng.standard_normal((h, w, 3))
+    ga, gb, gr = ctx.upsample_coefficients(to_dev(a, dev), to_dev(b, dev), to_dev(lab, dev))
+    out, out_lab = ctx.apply_coefficients(to_dev(lab, dev), ga, gb, want_lab=True)
+    ctx.synchronize()
+    oa, ob, orr = color.upsample_coefficients(a, b, lab / 255.0, W, H)
+    assert np.array_equal(ga.cpu().numpy(), oa) and np.array_equal(gb.cpu().numpy(), ob)
+    assert np.array_equal(gr.cpu().numpy(), orr)
+    assert (orr == 1e-6).any() and (orr == 1.0).any()
+    res = np.minimum(np.maximum(lab / 255.0 * oa + ob, 0.0), 1.0)
+    assert np.array_equal(out_lab.cpu().numpy(), color.to_u8_x255(res))
+    assert np.array_equal(out.cpu().numpy(), color.apply_coefficients(lab / 255.0, oa, ob))
+
+
+@pytest.mark.parametrize("H,W,lam", [(96, 80, 6.07), (128, 128, 0.096), (175, 160, 1.5)])
+def test_solve_wls_matches_direct_solve(ctx, dev, H, W, lam):
+    rng = np.random.default_rng(W)
+    cnt, _ = synth.pair(4, H, W)
+    lab = color.bgr2lab_u8(cnt)
+    a = 1.0 + 0.5 * rng.standard_normal((H, W, 3))
+    b = 0.2 * rng.standard_normal((H, W, 3))
+    rough = np.where(rng.random((H, W)) < 0.1, 1e-6, 1.0)
+    ga, gb = to_dev(a, dev), to_dev(b, dev)
+    its, res = ctx.solve_wls(ga, gb, to_dev(rough, dev), to_dev(lab, dev), lam, 1.2)
+    oa, ob = color.solve_wls(a, b, rough, lab[..., 0] / 255.0, lam, 1.2)
+    assert res <= 1e-10 and its > 0
+    for c in range(3):
+        assert relerr(ga.cpu().numpy()[..., c], oa[..., c]) < REL_TOL
+        assert relerr(gb.cpu().numpy()[..., c], ob[..., c]) < REL_TOL
+    print(f"WLS {H}x{W} lam={lam}: {its} PCG iterations, rel.res {res:.2e}, "
+          f"max rel.err a {max(relerr(ga.cpu().numpy()[..., c], oa[..., c]) for c in range(3)):.2e}")
