@@ -58,6 +58,10 @@ int nct_version(void);
 long long nct_launch_count(const nct_ctx *ctx);
 void nct_reset_launch_count(nct_ctx *ctx);
 
+/* Test hook: copy `bytes` of the named internal scratch buffer to host (synchronises).  Lets parity tests feed
+ * the kernel's own intermediate arrays (e.g. "nl_d2", "nl_wx2", "nl_wy2", "nl_kw2") to the oracle. */
+int nct_debug_read_scratch(nct_ctx *ctx, const char *name, void *host_dst, size_t bytes);
+
 /* ---------------------------------------------------------------- layout / normalise */
 
 /* Caffe blob (planar C x H x W) -> pixel-major H x W x C.  No reference counterpart

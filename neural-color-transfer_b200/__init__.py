@@ -34,6 +34,7 @@ ABI = {
     "nct_version": (_i, []),
     "nct_launch_count": (_ll, [c_ctx_p]),
     "nct_reset_launch_count": (None, [c_ctx_p]),
+    "nct_debug_read_scratch": (_i, [c_ctx_p, C.c_char_p, _p, C.c_size_t]),
     "nct_chw_to_hwc": (_i, [c_ctx_p, _p, _p, _i, _i, _i]),
     "nct_hwc_to_chw": (_i, [c_ctx_p, _p, _p, _i, _i, _i]),
     "nct_l2norm": (_i, [c_ctx_p, _p, _p, _i, _i, _i]),
@@ -152,6 +153,13 @@ class Context:
 
     def reset_launch_count(self):
         self.lib.nct_reset_launch_count(self.h)
+
+    def read_scratch(self, name, dtype, count):
+        """test hook: copy an internal scratch buffer to a numpy array"""
+        import numpy as np
+        out = np.empty(count, dtype)
+        self._check(self.lib.nct_debug_read_scratch(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
 
     # -- feature helpers
     def chw_to_hwc(self, src, dst=None):

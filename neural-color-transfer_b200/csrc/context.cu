@@ -114,6 +114,17 @@ int nct_synchronize(nct_ctx *ctx)
     return NCT_OK;
 }
 
+int nct_debug_read_scratch(nct_ctx *ctx, const char *name, void *host_dst, size_t bytes)
+{
+    if (!ctx || !name || !host_dst) return NCT_ERR_ARG;
+    auto it = ctx->scratch.find(name);
+    if (it == ctx->scratch.end() || !it->second.ptr) return nct_fail(ctx, NCT_ERR_ARG, "no scratch buffer named '%s'", name);
+    if (it->second.bytes < bytes) return nct_fail(ctx, NCT_ERR_ARG, "scratch '%s' holds %zu bytes < %zu", name, it->second.bytes, bytes);
+    NCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NCT_CUDA(ctx, cudaMemcpy(host_dst, it->second.ptr, bytes, cudaMemcpyDeviceToHost));
+    return NCT_OK;
+}
+
 long long nct_launch_count(const nct_ctx *ctx) { return ctx ? ctx->launches : 0; }
 void nct_reset_launch_count(nct_ctx *ctx)
 {

@@ -22,7 +22,7 @@ _lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 
 def build(force: bool = False):
     """Compile the C restatement (gcc). Building the checker is not using it."""
-    srcs = [os.path.join(_HERE, f) for f in ("pm_oracle.c", "bds_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("pm_oracle.c", "bds_oracle.c", "cg_oracle.c")]
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle_pm.so"], stdout=subprocess.DEVNULL)
     return _LIB
@@ -51,6 +51,8 @@ def lib():
         _bp = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
         L.orc_reconstruct_bds.argtypes = [_bp, _bp, _up, _up] + [C.c_int] * 4 + [C.c_double, C.c_double, _bp]
         L.orc_bds_feature_error.argtypes = [_fp, _fp, _up, _up] + [C.c_int] * 5 + [C.c_float, C.c_float, C.c_int, _fp, C.c_void_p]
+        _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+        L.orc_solve_nonlocal_canon.argtypes = [_dp, _dp, _bp, _bp, _dp, _dp, _dp, _ip, _dp, C.c_int, C.c_int, C.c_int, C.c_double, _ip]
         _lib = L
     return _lib
 
@@ -168,3 +170,16 @@ def bds_feature_error(c_norm, s_raw, ann, bnn, w_cohen=1.0, w_complete=2.0, mode
                                 Cn, ah, aw, bh, bw, float(w_cohen), float(w_complete), mode, err,
                                 vote.ctypes.data if want_vote else None)
     return (err, vote) if want_vote else err
+
+
+def solve_nonlocal_canon(a0, b0, src_u8, ref_u8, d2, wx2, wy2, knn_id, kw2, maxit, tol=1e-6):
+    """Canonical-order matrix-free CG of cg_oracle.c (decision N1). a0/b0 (h, w, 3) float64; returns (a, b, iters)."""
+    h, w, _ = a0.shape
+    a = np.array(a0, np.float64, copy=True)
+    b = np.array(b0, np.float64, copy=True)
+    its = np.zeros(3, np.int32)
+    lib().orc_solve_nonlocal_canon(a, b, np.ascontiguousarray(src_u8, np.uint8), np.ascontiguousarray(ref_u8, np.uint8),
+                                   np.ascontiguousarray(d2, np.float64), np.ascontiguousarray(wx2, np.float64),
+                                   np.ascontiguousarray(wy2, np.float64), np.ascontiguousarray(knn_id, np.int32),
+                                   np.ascontiguousarray(kw2, np.float64), h, w, int(maxit), float(tol), its)
+    return a, b, [int(v) for v in its]

@@ -88,8 +88,13 @@ def test_local_fit_and_weights_bit_exact(ctx, dev, h, w):
     assert np.array_equal(wg.cpu().numpy(), color.confidence_weights(err.reshape(h, w)).ravel())
 
 
-@pytest.mark.parametrize("h,w,layer,dwt", [(44, 44, 0, 253.0), (60, 52, 2, 16.0), (96, 96, 4, 1.0)])
-def test_solve_nonlocal_within_tolerance(ctx, dev, h, w, layer, dwt):
+@pytest.mark.parametrize("h,w,layer,dwt", [(44, 44, 0, 253.0), (60, 52, 2, 16.0), (96, 96, 4, 1.0), (175, 175, 2, 16.0)])
+def test_solve_nonlocal(ctx, dev, h, w, layer, dwt):
+    """The un-converged CG iterate is chaotically sensitive to rounding (see oracle/cg_oracle.c), so parity is
+    pinned bit-for-bit against the canonical-order oracle fed with the kernel's own weight arrays; those arrays and
+    the result are additionally checked against the reference-order oracle (explicit A^T A, scipy)."""
+    import oracle
+
     rng = np.random.default_rng(h)
     n = h * w
     cnt, stl = synth.pair(2, h, w)
@@ -100,11 +105,26 @@ def test_solve_nonlocal_within_tolerance(ctx, dev, h, w, layer, dwt):
     ga, gb = to_dev(a0, dev), to_dev(b0, dev)
     its = ctx.solve_nonlocal(ga, gb, to_dev(weight.ravel(), dev), to_dev(cl, dev), to_dev(sl, dev), to_dev(ids, dev),
                              to_dev(kw, dev), layer, d_weight=dwt, want_iters=True)
+    d2, wx2, wy2 = (ctx.read_scratch(k, np.float64, n) for k in ("nl_d2", "nl_wx2", "nl_wy2"))
+    kw2 = ctx.read_scratch("nl_kw2", np.float64, n * 8)
+    # the kernel's operator coefficients agree with the reference formulas (pow() may differ in the last ulps)
+    gx, gy = color.gradient_weights(cl[..., 0] / 255.0, float(np.float32(0.125)), float(np.float32(1.2)))
+    dw = np.sqrt(weight.ravel()) * float(np.sqrt(np.float32(dwt)))
+    assert np.allclose(wx2, 2 * (gx * gx).ravel(), rtol=1e-14) and np.allclose(wy2, 2 * (gy * gy).ravel(), rtol=1e-14)
+    assert np.array_equal(d2, dw * dw)
+    iw = np.sqrt(kw) * np.sqrt(2.0 / 8)
+    assert np.array_equal(kw2.reshape(n, 8), np.where(ids >= 0, iw * iw, 0.0))
+    # bit-exact against the canonical-order oracle
+    maxit = 50 if layer == 4 else 100
+    ca, cb, cits = oracle.solve_nonlocal_canon(a0, b0, cl, sl, d2, wx2, wy2, ids, kw2, maxit)
+    assert its == cits
+    assert np.array_equal(ga.cpu().numpy(), ca) and np.array_equal(gb.cpu().numpy(), cb)
+    # against the reference-order oracle: same iteration count, agreement limited by the iterate's own sensitivity
     oa, ob, oits = color.solve_nonlocal(a0, b0, weight, cl / 255.0, sl / 255.0, ids, kw, layer, d_weight=dwt)
     assert its == oits
-    for c in range(3):
-        assert relerr(ga.cpu().numpy()[..., c], oa[..., c]) < REL_TOL
-        assert relerr(gb.cpu().numpy()[..., c], ob[..., c]) < REL_TOL
+    worst = max(max(relerr(ga.cpu().numpy()[..., c], oa[..., c]), relerr(gb.cpu().numpy()[..., c], ob[..., c])) for c in range(3))
+    print(f"non-local CG {h}x{w} layer {layer}: iters {its}, max rel. diff vs reference-order oracle {worst:.2e}")
+    assert worst < 5e-3
 
 
 @pytest.mark.parametrize("h,w,H,W", [(44, 44, 700, 700), (30, 25, 120, 100), (64, 64, 64, 64)])

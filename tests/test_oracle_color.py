@@ -109,3 +109,38 @@ def test_transfer_color_level_runs_end_to_end_small():
     r = color.transfer_color_level(err, down_cnt, sml, cnt_lab_d, ids, kw, layer=3, return_all=True)
     assert r["out"].shape == (H, W, 3) and r["out"].dtype == np.uint8
     assert max(r["cg_iters"]) <= 100 and np.isfinite(r["a3"]).all()
+
+
+def test_unconverged_cg_iterate_is_rounding_sensitive_and_canonical_order_is_close():
+    """Evidence for decision N1 (oracle/cg_oracle.c): (i) perturbing A^T A by 1e-15 relative moves the 100-iteration
+    iterate by far more than 1e-15 -- the reference's own result is only defined up to that; (ii) the canonical-order
+    matrix-free CG agrees with the reference-order CG to within that same sensitivity band."""
+    import oracle
+
+    rng = np.random.default_rng(44)
+    h = w = 32
+    n = h * w
+    cnt, stl = synth.pair(2, h, w)
+    cl, sl = color.bgr2lab_u8(cnt), color.bgr2lab_u8(stl)
+    ids, kw = rand_knn(rng, n, frac_invalid=0.0)
+    weight = np.maximum(rng.random((h, w)), 1e-6)
+    a0, b0 = color.local_fit(cl, sl, 0.6)
+    A, B = color.assemble_nonlocal(weight, cl / 255.0, sl / 255.0, ids, kw, d_weight=253.0)
+    x0 = np.concatenate([a0[..., 0].ravel(), b0[..., 0].ravel()])
+    x_ref, _ = color.cg_normal_equations(A[0], B[0], x0, 1e-6, 100)
+    Ap = A[0].copy()
+    Ap.data = Ap.data * (1.0 + 1e-15 * rng.standard_normal(Ap.data.shape))
+    x_per, _ = color.cg_normal_equations(Ap, B[0], x0, 1e-6, 100)
+    sens = np.abs(x_per - x_ref).max() / np.abs(x_ref).max()
+    assert sens > 1e-9  # amplification by >= 6 orders of magnitude
+    gx, gy = color.gradient_weights(cl[..., 0] / 255.0, 0.125, float(np.float32(1.2)))
+    dw = np.sqrt(weight.ravel()) * float(np.sqrt(np.float32(253.0)))
+    iw = np.sqrt(kw) * np.sqrt(2.0 / 8)
+    ca, cb, its = oracle.solve_nonlocal_canon(a0, b0, cl, sl, dw * dw, 2 * (gx * gx).ravel(), 2 * (gy * gy).ravel(), ids, iw * iw, 100)
+    xc = np.concatenate([ca[..., 0].ravel(), cb[..., 0].ravel()])
+    diff = np.abs(xc - x_ref).max() / np.abs(x_ref).max()
+    assert its == [100, 100, 100] and diff < max(50 * sens, 5e-3)
+    # run to convergence and the two agree tightly: the disagreement above is the truncation, not the operator
+    x_conv, _ = color.cg_normal_equations(A[0], B[0], x0, 1e-11, 20000)
+    cca, ccb, _ = oracle.solve_nonlocal_canon(a0, b0, cl, sl, dw * dw, 2 * (gx * gx).ravel(), 2 * (gy * gy).ravel(), ids, iw * iw, 20000, 1e-11)
+    assert np.abs(np.concatenate([cca[..., 0].ravel(), ccb[..., 0].ravel()]) - x_conv).max() / np.abs(x_conv).max() < 1e-6
