@@ -179,6 +179,22 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
 int nct_apply_coefficients(nct_ctx *ctx, const uint8_t *cnt_lab_full_dev, const double *a_dev, const double *b_dev,
                            int H, int W, uint8_t *out_bgr_dev, uint8_t *out_lab_dev);
 
+/* ---------------------------------------------------------------- clustering / non-local neighbours */
+
+/* ColorTransfer::clusterFeastures (CT/ColorTransfer.cpp:355-395) = root split of cvflann's hierarchical k-means
+ * (CT/Flann/kmeans_index.h:700-880; branching k = 10, 11 iterations, FLANN_CENTERS_RANDOM after srand(1)).
+ * feat: L2-normalised conv5_1 of the content image, HWC (h*w rows of C floats).  labels_dev: h*w ints in [0, k).
+ * If the root cannot be split (fewer than k distinct points) all labels are 0.  Synchronises the stream. */
+int nct_cluster_features(nct_ctx *ctx, const float *feat_norm_hwc_dev, int h, int w, int C, int k, int iterations,
+                         int *labels_dev);
+
+/* ColorTransfer::findKnns (CT/ColorTransfer.cpp:397-423 with getClusters :273-353, findSubKNNs :136-195,
+ * sortMergeComputeWeight :60-110): for every pixel of the level-size 8-bit Lab image the 8 nearest other pixels
+ * (in Lab) among the pixels sharing one of its (4-neighbour dilated) clusters; label cell (cx, cy) covers a
+ * samples x samples pixel block.  knn_id_dev: [h*w][8] pixel ids (-1 = none), knn_w_dev: [h*w][8] exp(1 - d/3). */
+int nct_find_knns(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int nlabels, const uint8_t *lab_dev, int h, int w,
+                  int samples, int *knn_id_dev, double *knn_w_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,8 @@ ABI = {
     "nct_upsample_coefficients": (_i, [c_ctx_p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p]),
     "nct_solve_wls": (_i, [c_ctx_p, _p, _p, _p, _p, _i, _i, _d, _d, _d, _i, C.POINTER(_i), C.POINTER(_d)]),
     "nct_apply_coefficients": (_i, [c_ctx_p, _p, _p, _p, _i, _i, _p, _p]),
+    "nct_cluster_features": (_i, [c_ctx_p, _p, _i, _i, _i, _i, _i, _p]),
+    "nct_find_knns": (_i, [c_ctx_p, _p, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
 }
 
 _lib = None
@@ -315,3 +317,21 @@ class Context:
         lab = torch.empty_like(out) if want_lab else None
         self._check(self.lib.nct_apply_coefficients(self.h, _ptr(cnt_lab_full), _ptr(a), _ptr(b), H, W, _ptr(out), _ptr(lab)))
         return (out, lab) if want_lab else out
+
+    # -- clustering / non-local neighbours
+    def cluster_features(self, feat_norm, k=10, iterations=11):
+        """ColorTransfer::clusterFeastures (CT/ColorTransfer.cpp:355-395); feat_norm (h, w, C) float32 cuda."""
+        import torch
+        h, w, Cn = feat_norm.shape
+        labels = torch.empty(h * w, dtype=torch.int32, device=feat_norm.device)
+        self._check(self.lib.nct_cluster_features(self.h, _ptr(feat_norm), h, w, Cn, k, iterations, _ptr(labels)))
+        return labels
+
+    def find_knns(self, labels, lw, lh, lab, samples, nlabels=10):
+        """ColorTransfer::findKnns (CT/ColorTransfer.cpp:397-423); lab (h, w, 3) uint8 cuda."""
+        import torch
+        h, w, _ = lab.shape
+        ids = torch.empty((h * w, 8), dtype=torch.int32, device=lab.device)
+        wts = torch.empty((h * w, 8), dtype=torch.float64, device=lab.device)
+        self._check(self.lib.nct_find_knns(self.h, _ptr(labels), lw, lh, nlabels, _ptr(lab), h, w, samples, _ptr(ids), _ptr(wts)))
+        return ids, wts

@@ -22,7 +22,7 @@ _lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 
 def build(force: bool = False):
     """Compile the C restatement (gcc). Building the checker is not using it."""
-    srcs = [os.path.join(_HERE, f) for f in ("pm_oracle.c", "bds_oracle.c", "cg_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("pm_oracle.c", "bds_oracle.c", "cg_oracle.c", "cluster_oracle.c")]
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle_pm.so"], stdout=subprocess.DEVNULL)
     return _LIB
@@ -53,6 +53,11 @@ def lib():
         L.orc_bds_feature_error.argtypes = [_fp, _fp, _up, _up] + [C.c_int] * 5 + [C.c_float, C.c_float, C.c_int, _fp, C.c_void_p]
         _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
         L.orc_solve_nonlocal_canon.argtypes = [_dp, _dp, _bp, _bp, _dp, _dp, _dp, _ip, _dp, C.c_int, C.c_int, C.c_int, C.c_double, _ip]
+        L.orc_msvc_shuffle.argtypes = [C.c_int, _ip]
+        L.orc_kmeans_labels.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, C.c_void_p]
+        L.orc_kmeans_labels.restype = C.c_int
+        for fn in (L.orc_find_knns, L.orc_find_knns_brute):
+            fn.argtypes = [_ip, C.c_int, C.c_int, C.c_int, _bp, C.c_int, C.c_int, C.c_int, _ip, _dp]
         _lib = L
     return _lib
 
@@ -183,3 +188,29 @@ def solve_nonlocal_canon(a0, b0, src_u8, ref_u8, d2, wx2, wy2, knn_id, kw2, maxi
                                    np.ascontiguousarray(wy2, np.float64), np.ascontiguousarray(knn_id, np.int32),
                                    np.ascontiguousarray(kw2, np.float64), h, w, int(maxit), float(tol), its)
     return a, b, [int(v) for v in its]
+
+
+def msvc_shuffle(n):
+    out = np.empty(n, np.int32)
+    lib().orc_msvc_shuffle(n, out)
+    return out
+
+
+def kmeans_labels(features, k=10, iterations=11):
+    """Root split of cvflann's hierarchical k-means (clusterFeastures). features (n, dim) float32.
+    Returns (labels int32[n], number of clusters)."""
+    f = np.ascontiguousarray(features, np.float32)
+    labels = np.zeros(f.shape[0], np.int32)
+    nl = lib().orc_kmeans_labels(f, f.shape[0], f.shape[1], k, iterations, labels, None)
+    return labels, int(nl)
+
+
+def find_knns(labels, lw, lh, lab_u8, samples, nlabels=10, brute=False):
+    """ColorTransfer::findKnns. Returns (knn_id int32 [n, 8], knn_w float64 [n, 8])."""
+    lab = np.ascontiguousarray(lab_u8, np.uint8)
+    h, w, _ = lab.shape
+    ids = np.empty((h * w, 8), np.int32)
+    wts = np.empty((h * w, 8), np.float64)
+    fn = lib().orc_find_knns_brute if brute else lib().orc_find_knns
+    fn(np.ascontiguousarray(labels, np.int32), lw, lh, nlabels, lab, h, w, samples, ids, wts)
+    return ids, wts
