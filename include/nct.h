@@ -179,6 +179,27 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
 int nct_apply_coefficients(nct_ctx *ctx, const uint8_t *cnt_lab_full_dev, const double *a_dev, const double *b_dev,
                            int H, int W, uint8_t *out_bgr_dev, uint8_t *out_lab_dev);
 
+/* ---------------------------------------------------------------- VGG-19 features
+ * Replaces Classifier (NCT/Classifier.h:51-61, NCT/Classifier.cpp:5-143) + caffe::Net<float> for the fixed graph of
+ * demo/model/vgg19/VGG_ILSVRC_19_layers_deploy.prototxt, truncated after conv5_1.  Trunk layer index 0..12 =
+ * conv1_1, conv1_2, conv2_1, conv2_2, conv3_1..conv3_4, conv4_1..conv4_4, conv5_1.  Feature level l = 0..4 =
+ * conv5_1, conv4_1, conv3_1, conv2_1, conv1_1 (post-ReLU: the prototxt's ReLUs are in place), the order of
+ * params.layers in NCT/main.cu:55-59. */
+int nct_vgg19_num_layers(void);
+const char *nct_vgg19_layer_name(int layer);
+int nct_vgg19_layer_shape(int layer, int *cin, int *cout);
+/* Caffe blob layout: weights O x I x 3 x 3, bias O (host pointers). Replaces Net::CopyTrainedLayersFrom
+ * (caffe/net.cpp:798) for one layer. */
+int nct_vgg19_set_weights(nct_ctx *ctx, int layer, const float *w_oihw_host, const float *bias_host);
+/* Feature-map sizes {C, H, W} per level for an h x w image under Caffe's ceil-mode pooling
+ * (caffe/layers/pooling_layer.cpp:90-93); replaces the Dim outputs of Classifier::Predict (NCT/Classifier.h:30-43). */
+int nct_vgg19_level_dims(int h, int w, int dims[5][3]);
+/* Classifier::Predict(img, layers, data_s): 8-bit BGR device image -> post-ReLU feature maps, HWC FP32, written to
+ * the caller's device buffers feat_dev[l] for l = deepest_level..4 (sizes from nct_vgg19_level_dims).  The forward
+ * stops after the layer of `deepest_level` (0 = conv5_1 = full trunk), which is all a re-forward needs
+ * (NCT/main.cu:424-427 re-runs the whole net). */
+int nct_vgg19_features(nct_ctx *ctx, const uint8_t *bgr_dev, int h, int w, int deepest_level, float *feat_dev[5]);
+
 /* ---------------------------------------------------------------- clustering / non-local neighbours */
 
 /* ColorTransfer::clusterFeastures (CT/ColorTransfer.cpp:355-395) = root split of cvflann's hierarchical k-means

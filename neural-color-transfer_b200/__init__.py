@@ -57,6 +57,12 @@ ABI = {
     "nct_upsample_coefficients": (_i, [c_ctx_p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p]),
     "nct_solve_wls": (_i, [c_ctx_p, _p, _p, _p, _p, _i, _i, _d, _d, _d, _i, C.POINTER(_i), C.POINTER(_d)]),
     "nct_apply_coefficients": (_i, [c_ctx_p, _p, _p, _p, _i, _i, _p, _p]),
+    "nct_vgg19_num_layers": (_i, []),
+    "nct_vgg19_layer_name": (C.c_char_p, [_i]),
+    "nct_vgg19_layer_shape": (_i, [_i, C.POINTER(_i), C.POINTER(_i)]),
+    "nct_vgg19_set_weights": (_i, [c_ctx_p, _i, _p, _p]),
+    "nct_vgg19_level_dims": (_i, [_i, _i, C.POINTER(_i * 3)]),
+    "nct_vgg19_features": (_i, [c_ctx_p, _p, _i, _i, _i, C.POINTER(_p)]),
     "nct_cluster_features": (_i, [c_ctx_p, _p, _i, _i, _i, _i, _i, _p]),
     "nct_find_knns": (_i, [c_ctx_p, _p, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
 }
@@ -335,3 +341,35 @@ class Context:
         wts = torch.empty((h * w, 8), dtype=torch.float64, device=lab.device)
         self._check(self.lib.nct_find_knns(self.h, _ptr(labels), lw, lh, nlabels, _ptr(lab), h, w, samples, _ptr(ids), _ptr(wts)))
         return ids, wts
+
+    # -- VGG-19 (Classifier)
+    def load_vgg19_weights(self, weights):
+        """weights: dict layer name -> (w OIHW float32 numpy, bias float32 numpy), Caffe blob layout."""
+        import numpy as np
+        for i in range(self.lib.nct_vgg19_num_layers()):
+            name = self.lib.nct_vgg19_layer_name(i).decode()
+            w, b = weights[name]
+            w = np.ascontiguousarray(w, np.float32)
+            b = np.ascontiguousarray(b, np.float32)
+            self._check(self.lib.nct_vgg19_set_weights(self.h, i, w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))
+
+    def level_dims(self, h, w):
+        d = ((_i * 3) * 5)()
+        self.lib.nct_vgg19_level_dims(h, w, d)
+        return [tuple(d[l]) for l in range(5)]
+
+    def predict(self, img_bgr, deepest_level=0, out=None):
+        """Classifier::Predict (NCT/Classifier.cpp:59-143): uint8 BGR (h, w, 3) cuda tensor -> list of 5 HWC float32
+        feature tensors (levels deeper than `deepest_level` are None)."""
+        import torch
+        h, w, _ = img_bgr.shape
+        dims = self.level_dims(h, w)
+        feats = list(out) if out is not None else [None] * 5
+        ptrs = (_p * 5)()
+        for l in range(deepest_level, 5):
+            Cn, fh, fw = dims[l]
+            if feats[l] is None:
+                feats[l] = torch.empty((fh, fw, Cn), dtype=torch.float32, device=img_bgr.device)
+            ptrs[l] = feats[l].data_ptr()
+        self._check(self.lib.nct_vgg19_features(self.h, _ptr(img_bgr), h, w, deepest_level, ptrs))
+        return feats

@@ -1,5 +1,4 @@
 #include "nct_internal.h"
 extern "C" {
-__attribute__((weak)) void nct_vgg_free(nct_ctx *) {}
 __attribute__((weak)) void nct_pipe_free(nct_ctx *) {}
 }

@@ -1,0 +1,320 @@
+// VGG-19 trunk (conv1_1 .. conv5_1) feature extractor.
+//
+// Replaces Classifier::Predict / Preprocess (NCT/Classifier.cpp:59-143, 185-275) and the Caffe Net::Forward it
+// drives (caffe/net.cpp:554-586; cudnn_conv_layer.cu:20-37 conv + bias, in-place ReLU, 2x2/2 ceil-mode MAX pooling
+// caffe/layers/pooling_layer.cpp:90-93, pooling_layer.cu:10-40) for the one graph the reference ever runs
+// (demo/model/vgg19/VGG_ILSVRC_19_layers_deploy.prototxt), truncated after conv5_1 -- the reference also runs
+// conv5_2..pool5 although nothing reads them -- and, on re-forwards, after the deepest layer still needed.
+//
+// Layout: activations are pixel-major FP32 (NHWC, N = 1), so every feature map is directly the HWC volume
+// PatchMatch consumes (the reference keeps planar blobs and pays strided gathers).  Weights are re-laid out
+// once to [tap][Cin][Cout].
+//
+// This file holds the FP32 CUDA-core implicit-GEMM path (exact FP32 products, fixed summation order:
+// tap-major, channel-minor).  It is the numerically conservative engine: FP32 like the reference's cuDNN path.
+#include "nct_internal.h"
+#include <vector>
+#include <cstring>
+
+namespace {
+
+struct ConvSpec { const char *name; int cin, cout; bool pool_before; int level; };
+// level: index into the 5 feature maps (0 = conv5_1 ... 4 = conv1_1), -1 = not exported
+const ConvSpec kTrunk[13] = {
+    {"conv1_1", 3, 64, false, 4},   {"conv1_2", 64, 64, false, -1},
+    {"conv2_1", 64, 128, true, 3},  {"conv2_2", 128, 128, false, -1},
+    {"conv3_1", 128, 256, true, 2}, {"conv3_2", 256, 256, false, -1}, {"conv3_3", 256, 256, false, -1}, {"conv3_4", 256, 256, false, -1},
+    {"conv4_1", 256, 512, true, 1}, {"conv4_2", 512, 512, false, -1}, {"conv4_3", 512, 512, false, -1}, {"conv4_4", 512, 512, false, -1},
+    {"conv5_1", 512, 512, true, 0},
+};
+
+}  // namespace
+
+struct VggState {
+    float *w[13] = {nullptr};   // [9][cin][cout]
+    float *b[13] = {nullptr};
+    bool have[13] = {false};
+};
+
+namespace {
+
+// ------------------------------------------------------------------ preprocessing (Classifier::Preprocess)
+// 8-bit BGR -> float, minus the BGR mean (103.939, 116.779, 123.68), kept HWC (3 channels)
+__global__ void preprocess_kernel(const uint8_t *__restrict__ bgr, float *__restrict__ out, int npix)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npix) return;
+    out[(size_t)p * 3 + 0] = __fsub_rn((float)bgr[(size_t)p * 3 + 0], 103.939f);
+    out[(size_t)p * 3 + 1] = __fsub_rn((float)bgr[(size_t)p * 3 + 1], 116.779f);
+    out[(size_t)p * 3 + 2] = __fsub_rn((float)bgr[(size_t)p * 3 + 2], 123.68f);
+}
+
+// ------------------------------------------------------------------ conv1_1: Cin = 3 (K = 27), direct
+// one thread = one pixel x 16 output channels; weights [27][64] in shared memory
+__global__ void __launch_bounds__(256) conv_first_kernel(const float *__restrict__ in, const float *__restrict__ wt,
+                                                         const float *__restrict__ bias, float *__restrict__ out, int H, int W)
+{
+    __shared__ float sw[27 * 64];
+    __shared__ float sb[64];
+    for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = wt[i];
+    if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = t >> 2, cg = (t & 3) * 16;
+    if (p >= H * W) return;
+    const int x = p % W, y = p / W;
+    float acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int yy = y + ky - 1, xx = x + kx - 1;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const float *ip = in + ((size_t)yy * W + xx) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = ip[c];
+                const float *wp = sw + ((ky * 3 + kx) * 3 + c) * 64 + cg;
+#pragma unroll
+                for (int o = 0; o < 16; ++o) acc[o] = __fmaf_rn(v, wp[o], acc[o]);
+            }
+        }
+    float4 *op = reinterpret_cast<float4 *>(out + (size_t)p * 64 + cg);
+#pragma unroll
+    for (int o = 0; o < 16; o += 4)
+        op[o / 4] = make_float4(fmaxf(acc[o] + sb[cg + o], 0.f), fmaxf(acc[o + 1] + sb[cg + o + 1], 0.f),
+                                fmaxf(acc[o + 2] + sb[cg + o + 2], 0.f), fmaxf(acc[o + 3] + sb[cg + o + 3], 0.f));
+}
+
+// ------------------------------------------------------------------ generic 3x3 conv, implicit GEMM on CUDA cores
+// C[M = H*W pixels][N = Cout] = sum over (tap, cin) A[pixel shifted by tap][cin] * Wt[tap][cin][cout]
+// block tile 128 (pixels) x 64 (couts), K chunk 16 channels of one tap, 256 threads, 8 x 4 outputs per thread.
+constexpr int BM = 128, BN = 64, BK = 16;
+
+__global__ void __launch_bounds__(256) conv3x3_kernel(const float *__restrict__ in, const float *__restrict__ wt,
+                                                      const float *__restrict__ bias, float *__restrict__ out, int H, int W,
+                                                      int Cin, int Cout)
+{
+    __shared__ float As[2][BK][BM + 4];
+    __shared__ float Bs[2][BK][BN];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int M = H * W;
+    // loader roles: A tile = 128 pixels x 16 channels = 512 float4 -> 2 per thread; B tile = 16 x 64 = 256 float4 -> 1 per thread
+    const int a_pix = tid >> 1;          // 0..127
+    const int a_c4 = (tid & 1) * 8;      // channel offset 0 or 8 (two float4 each)
+    const int pm = m0 + a_pix;
+    const int px = pm % W, py = pm / W;
+    const bool pvalid = pm < M;
+    const int b_k = tid >> 4, b_n4 = (tid & 15) * 4;
+    // compute roles
+    const int tx = tid & 15, ty = tid >> 4;  // tx -> 4 couts, ty -> 8 pixels
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int kchunks = Cin / BK;
+    const int total = 9 * kchunks;
+    float4 ra0, ra1, rb;
+    auto load_global = [&](int it) {
+        const int tap = it / kchunks, kc = (it % kchunks) * BK;
+        const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+        ra0 = ra1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pvalid && yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const float4 *ip = reinterpret_cast<const float4 *>(in + ((size_t)yy * W + xx) * Cin + kc + a_c4);
+            ra0 = __ldg(ip);
+            ra1 = __ldg(ip + 1);
+        }
+        rb = __ldg(reinterpret_cast<const float4 *>(wt + ((size_t)tap * Cin + kc + b_k) * Cout + n0 + b_n4));
+    };
+    auto store_smem = [&](int buf) {
+        As[buf][a_c4 + 0][a_pix] = ra0.x; As[buf][a_c4 + 1][a_pix] = ra0.y; As[buf][a_c4 + 2][a_pix] = ra0.z; As[buf][a_c4 + 3][a_pix] = ra0.w;
+        As[buf][a_c4 + 4][a_pix] = ra1.x; As[buf][a_c4 + 5][a_pix] = ra1.y; As[buf][a_c4 + 6][a_pix] = ra1.z; As[buf][a_c4 + 7][a_pix] = ra1.w;
+        *reinterpret_cast<float4 *>(&Bs[buf][b_k][b_n4]) = rb;
+    };
+    load_global(0);
+    store_smem(0);
+    __syncthreads();
+    for (int it = 0; it < total; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < total) load_global(it + 1);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(av[i], bv[j], acc[i][j]);
+        }
+        if (it + 1 < total) {
+            store_smem(buf ^ 1);
+            __syncthreads();
+        }
+    }
+    const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + n0 + tx * 4));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
+        if (m < M) {
+            float4 o;
+            o.x = fmaxf(acc[i][0] + bb.x, 0.f);
+            o.y = fmaxf(acc[i][1] + bb.y, 0.f);
+            o.z = fmaxf(acc[i][2] + bb.z, 0.f);
+            o.w = fmaxf(acc[i][3] + bb.w, 0.f);
+            *reinterpret_cast<float4 *>(out + (size_t)m * Cout + n0 + tx * 4) = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ 2x2 / stride 2 max pooling, ceil mode, NHWC
+__global__ void maxpool_kernel(const float *__restrict__ in, float *__restrict__ out, int H, int W, int C, int Ho, int Wo)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c4n = C / 4;
+    if (t >= (long long)Ho * Wo * c4n) return;
+    const int c4 = (int)(t % c4n);
+    const int po = (int)(t / c4n);
+    const int xo = po % Wo, yo = po / Wo;
+    float4 m = make_float4(-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int y = 2 * yo + dy, x = 2 * xo + dx;
+            if (y < H && x < W) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(in + ((size_t)y * W + x) * C) + c4);
+                m.x = v.x > m.x ? v.x : m.x;
+                m.y = v.y > m.y ? v.y : m.y;
+                m.z = v.z > m.z ? v.z : m.z;
+                m.w = v.w > m.w ? v.w : m.w;
+            }
+        }
+    reinterpret_cast<float4 *>(out + (size_t)po * C)[c4] = m;
+}
+
+int pooled(int n) { return (n - 2 + 1) / 2 + 1; }  // ceil((n - 2) / 2) + 1
+
+}  // namespace
+
+void nct_vgg_free(nct_ctx *ctx)
+{
+    if (!ctx || !ctx->vgg) return;
+    for (int i = 0; i < 13; ++i) {
+        if (ctx->vgg->w[i]) cudaFree(ctx->vgg->w[i]);
+        if (ctx->vgg->b[i]) cudaFree(ctx->vgg->b[i]);
+    }
+    delete ctx->vgg;
+    ctx->vgg = nullptr;
+}
+
+extern "C" {
+
+int nct_vgg19_num_layers(void) { return 13; }
+
+const char *nct_vgg19_layer_name(int layer) { return (layer >= 0 && layer < 13) ? kTrunk[layer].name : nullptr; }
+
+int nct_vgg19_layer_shape(int layer, int *cin, int *cout)
+{
+    if (layer < 0 || layer >= 13) return NCT_ERR_ARG;
+    if (cin) *cin = kTrunk[layer].cin;
+    if (cout) *cout = kTrunk[layer].cout;
+    return NCT_OK;
+}
+
+int nct_vgg19_set_weights(nct_ctx *ctx, int layer, const float *w_oihw_host, const float *bias_host)
+{
+    if (!ctx) return NCT_ERR_ARG;
+    NCT_REQUIRE(ctx, layer >= 0 && layer < 13 && w_oihw_host && bias_host, "bad arguments");
+    if (!ctx->vgg) ctx->vgg = new VggState();
+    const int cin = kTrunk[layer].cin, cout = kTrunk[layer].cout;
+    std::vector<float> wt((size_t)9 * cin * cout);
+    for (int o = 0; o < cout; ++o)
+        for (int i = 0; i < cin; ++i)
+            for (int t = 0; t < 9; ++t) wt[((size_t)t * cin + i) * cout + o] = w_oihw_host[((size_t)o * cin + i) * 9 + t];
+    VggState *v = ctx->vgg;
+    if (!v->w[layer]) NCT_CUDA(ctx, cudaMalloc(&v->w[layer], wt.size() * sizeof(float)));
+    if (!v->b[layer]) NCT_CUDA(ctx, cudaMalloc(&v->b[layer], cout * sizeof(float)));
+    NCT_CUDA(ctx, cudaMemcpy(v->w[layer], wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+    NCT_CUDA(ctx, cudaMemcpy(v->b[layer], bias_host, cout * sizeof(float), cudaMemcpyHostToDevice));
+    v->have[layer] = true;
+    return NCT_OK;
+}
+
+int nct_vgg19_level_dims(int h, int w, int dims[5][3])
+{
+    if (!dims || h <= 0 || w <= 0) return NCT_ERR_ARG;
+    const int ch[5] = {512, 512, 256, 128, 64};
+    int hh = h, ww = w;
+    for (int l = 4; l >= 0; --l) {
+        dims[l][0] = ch[l];
+        dims[l][1] = hh;
+        dims[l][2] = ww;
+        hh = pooled(hh);
+        ww = pooled(ww);
+    }
+    return NCT_OK;
+}
+
+int nct_vgg19_features(nct_ctx *ctx, const uint8_t *bgr_dev, int h, int w, int deepest_level, float *feat_dev[5])
+{
+    if (!ctx) return NCT_ERR_ARG;
+    NCT_REQUIRE(ctx, bgr_dev && feat_dev && h >= 16 && w >= 16, "bad arguments (image must be at least 16 x 16)");
+    NCT_REQUIRE(ctx, deepest_level >= 0 && deepest_level <= 4, "deepest_level must be in [0, 4] (0 = conv5_1)");
+    VggState *v = ctx->vgg;
+    NCT_REQUIRE(ctx, v != nullptr, "VGG-19 weights not loaded");
+    int last_layer = 0;
+    for (int i = 0; i < 13; ++i)
+        if (kTrunk[i].level >= deepest_level && kTrunk[i].level >= 0) last_layer = i > last_layer ? i : last_layer;
+    for (int i = 0; i <= last_layer; ++i)
+        if (!v->have[i]) return nct_fail(ctx, NCT_ERR_STATE, "weights of %s not loaded", kTrunk[i].name);
+    for (int l = deepest_level; l <= 4; ++l) NCT_REQUIRE(ctx, feat_dev[l] != nullptr, "feat_dev[%d] is null", l);
+
+    const size_t max_act = (size_t)h * w * 64;  // largest activation: conv1_x
+    float *buf0 = (float *)nct_scratch(ctx, "vgg_act0", sizeof(float) * max_act);
+    float *buf1 = (float *)nct_scratch(ctx, "vgg_act1", sizeof(float) * max_act);
+    float *inp = (float *)nct_scratch(ctx, "vgg_input", sizeof(float) * (size_t)h * w * 3);
+    if (!buf0 || !buf1 || !inp) return NCT_ERR_NOMEM;
+    preprocess_kernel<<<nct_div_up(h * w, 256), 256, 0, ctx->stream>>>(bgr_dev, inp, h * w);
+    NCT_CHECK_LAUNCH(ctx);
+
+    int H = h, W = w;
+    const float *cur = inp;
+    float *bufs[2] = {buf0, buf1};
+    int flip = 0;
+    for (int i = 0; i <= last_layer; ++i) {
+        const ConvSpec &L = kTrunk[i];
+        if (L.pool_before) {
+            const int Ho = pooled(H), Wo = pooled(W);
+            float *dst = bufs[flip];
+            flip ^= 1;
+            const long long threads = (long long)Ho * Wo * (L.cin / 4);
+            maxpool_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(cur, dst, H, W, L.cin, Ho, Wo);
+            NCT_CHECK_LAUNCH(ctx);
+            cur = dst;
+            H = Ho;
+            W = Wo;
+        }
+        float *dst = (L.level >= 0) ? feat_dev[L.level] : bufs[flip];
+        if (L.level < 0) flip ^= 1;
+        if (dst == cur) return nct_fail(ctx, NCT_ERR_STATE, "internal: aliasing activation buffers");
+        if (i == 0) {
+            conv_first_kernel<<<nct_div_up(H * W * 4, 256), 256, 0, ctx->stream>>>(cur, v->w[0], v->b[0], dst, H, W);
+        } else {
+            dim3 grid(nct_div_up(H * W, BM), L.cout / BN);
+            conv3x3_kernel<<<grid, 256, 0, ctx->stream>>>(cur, v->w[i], v->b[i], dst, H, W, L.cin, L.cout);
+        }
+        NCT_CHECK_LAUNCH(ctx);
+        cur = dst;
+    }
+    return NCT_OK;
+}
+
+}  // extern "C"

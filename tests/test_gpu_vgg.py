@@ -1,0 +1,79 @@
+"""GPU parity tests of the VGG-19 trunk against oracle/vgg.py (FP32, tolerance like Caffe's own conv test: 1e-4)."""
+import numpy as np
+import pytest
+
+from oracle import synth, vgg
+
+pytestmark = pytest.mark.gpu
+
+
+def to_dev(x, dev):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return synth.vgg19_weights(19)
+
+
+@pytest.fixture(scope="module")
+def vctx(pkg, weights):
+    c = pkg.Context(0)
+    c.load_vgg19_weights(weights)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("h,w", [(64, 48), (97, 131), (256, 256)])
+def test_vgg19_features_match_oracle(vctx, dev, weights, h, w):
+    img, _ = synth.pair(0, h, w)
+    feats = vctx.predict(to_dev(img, dev), 0)
+    vctx.synchronize()
+    ref = vgg.features(img, weights, 0)
+    dims = vctx.level_dims(h, w)
+    for l in range(5):
+        g = feats[l].cpu().numpy()
+        assert g.shape == ref[l].shape == (dims[l][1], dims[l][2], dims[l][0])
+        scale = np.abs(ref[l]).max()
+        err = np.abs(g - ref[l]).max() / scale
+        assert err < 1e-4, f"level {l}: max error {err:.2e} of the feature range"
+        assert (g >= 0).all()  # post-ReLU
+
+
+def test_vgg19_im2col_oracle_agrees_with_direct(weights):
+    img, _ = synth.pair(1, 40, 36)
+    a = vgg.features(img, weights, 0)
+    b = vgg.features(img, weights, 0, im2col=True)
+    for l in range(5):
+        assert np.abs(a[l] - b[l]).max() / np.abs(a[l]).max() < 1e-5
+
+
+@pytest.mark.parametrize("deepest", [1, 2, 3, 4])
+def test_truncated_forward_equals_full_forward(vctx, dev, deepest):
+    img, _ = synth.pair(2, 80, 72)
+    t = to_dev(img, dev)
+    full = vctx.predict(t, 0)
+    part = vctx.predict(t, deepest)
+    vctx.synchronize()
+    for l in range(5):
+        if l < deepest:
+            assert part[l] is None
+        else:
+            assert np.array_equal(part[l].cpu().numpy(), full[l].cpu().numpy())
+
+
+def test_level_dims_ceil_mode(vctx):
+    assert [d[1] for d in vctx.level_dims(700, 700)] == [44, 88, 175, 350, 700]
+    assert [d[2] for d in vctx.level_dims(520, 352)] == [22, 44, 88, 176, 352]
+    assert [d[0] for d in vctx.level_dims(700, 700)] == [512, 512, 256, 128, 64]
+
+
+def test_missing_weights_fail_loudly(pkg, dev):
+    import torch
+
+    c = pkg.Context(0)
+    with pytest.raises(pkg.NctError):
+        c.predict(torch.zeros((32, 32, 3), dtype=torch.uint8, device=dev))
+    c.close()
