@@ -216,6 +216,36 @@ int nct_cluster_features(nct_ctx *ctx, const float *feat_norm_hwc_dev, int h, in
 int nct_find_knns(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int nlabels, const uint8_t *lab_dev, int h, int w,
                   int samples, int *knn_id_dev, double *knn_w_dev);
 
+/* ---------------------------------------------------------------- per-pair pipeline */
+
+/* Config (CT/Config.h:55-98) + the constants hard-coded in the orchestrator (NCT/main.cu:64-83). */
+typedef struct nct_config {
+    double bds_weight;       /* m_reverseWeight  (-bds, overridden per pair by pairs.txt)  default 2.0   */
+    double var_eps;          /* m_varEpslon      (-eps)                                    default 0.6   */
+    double nonlocal_weight;  /* m_nonlocalWeight (-nl)                                     default 2.0   */
+    double local_weight;     /* m_localWeight    (-l)                                      default 0.125 */
+    double wls_lambda_init;  /* m_wlsLamdaInit   (-w)                                      default 0.024 */
+    int cluster_num;         /* m_clusterNum  10 */
+    int k_num;               /* m_kNum         8 */
+    int patch_size;          /* m_patchSize    3 */
+    double wls_alpha;        /* m_wlsAlpha   1.2 */
+    int pm_iters;            /* params.iter   10 (NCT/main.cu:65) */
+    int kmeans_iters;        /* 11 (CT/ColorTransfer.cpp:373) */
+    double wls_rel_tol;      /* relative residual at which the WLS PCG stops (stands in for PARDISO's exact solve) */
+    int stop_after_level;    /* 4 = full pyramid; smaller values stop early (test hook: intermediates stay in scratch) */
+} nct_config;
+
+void nct_config_default(nct_config *cfg);
+
+/* transfer_color_single_bds(refineCS, classifier_C, classifier_S, config, cnt, stl, preName), NCT/main.cu:47-454:
+ * 8-bit BGR content (ch x cw) and style (sh x sw) -> 8-bit BGR result of the content's size.  VGG-19 weights must
+ * have been loaded.  _dev: all three images are device buffers, asynchronous except for the data-dependent WLS
+ * iteration counts; the host variant copies in, runs, copies out and synchronises.  cfg == NULL -> defaults. */
+int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int cw, const uint8_t *stl_bgr_dev, int sh, int sw,
+                          const nct_config *cfg, uint8_t *out_bgr_dev);
+int nct_transfer_pair(nct_ctx *ctx, const uint8_t *cnt_bgr_host, int ch, int cw, const uint8_t *stl_bgr_host, int sh, int sw,
+                      const nct_config *cfg, uint8_t *out_bgr_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,13 @@ LIB_PATH = os.path.join(_HERE, "libnct.so")
 c_ctx_p = C.c_void_p
 _i, _f, _d, _p, _ll = C.c_int, C.c_float, C.c_double, C.c_void_p, C.c_longlong
 
+class Config(C.Structure):
+    """nct_config (CT/Config.h:55-98 + NCT/main.cu:64-83)"""
+    _fields_ = [("bds_weight", _d), ("var_eps", _d), ("nonlocal_weight", _d), ("local_weight", _d), ("wls_lambda_init", _d),
+                ("cluster_num", _i), ("k_num", _i), ("patch_size", _i), ("wls_alpha", _d), ("pm_iters", _i),
+                ("kmeans_iters", _i), ("wls_rel_tol", _d), ("stop_after_level", _i)]
+
+
 # name -> (restype, argtypes); every symbol include/nct.h declares must be listed here
 # (tests/test_abi.py cross-checks this table against the header).
 ABI = {
@@ -63,9 +70,14 @@ ABI = {
     "nct_vgg19_set_weights": (_i, [c_ctx_p, _i, _p, _p]),
     "nct_vgg19_level_dims": (_i, [_i, _i, C.POINTER(_i * 3)]),
     "nct_vgg19_features": (_i, [c_ctx_p, _p, _i, _i, _i, C.POINTER(_p)]),
+    "nct_config_default": (None, [C.POINTER(Config)]),
+    "nct_transfer_pair_dev": (_i, [c_ctx_p, _p, _i, _i, _p, _i, _i, C.POINTER(Config), _p]),
+    "nct_transfer_pair": (_i, [c_ctx_p, _p, _i, _i, _p, _i, _i, C.POINTER(Config), _p]),
     "nct_cluster_features": (_i, [c_ctx_p, _p, _i, _i, _i, _i, _i, _p]),
     "nct_find_knns": (_i, [c_ctx_p, _p, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
 }
+
+
 
 _lib = None
 
@@ -373,3 +385,35 @@ class Context:
             ptrs[l] = feats[l].data_ptr()
         self._check(self.lib.nct_vgg19_features(self.h, _ptr(img_bgr), h, w, deepest_level, ptrs))
         return feats
+
+    # -- per-pair pipeline
+    def default_config(self, **overrides):
+        cfg = Config()
+        self.lib.nct_config_default(C.byref(cfg))
+        for k, v in overrides.items():
+            setattr(cfg, k, v)
+        return cfg
+
+    def transfer_pair_dev(self, cnt, stl, cfg=None, out=None):
+        """transfer_color_single_bds (NCT/main.cu:47-454) on device-resident uint8 BGR tensors."""
+        import torch
+        ch, cw, _ = cnt.shape
+        sh, sw, _ = stl.shape
+        out = out if out is not None else torch.empty_like(cnt)
+        self._check(self.lib.nct_transfer_pair_dev(self.h, _ptr(cnt), ch, cw, _ptr(stl), sh, sw,
+                                                   C.byref(cfg) if cfg is not None else None, _ptr(out)))
+        return out
+
+    def transfer_pair(self, cnt_host, stl_host, cfg=None, out_host=None):
+        """Host-buffer entry point (what the CLI calls): uint8 BGR host tensors / numpy arrays (pinned preferred)."""
+        import numpy as np
+        import torch
+        def hp(x):
+            return C.c_void_p(x.data_ptr()) if isinstance(x, torch.Tensor) else x.ctypes.data_as(C.c_void_p)
+        ch, cw, _ = cnt_host.shape
+        sh, sw, _ = stl_host.shape
+        if out_host is None:
+            out_host = np.empty((ch, cw, 3), np.uint8)
+        self._check(self.lib.nct_transfer_pair(self.h, hp(cnt_host), ch, cw, hp(stl_host), sh, sw,
+                                               C.byref(cfg) if cfg is not None else None, hp(out_host)))
+        return out_host

@@ -79,7 +79,7 @@ int nct_create(int gpu_id, nct_ctx **out)
 
 // defined by vgg19.cu / pipeline.cu
 extern "C++" void nct_vgg_free(nct_ctx *ctx);
-void nct_pipe_free(nct_ctx *ctx);
+extern "C++" void nct_pipe_free(nct_ctx *ctx);
 
 int nct_destroy(nct_ctx *ctx)
 {

@@ -1,0 +1,139 @@
+"""oracle/pipeline.py -- CPU restatement of transfer_color_single_bds (NCT/main.cu:47-454), composed from the
+per-stage oracles.  TEST / BASELINE INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+`transfer_pair` is also the "port" CPU baseline of bench.py (cpu_baseline / --impl reference): VGG as im2col + SGEMM
+(torch-CPU), PatchMatch / votes / clustering / k-NN in C with OpenMP, colour solves with scipy -- the reference's own
+CPU-side algorithmic structure.
+
+Hooks: `features_fn(image_bgr, deepest_level)` lets a test inject feature maps (e.g. the GPU's) so the downstream
+stages can be compared in lock step; `on_level(level, dict)` receives every intermediate of a level.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import color, vgg
+from . import pm as _pm
+
+
+def level_dims(h, w):
+    ch = [512, 512, 256, 128, 64]
+    dims = [None] * 5
+    for l in range(4, -1, -1):
+        dims[l] = (ch[l], h, w)
+        h = -(-(h - 2) // 2) + 1
+        w = -(-(w - 2) // 2) + 1
+    return dims
+
+
+DEFAULT_CFG = dict(bds=2.0, eps=0.6, nl=2.0, l=0.125, w=0.024, clusters=10, knum=8, alpha=1.2, pm_iters=10, kmeans_iters=11)
+
+
+def transfer_pair(cnt, stl, weights=None, cfg=None, features_fn=None, on_level=None, stop_after_level=4, timings=None,
+                  im2col=True, pm_mode="canonical", result_hook=None):
+    """cnt, stl: uint8 BGR (H, W, 3).  Returns the uint8 BGR result (content size).
+    pm_mode: "canonical" = deterministic jump-flood oracle (the parity target); "reference" = reference-semantics
+    in-place serial PatchMatch in the reference's layout / summation order (CPU baseline only)."""
+    cfg = DEFAULT_CFG | (cfg or {})
+    t_acc = timings if timings is not None else {}
+
+    def tick(name, t0):
+        t_acc[name] = t_acc.get(name, 0.0) + time.perf_counter() - t0
+
+    if features_fn is None:
+        def features_fn(img, deepest):
+            return vgg.features(img, weights, deepest, im2col=im2col)
+
+    ch, cw, _ = cnt.shape
+    sh, sw, _ = stl.shape
+    dc, ds = level_dims(ch, cw), level_dims(sh, sw)
+    max_len = max(cw, ch, sw, sh)
+    rng = [max_len // 16, max_len // 32, max_len // 64, 32, 32]
+    cnt_lab_full_d = color.bgr2lab_u8(cnt).astype(np.float64) * (1.0 / 255.0)
+
+    t0 = time.perf_counter()
+    featC = features_fn(cnt, 0)
+    featS = features_fn(stl, 0)
+    tick("vgg", t0)
+    cnt_imgs = color.pyramid(cnt, [(d[1], d[2]) for d in dc])
+    stl_imgs = color.pyramid(stl, [(d[1], d[2]) for d in ds])
+
+    t0 = time.perf_counter()
+    nC0 = _pm.l2norm_hwc(featC[0])
+    labels, nlabels = _pm.kmeans_labels(nC0.reshape(-1, dc[0][0]), cfg["clusters"], cfg["kmeans_iters"])
+    tick("kmeans", t0)
+
+    ann = bnn = None
+    result = cnt
+    for l in range(5):
+        Cn, ah, aw = dc[l]
+        _, bh, bw = ds[l]
+        t0 = time.perf_counter()
+        if l == 0:
+            ann = _pm.nnf_init(ah, aw, bh, bw)
+            bnn = _pm.nnf_init(bh, bw, ah, aw)
+        else:
+            ann = _pm.nnf_upsample(ann, dc[l - 1][1], dc[l - 1][2], ah, aw, bh, bw)
+            bnn = _pm.nnf_upsample(bnn, ds[l - 1][1], ds[l - 1][2], bh, bw, ah, aw)
+        nS = _pm.l2norm_hwc(featS[l])
+        nC = _pm.l2norm_hwc(featC[l])
+        p_ab = _pm.make_params(Cn, ah, aw, bh, bw, cfg["pm_iters"], rng[l])
+        p_ba = _pm.make_params(Cn, bh, bw, ah, aw, cfg["pm_iters"], rng[l])
+        if pm_mode == "canonical":
+            ann, annd, st_a = _pm.patchmatch(nC, nS, ann, p_ab)
+            bnn, bnnd, st_b = _pm.patchmatch(nS, nC, bnn, p_ba)
+        else:
+            nC_chw = np.ascontiguousarray(nC.transpose(2, 0, 1))
+            nS_chw = np.ascontiguousarray(nS.transpose(2, 0, 1))
+            ann, annd = _pm.patchmatch_ref_serial(nC_chw, nS_chw, ann, p_ab)
+            bnn, bnnd = _pm.patchmatch_ref_serial(nS_chw, nC_chw, bnn, p_ba)
+            st_a = st_b = (0, 0)
+        tick("patchmatch", t0)
+        t0 = time.perf_counter()
+        bds_f = float(np.float32(cfg["bds"]))
+        sml = _pm.reconstruct_bds(cnt_imgs[l], stl_imgs[l], ann, bnn, 1.0, bds_f)
+        err = _pm.bds_feature_error(nC, featS[l], ann, bnn, 1.0, bds_f, mode=0)
+        tick("bds", t0)
+        t0 = time.perf_counter()
+        cnt_lab = color.bgr2lab_u8(cnt_imgs[l])
+        knn_id, knn_w = _pm.find_knns(labels, dc[0][2], dc[0][1], cnt_lab, 1 << l, cfg["clusters"])
+        tick("knn", t0)
+        t0 = time.perf_counter()
+        stl_lab = color.bgr2lab_u8(sml)
+        a0, b0 = color.local_fit(cnt_lab, stl_lab, cfg["eps"])
+        weight = color.confidence_weights(err.reshape(ah, aw))
+        norm_factor = float(cw * ch) / float(aw * ah)
+        lam = cfg["w"] * norm_factor
+        a1, b1, its = color.solve_nonlocal(a0, b0, weight, cnt_lab * (1.0 / 255.0), stl_lab * (1.0 / 255.0), knn_id, knn_w, l,
+                                           cfg["l"], cfg["alpha"], cfg["nl"], cfg["knum"], norm_factor)
+        tick("nonlocal", t0)
+        t0 = time.perf_counter()
+        a2, b2, rough = color.upsample_coefficients(a1, b1, cnt_lab_full_d, cw, ch)
+        if ah == ch and aw == cw:
+            lam = lam * 4
+        a3, b3 = color.solve_wls(a2, b2, rough, cnt_lab_full_d[..., 0], lam, cfg["alpha"])
+        result = color.apply_coefficients(cnt_lab_full_d, a3, b3)
+        tick("wls", t0)
+        if on_level is not None:
+            on_level(l, dict(ann=ann, annd=annd, bnn=bnn, bnnd=bnnd, sml=sml, err=err, knn_id=knn_id, knn_w=knn_w, a0=a0, b0=b0,
+                             weight=weight, a1=a1, b1=b1, a2=a2, b2=b2, rough=rough, a3=a3, b3=b3, result=result, cg_iters=its,
+                             lam=lam, evals=(st_a, st_b), labels=labels, nC=nC, nS=nS, cnt_lab=cnt_lab, stl_lab=stl_lab))
+        if result_hook is not None:  # lock-step tests: continue from the implementation-under-test's image
+            result = result_hook(l, result)
+        if l >= stop_after_level:
+            break
+        if l < 4:
+            t0 = time.perf_counter()
+            new = features_fn(result, l + 1)
+            for k in range(l + 1, 5):
+                featC[k] = new[k]
+            tick("vgg", t0)
+    return result
+
+
+def psnr(a, b):
+    d = a.astype(np.float64) - b.astype(np.float64)
+    mse = float((d * d).mean())
+    return float("inf") if mse == 0 else 10.0 * np.log10(255.0 * 255.0 / mse)
