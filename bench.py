@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- megapixels/s of the full L=5->1 colour-transfer pipeline on synthetic 700x700 pairs (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--side 700] [--impl ours|reference]
+
+A "step" = one pass of the hot path (nct_transfer_pair: VGG-19 features -> bidirectional PatchMatch -> BDS votes ->
+clustering/8-NN -> colour least squares -> WLS -> apply, levels 5..1) over one batch = ONE pair per rank.  Pairs are
+independent, so ranks share nothing (weak scaling); NCCL is used only to gather the result images on rank 0.
+
+  value    whole-job MP/s with the inputs already resident in HBM (nct_transfer_pair_dev), CUDA events on the
+           launching stream, barrier + synchronize on both sides, max over ranks
+  e2e      the same through the host-buffer C-ABI call the CLI makes (nct_transfer_pair): pinned host inputs, H2D and
+           D2H copies inside the timed region
+  roofline PatchMatch step kernel (dominant): algorithmic bytes = evaluated candidates x 9 x C x 4 B, divided by the
+           kernel's device time measured with CUDA events inside the timed region (nct_profile_*)
+  cpu_baseline   the oracle "port" of the reference's CPU-side path timed on this box's host cores on a bounded sample
+  --impl reference   the CPU arm: reference-semantics pipeline (in-place serial PatchMatch in the reference's layout and
+           summation order, im2col+SGEMM VGG, scipy solves) on the host cores, bounded sample per step
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PM_CHANNELS = [512, 512, 256, 128, 64]
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, sustained copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_pipeline_mps(side, pm_mode, threads):
+    """one pair of side x side through the oracle pipeline on the host cores -> (MP/s, seconds, stage seconds)"""
+    import torch
+
+    from oracle import pipeline, synth
+
+    torch.set_num_threads(threads)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    w = synth.vgg19_weights(19)
+    cnt, stl = synth.pair(0, side, side)
+    t = {}
+    t0 = time.perf_counter()
+    pipeline.transfer_pair(cnt, stl, w, timings=t, im2col=True, pm_mode=pm_mode)
+    dt = time.perf_counter() - t0
+    return side * side / 1e6 / dt, dt, {k: round(v, 3) for k, v in t.items()}
+
+
+def run_reference(args):
+    """CPU arm: the reference's own algorithmic path restated on the host (the reference binary cannot be built here:
+    Windows-only sources, Caffe, OpenCV 2.4.10, MKL PARDISO, legacy cuSPARSE -- DESIGN.md section 7)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = len(os.sched_getaffinity(0))
+    sample_side = args.cpu_side
+    vals = []
+    for i in range(args.warmup + args.steps):
+        mps, dt, stages = cpu_pipeline_mps(sample_side, "reference", threads)
+        if i >= args.warmup:
+            vals.append((mps, dt, stages))
+    mps = sum(v[0] for v in vals) / len(vals)
+    ms = 1e3 * sum(v[1] for v in vals) / len(vals)
+    sample = f"one {sample_side}x{sample_side} synthetic pair per step, full L=5->1 pipeline (bounded sample of the {args.side}x{args.side} workload)"
+    line = {
+        "impl": "reference", "metric": "MP/s full L=5->1 pipeline", "value": round(mps, 5), "unit": "MP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "config": {"workload": f"single {args.side}x{args.side} pair, full L=5->1 pyramid, BDS=2.0", "cpu_sample": sample},
+        "cpu_baseline": {"value": round(mps, 5), "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample,
+                         "stage_seconds": vals[-1][2]},
+        "e2e": {"value": round(mps, 5), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as g
+    from oracle import synth  # synthetic inputs only (numpy); no oracle compute on this path
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    pkg = g.load_package()
+    stream = torch.cuda.Stream(device=dev)
+    ctx = pkg.Context(local, stream)
+    ctx.load_vgg19_weights(synth.vgg19_weights(19))
+    side = args.side
+    npairs = 2  # two distinct pairs per rank, alternated, so no step re-reads the previous step's data
+    pairs = [synth.pair(rank * npairs + j, side, side) for j in range(npairs)]
+    dev_pairs = [(torch.from_numpy(c).to(dev), torch.from_numpy(s).to(dev)) for c, s in pairs]
+    pin_pairs = [(torch.from_numpy(c).pin_memory(), torch.from_numpy(s).pin_memory()) for c, s in pairs]
+    out_dev = torch.empty((side, side, 3), dtype=torch.uint8, device=dev)
+    out_pin = torch.empty((side, side, 3), dtype=torch.uint8).pin_memory()
+    gather_list = [torch.empty_like(out_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    cfg = ctx.default_config()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def gather():
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.gather(out_dev, gather_list, dst=0)
+
+    # ---- device-resident steps
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            ctx.transfer_pair_dev(*dev_pairs[i % npairs], cfg, out_dev)
+            gather()
+        stream.synchronize()
+        # PatchMatch evaluation counts for the roofline: one untimed pass with the kernel's counters on
+        # (deterministic, so the timed steps evaluate exactly the same candidates)
+        evals_bytes = []
+        for j in range(npairs):
+            tot = 0
+            # counters are per PatchMatch call; run level by level through the pipeline's own stop hook
+            prev = 0
+            ctx.count_evals(True)
+            for l in range(5):
+                ctx.transfer_pair_dev(*dev_pairs[j], ctx.default_config(stop_after_level=l), out_dev)
+                ev, _ = ctx.patchmatch_stats()
+                tot += ev * 9 * PM_CHANNELS[l] * 4
+            ctx.count_evals(False)
+            evals_bytes.append(tot)
+        sampler = ClockSampler(local)
+        sampler.start()
+        barrier()
+        ctx.profile(True)
+        ctx.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            ctx.transfer_pair_dev(*dev_pairs[i % npairs], cfg, out_dev)
+            gather()
+        e1.record(stream)
+        stream.synchronize()
+        barrier()
+        sampler.stop_flag = True
+        dev_ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count
+        prof = ctx.profile_report()
+        ctx.profile(False)
+
+        # ---- end to end through the host-buffer C-ABI entry point (pinned host buffers, H2D + D2H inside)
+        for i in range(min(args.warmup, 2)):
+            ctx.transfer_pair(*pin_pairs[i % npairs], cfg, out_pin)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            ctx.transfer_pair(*pin_pairs[i % npairs], cfg, out_pin)
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        barrier()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    mp_per_step = world * side * side / 1e6
+    value = mp_per_step * args.steps / (dev_ms / 1e3)
+    e2e = mp_per_step * args.steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        pm_ms, pm_spans = prof["patchmatch"]
+        pm_bytes = sum(evals_bytes[i % npairs] for i in range(args.steps))
+        pm_launches = pm_spans * 4 * cfg.pm_iters
+        achieved = pm_bytes / 1e9 / (pm_ms / 1e3) if pm_ms > 0 else None
+        line = {
+            "metric": "MP/s full L=5->1 pipeline", "value": round(value, 4), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (features, PatchMatch) / f64 (colour solves) / u8 (images)", "data": "synthetic",
+            "config": {"workload": f"single {side}x{side} pair per GPU per step, full L=5->1 pyramid, BDS=2.0 (BASELINE configs[1])",
+                       "pairs_per_step": world, "l2_policy": "inputs larger than L2: ~1.1 GB working set per pair, two alternating pairs",
+                       "vgg_weights": "synthetic He-normal (seed 19)", "collective": "NCCL gather of result images to rank 0" if world > 1 else "none"},
+            "e2e": {"value": round(e2e, 4), "unit": "MP/s", "h2d_bytes_per_step": 2 * side * side * 3, "d2h_bytes_per_step": side * side * 3,
+                    "ms_per_step": round(e2e_ms / args.steps, 2)},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "pm_step_kernel (PatchMatch propagate + random search)", "bound": "hbm",
+                         "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 3) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "launches": int(pm_launches), "avg_launch_ms": round(pm_ms / max(pm_launches, 1), 4),
+                         "algorithmic_GB_per_pair": round(evals_bytes[0] / 1e9, 1)},
+            "stage_ms_per_step": {k: round(v[0] / args.steps, 2) for k, v in prof.items()},
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = len(os.sched_getaffinity(0))
+            mps, dt, stages = cpu_pipeline_mps(args.cpu_side, "canonical", threads)
+            line["cpu_baseline"] = {"value": round(mps, 5), "unit": "MP/s", "cores": threads, "kind": "port",
+                                    "sample": f"one {args.cpu_side}x{args.cpu_side} synthetic pair, full L=5->1 pipeline, {dt:.1f} s",
+                                    "stage_seconds": stages}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--side", type=int, default=700)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-side", type=int, default=256, help="side of the bounded CPU sample pair")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

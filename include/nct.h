@@ -58,6 +58,14 @@ int nct_version(void);
 long long nct_launch_count(const nct_ctx *ctx);
 void nct_reset_launch_count(nct_ctx *ctx);
 
+/* Stage timing of nct_transfer_pair* (CUDA events recorded on the ctx stream around each stage; the spans are
+ * resolved when nct_profile_get is called, which synchronises).  Stages: 0 vgg, 1 patchmatch, 2 bds, 3 knn,
+ * 4 nonlocal_cg, 5 wls, 6 misc, 7 kmeans.  ms_out = accumulated device milliseconds, spans_out = timed spans. */
+int nct_profile_enable(nct_ctx *ctx, int enable);
+int nct_profile_reset(nct_ctx *ctx);
+int nct_profile_get(nct_ctx *ctx, int stage, double *ms_out, long long *spans_out);
+const char *nct_profile_stage_name(int stage);
+
 /* Test hook: copy `bytes` of the named internal scratch buffer to host (synchronises).  Lets parity tests feed
  * the kernel's own intermediate arrays (e.g. "nl_d2", "nl_wx2", "nl_wy2", "nl_kw2") to the oracle. */
 int nct_debug_read_scratch(nct_ctx *ctx, const char *name, void *host_dst, size_t bytes);

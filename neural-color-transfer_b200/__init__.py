@@ -41,6 +41,10 @@ ABI = {
     "nct_version": (_i, []),
     "nct_launch_count": (_ll, [c_ctx_p]),
     "nct_reset_launch_count": (None, [c_ctx_p]),
+    "nct_profile_enable": (_i, [c_ctx_p, _i]),
+    "nct_profile_reset": (_i, [c_ctx_p]),
+    "nct_profile_get": (_i, [c_ctx_p, _i, C.POINTER(_d), C.POINTER(_ll)]),
+    "nct_profile_stage_name": (C.c_char_p, [_i]),
     "nct_debug_read_scratch": (_i, [c_ctx_p, C.c_char_p, _p, C.c_size_t]),
     "nct_chw_to_hwc": (_i, [c_ctx_p, _p, _p, _i, _i, _i]),
     "nct_hwc_to_chw": (_i, [c_ctx_p, _p, _p, _i, _i, _i]),
@@ -173,6 +177,19 @@ class Context:
 
     def reset_launch_count(self):
         self.lib.nct_reset_launch_count(self.h)
+
+    def profile(self, enable=True):
+        self._check(self.lib.nct_profile_enable(self.h, 1 if enable else 0))
+        self._check(self.lib.nct_profile_reset(self.h))
+
+    def profile_report(self):
+        """{stage name: (device ms, spans)} accumulated since the last profile()/reset"""
+        out = {}
+        for st in range(8):
+            ms, n = _d(0), _ll(0)
+            self._check(self.lib.nct_profile_get(self.h, st, C.byref(ms), C.byref(n)))
+            out[self.lib.nct_profile_stage_name(st).decode()] = (ms.value, n.value)
+        return out
 
     def read_scratch(self, name, dtype, count):
         """test hook: copy an internal scratch buffer to a numpy array"""

@@ -37,7 +37,69 @@ void *nct_scratch(nct_ctx *ctx, const char *name, size_t bytes)
     return p;
 }
 
+NctStageTimer::NctStageTimer(nct_ctx *c, int stage) : ctx(c)
+{
+    if (!c || !c->profile) return;
+    nct_ctx::ProfSpan sp;
+    sp.stage = stage;
+    auto get = [&]() {
+        cudaEvent_t e;
+        if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    };
+    sp.e0 = get();
+    sp.e1 = get();
+    cudaEventRecord(sp.e0, c->stream);
+    idx = (int)c->prof_spans.size();
+    c->prof_spans.push_back(sp);
+}
+
+NctStageTimer::~NctStageTimer()
+{
+    if (idx >= 0) cudaEventRecord(ctx->prof_spans[idx].e1, ctx->stream);
+}
+
 extern "C" {
+
+int nct_profile_enable(nct_ctx *ctx, int enable)
+{
+    if (!ctx) return NCT_ERR_ARG;
+    ctx->profile = enable ? 1 : 0;
+    return NCT_OK;
+}
+
+int nct_profile_reset(nct_ctx *ctx)
+{
+    if (!ctx) return NCT_ERR_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &sp : ctx->prof_spans) { ctx->prof_pool.push_back(sp.e0); ctx->prof_pool.push_back(sp.e1); }
+    ctx->prof_spans.clear();
+    for (int i = 0; i < 16; ++i) { ctx->prof_ms[i] = 0; ctx->prof_calls[i] = 0; }
+    return NCT_OK;
+}
+
+int nct_profile_get(nct_ctx *ctx, int stage, double *ms_out, long long *spans_out)
+{
+    if (!ctx || stage < 0 || stage >= ST_COUNT) return NCT_ERR_ARG;
+    NCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &sp : ctx->prof_spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) { ctx->prof_ms[sp.stage] += ms; ctx->prof_calls[sp.stage] += 1; }
+        ctx->prof_pool.push_back(sp.e0);
+        ctx->prof_pool.push_back(sp.e1);
+    }
+    ctx->prof_spans.clear();
+    if (ms_out) *ms_out = ctx->prof_ms[stage];
+    if (spans_out) *spans_out = ctx->prof_calls[stage];
+    return NCT_OK;
+}
+
+const char *nct_profile_stage_name(int stage)
+{
+    static const char *names[ST_COUNT] = {"vgg", "patchmatch", "bds", "knn", "nonlocal_cg", "wls", "misc", "kmeans"};
+    return (stage >= 0 && stage < ST_COUNT) ? names[stage] : nullptr;
+}
 
 int nct_version(void) { return 100; }
 
@@ -88,6 +150,8 @@ int nct_destroy(nct_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     nct_pipe_free(ctx);
     nct_vgg_free(ctx);
+    for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
+    for (auto &e : ctx->prof_pool) cudaEventDestroy(e);
     for (auto &kv : ctx->scratch)
         if (kv.second.ptr) cudaFree(kv.second.ptr);
     if (ctx->pm_counters) cudaFree(ctx->pm_counters);

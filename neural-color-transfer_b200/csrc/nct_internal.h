@@ -31,6 +31,14 @@ struct nct_ctx {
     int pm_count_evals = 0;
     unsigned long long *pm_counters = nullptr;  // device, 2 x u64
 
+    // optional stage timing (CUDA events on ctx->stream), see nct_profile_*
+    int profile = 0;
+    struct ProfSpan { int stage; cudaEvent_t e0, e1; };
+    std::vector<ProfSpan> prof_spans;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[16] = {0};
+    long long prof_calls[16] = {0};
+
     // opaque sub-module states (owned, freed in nct_destroy)
     struct VggState *vgg = nullptr;
     struct PipeState *pipe = nullptr;
@@ -61,5 +69,14 @@ void *nct_scratch(nct_ctx *ctx, const char *name, size_t bytes);
     do {                                                                                             \
         if (!(cond)) return nct_fail((ctx), NCT_ERR_ARG, __VA_ARGS__);                               \
     } while (0)
+
+enum NctStage { ST_VGG = 0, ST_PM, ST_BDS, ST_KNN, ST_CG, ST_WLS, ST_MISC, ST_KMEANS, ST_COUNT };
+// RAII stage timer: records two events on the ctx stream when profiling is on
+struct NctStageTimer {
+    nct_ctx *ctx;
+    int idx = -1;
+    NctStageTimer(nct_ctx *c, int stage);
+    ~NctStageTimer();
+};
 
 static inline int nct_div_up(int a, int b) { return (a + b - 1) / b; }

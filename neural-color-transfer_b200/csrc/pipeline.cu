@@ -119,8 +119,11 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
     // ---- ColorTransfer ctor: m_cntLab (CT/ColorTransfer.h:54-60)
     STEP(nct_bgr2lab_u8(ctx, cnt_bgr_dev, cntLabFull, (int)nC));
     // ---- features of both images (NCT/main.cu:94,102)
-    STEP(nct_vgg19_features(ctx, cnt_bgr_dev, ch, cw, 0, featC));
-    STEP(nct_vgg19_features(ctx, stl_bgr_dev, sh, sw, 0, featS));
+    {
+        NctStageTimer t(ctx, ST_VGG);
+        STEP(nct_vgg19_features(ctx, cnt_bgr_dev, ch, cw, 0, featC));
+        STEP(nct_vgg19_features(ctx, stl_bgr_dev, sh, sw, 0, featS));
+    }
     // ---- image pyramids from the ORIGINAL images (NCT/main.cu:104-108)
     NCT_CUDA(ctx, cudaMemcpyAsync(cntImg[4], cnt_bgr_dev, nC * 3, cudaMemcpyDeviceToDevice, ctx->stream));
     NCT_CUDA(ctx, cudaMemcpyAsync(stlImg[4], stl_bgr_dev, nS * 3, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -130,7 +133,8 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
     }
     // ---- cluster the normalised conv5_1 features of the content image (NCT/main.cu:139-168)
     STEP(nct_l2norm(ctx, featC[0], normC, dc[0][0], dc[0][1], dc[0][2]));
-    STEP(nct_cluster_features(ctx, normC, dc[0][1], dc[0][2], dc[0][0], cfg.cluster_num, cfg.kmeans_iters, labels));
+    { NctStageTimer t(ctx, ST_KMEANS);
+    STEP(nct_cluster_features(ctx, normC, dc[0][1], dc[0][2], dc[0][0], cfg.cluster_num, cfg.kmeans_iters, labels)); }
 
     const uint8_t *result = cnt_bgr_dev;
     for (int l = 0; l < L; ++l) {
@@ -150,30 +154,33 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
         STEP(nct_l2norm(ctx, featC[l], normC, C, ah, aw));
         // bidirectional PatchMatch (:283-284)
         const int params[11] = {C, ah, aw, bh, bw, cfg.patch_size, cfg.pm_iters, range[l], 0, 10, 1};
-        STEP(nct_patchmatch_bidir(ctx, normC, normS, ann, annd, bnn, bnnd, params));
+        { NctStageTimer t(ctx, ST_PM); STEP(nct_patchmatch_bidir(ctx, normC, normS, ann, annd, bnn, bnnd, params)); }
         // BDS colour reconstruction at level size (:291) and BDS feature error (:297-318)
+        { NctStageTimer t(ctx, ST_BDS);
         STEP(nct_reconstruct_bds(ctx, cntImg[l], stlImg[l], ann, bnn, ah, aw, bh, bw, 1.0, (double)(float)cfg.bds_weight, smlRes));
-        STEP(nct_bds_feature_error(ctx, normC, featS[l], ann, bnn, C, ah, aw, bh, bw, 1.0f, (float)cfg.bds_weight, err, nullptr));
+        STEP(nct_bds_feature_error(ctx, normC, featS[l], ann, bnn, C, ah, aw, bh, bw, 1.0f, (float)cfg.bds_weight, err, nullptr)); }
         // Lab images of the level (:351-375)
         STEP(nct_bgr2lab_u8(ctx, cntImg[l], cntLab, ah * aw));
         STEP(nct_bgr2lab_u8(ctx, smlRes, stlLab, ah * aw));
         // non-local neighbours (:359); label cells are 2^l pixels wide
-        STEP(nct_find_knns(ctx, labels, dc[0][2], dc[0][1], cfg.cluster_num, cntLab, ah, aw, 1 << l, knn_id, knn_w));
+        { NctStageTimer t(ctx, ST_KNN); STEP(nct_find_knns(ctx, labels, dc[0][2], dc[0][1], cfg.cluster_num, cntLab, ah, aw, 1 << l, knn_id, knn_w)); }
         // transfer_color_downsample (CT/ColorTransfer.cpp:1180-1478)
         STEP(nct_local_fit(ctx, cntLab, stlLab, ah, aw, cfg.var_eps, a_lvl, b_lvl));
         STEP(nct_confidence_weights(ctx, err, ah * aw, weight));
         const double normFactor = (double)(cw * ch) / (double)(aw * ah);
         double lam = cfg.wls_lambda_init * normFactor;
+        { NctStageTimer t(ctx, ST_CG);
         STEP(nct_solve_nonlocal(ctx, a_lvl, b_lvl, weight, cntLab, stlLab, knn_id, knn_w, ah, aw, l, cfg.local_weight, cfg.wls_alpha,
-                                cfg.nonlocal_weight, cfg.k_num, normFactor, nullptr));
+                                cfg.nonlocal_weight, cfg.k_num, normFactor, nullptr)); }
         STEP(nct_upsample_coefficients(ctx, a_lvl, b_lvl, ah, aw, cntLabFull, ch, cw, a_full, b_full, rough));
         if (ah == ch && aw == cw) lam = lam * 4;
-        STEP(nct_solve_wls(ctx, a_full, b_full, rough, cntLabFull, ch, cw, lam, cfg.wls_alpha, cfg.wls_rel_tol, 0, nullptr, nullptr));
+        { NctStageTimer t(ctx, ST_WLS);
+        STEP(nct_solve_wls(ctx, a_full, b_full, rough, cntLabFull, ch, cw, lam, cfg.wls_alpha, cfg.wls_rel_tol, 0, nullptr, nullptr)); }
         STEP(nct_apply_coefficients(ctx, cntLabFull, a_full, b_full, ch, cw, refine, nullptr));
         result = refine;
         if (l >= cfg.stop_after_level) break;
         // re-extract the content features from the intermediate result (:424-427), only as deep as still needed
-        if (l < L - 1) STEP(nct_vgg19_features(ctx, refine, ch, cw, l + 1, featC));
+        if (l < L - 1) { NctStageTimer t(ctx, ST_VGG); STEP(nct_vgg19_features(ctx, refine, ch, cw, l + 1, featC)); }
     }
 #undef STEP
     NCT_CUDA(ctx, cudaMemcpyAsync(out_bgr_dev, result, nC * 3, cudaMemcpyDeviceToDevice, ctx->stream));
