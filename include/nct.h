@@ -182,6 +182,12 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
                   int H, int W, double lam, double alpha, double rel_tol, int max_iters, int *iters_out,
                   double *rel_res_out);
 
+/* Same system solved by Jacobi-preconditioned CG (thousands of iterations; kept as an independent cross-check of
+ * the multigrid solver above). */
+int nct_solve_wls_jacobi(nct_ctx *ctx, double *a_dev, double *b_dev, const double *rough_dev,
+                         const uint8_t *cnt_lab_full_dev, int H, int W, double lam, double alpha, double rel_tol,
+                         int max_iters, int *iters_out, double *rel_res_out);
+
 /* res = clamp(Lab a + b, 0, 1) -> convertTo(8U, 255) -> Lab2BGR (CT/ColorTransfer.cpp:1436-1469).
  * out_lab_dev may be NULL. */
 int nct_apply_coefficients(nct_ctx *ctx, const uint8_t *cnt_lab_full_dev, const double *a_dev, const double *b_dev,
@@ -253,6 +259,11 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
                           const nct_config *cfg, uint8_t *out_bgr_dev);
 int nct_transfer_pair(nct_ctx *ctx, const uint8_t *cnt_bgr_host, int ch, int cw, const uint8_t *stl_bgr_host, int sh, int sw,
                       const nct_config *cfg, uint8_t *out_bgr_host);
+
+/* The same search by exhaustive comparison inside each cluster (O(sum of squared cluster sizes)); independent
+ * cross-check of the grid search above. */
+int nct_find_knns_brute(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int nlabels, const uint8_t *lab_dev, int h,
+                        int w, int samples, int *knn_id_dev, double *knn_w_dev);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,7 @@ ABI = {
     "nct_solve_nonlocal": (_i, [c_ctx_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _d, _d, _d, _i, _d, C.POINTER(_i)]),
     "nct_upsample_coefficients": (_i, [c_ctx_p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p]),
     "nct_solve_wls": (_i, [c_ctx_p, _p, _p, _p, _p, _i, _i, _d, _d, _d, _i, C.POINTER(_i), C.POINTER(_d)]),
+    "nct_solve_wls_jacobi": (_i, [c_ctx_p, _p, _p, _p, _p, _i, _i, _d, _d, _d, _i, C.POINTER(_i), C.POINTER(_d)]),
     "nct_apply_coefficients": (_i, [c_ctx_p, _p, _p, _p, _i, _i, _p, _p]),
     "nct_vgg19_num_layers": (_i, []),
     "nct_vgg19_layer_name": (C.c_char_p, [_i]),
@@ -79,6 +80,7 @@ ABI = {
     "nct_transfer_pair": (_i, [c_ctx_p, _p, _i, _i, _p, _i, _i, C.POINTER(Config), _p]),
     "nct_cluster_features": (_i, [c_ctx_p, _p, _i, _i, _i, _i, _i, _p]),
     "nct_find_knns": (_i, [c_ctx_p, _p, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
+    "nct_find_knns_brute": (_i, [c_ctx_p, _p, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
 }
 
 
@@ -336,12 +338,13 @@ class Context:
                                                        _ptr(a), _ptr(b), _ptr(rough)))
         return a, b, rough
 
-    def solve_wls(self, a, b, rough, cnt_lab_full, lam, alpha=1.2, rel_tol=0.0, max_iters=0):
+    def solve_wls(self, a, b, rough, cnt_lab_full, lam, alpha=1.2, rel_tol=0.0, max_iters=0, jacobi=False):
         """solve_WLS_roughness_cpu (CT/ColorTransfer.cpp:951-1125); a, b updated in place. Returns (iters, rel_res)."""
         H, W, _ = cnt_lab_full.shape
         it = _i(0)
         res = _d(0.0)
-        self._check(self.lib.nct_solve_wls(self.h, _ptr(a), _ptr(b), _ptr(rough), _ptr(cnt_lab_full), H, W, lam, alpha,
+        fn = self.lib.nct_solve_wls_jacobi if jacobi else self.lib.nct_solve_wls
+        self._check(fn(self.h, _ptr(a), _ptr(b), _ptr(rough), _ptr(cnt_lab_full), H, W, lam, alpha,
                                            rel_tol, max_iters, C.byref(it), C.byref(res)))
         return it.value, res.value
 
@@ -362,13 +365,14 @@ class Context:
         self._check(self.lib.nct_cluster_features(self.h, _ptr(feat_norm), h, w, Cn, k, iterations, _ptr(labels)))
         return labels
 
-    def find_knns(self, labels, lw, lh, lab, samples, nlabels=10):
+    def find_knns(self, labels, lw, lh, lab, samples, nlabels=10, brute=False):
         """ColorTransfer::findKnns (CT/ColorTransfer.cpp:397-423); lab (h, w, 3) uint8 cuda."""
         import torch
         h, w, _ = lab.shape
         ids = torch.empty((h * w, 8), dtype=torch.int32, device=lab.device)
         wts = torch.empty((h * w, 8), dtype=torch.float64, device=lab.device)
-        self._check(self.lib.nct_find_knns(self.h, _ptr(labels), lw, lh, nlabels, _ptr(lab), h, w, samples, _ptr(ids), _ptr(wts)))
+        fn = self.lib.nct_find_knns_brute if brute else self.lib.nct_find_knns
+        self._check(fn(self.h, _ptr(labels), lw, lh, nlabels, _ptr(lab), h, w, samples, _ptr(ids), _ptr(wts)))
         return ids, wts
 
     # -- VGG-19 (Classifier)

@@ -397,7 +397,7 @@ int nct_cluster_features(nct_ctx *ctx, const float *feat_norm_hwc_dev, int h, in
     return NCT_OK;
 }
 
-int nct_find_knns(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int nlabels, const uint8_t *lab_dev, int h, int w,
+int nct_find_knns_brute(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int nlabels, const uint8_t *lab_dev, int h, int w,
                   int samples, int *knn_id_dev, double *knn_w_dev)
 {
     if (!ctx) return NCT_ERR_ARG;

@@ -620,7 +620,7 @@ int nct_solve_nonlocal(nct_ctx *ctx, double *a_dev, double *b_dev, const double 
     return NCT_OK;
 }
 
-int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *rough_dev, const uint8_t *cnt_lab_full_dev, int H,
+int nct_solve_wls_jacobi(nct_ctx *ctx, double *a_dev, double *b_dev, const double *rough_dev, const uint8_t *cnt_lab_full_dev, int H,
                   int W, double lam, double alpha, double rel_tol, int max_iters, int *iters_out, double *rel_res_out)
 {
     if (!ctx) return NCT_ERR_ARG;
@@ -632,7 +632,7 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
     double *wx = (double *)nct_scratch(ctx, "wls_wx", sizeof(double) * n);
     double *wy = (double *)nct_scratch(ctx, "wls_wy", sizeof(double) * n);
     double *invd = (double *)nct_scratch(ctx, "wls_invd", sizeof(double) * n);
-    double *vec = (double *)nct_scratch(ctx, "wls_vec", sizeof(double) * (size_t)n * 6 * 6);
+    double *vec = (double *)nct_scratch(ctx, "wlsj_vec", sizeof(double) * (size_t)n * 6 * 6);
     double *partials = (double *)nct_scratch(ctx, "solver_partials", sizeof(double) * 18 * (size_t)(blocks + 1));
     char *misc = (char *)nct_scratch(ctx, "solver_misc", 1024);
     if (!wx || !wy || !invd || !vec || !partials || !misc) return NCT_ERR_NOMEM;

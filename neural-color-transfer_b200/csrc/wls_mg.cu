@@ -1,0 +1,631 @@
+// Multigrid-preconditioned CG for the full-resolution WLS system (diag(rough) + L_g) x = diag(rough) x0, 6 right-hand sides.
+//
+// Replaces solve_WLS_roughness_cpu + solve_direct_cpu / MKL PARDISO (CT/ColorTransfer.cpp:951-1125,
+// CT/SparseSolver_CPU.cpp:104-286): the reference factorises the 490k x 490k SPD matrix on the CPU at every level.
+// Here: CG in FP64 preconditioned by one symmetric V(2,2)-cycle of an aggregation multigrid:
+//   * coarse grids by 2x2 aggregation down to a single node; the coarse operators are the exact Galerkin products
+//     P^T M P for piecewise-constant P -- again 5-point graph Laplacians (edge weight = sum of the fine edges
+//     crossing two aggregates) plus the summed diagonal, so strongly varying edge weights (1e0..1e5) are handled
+//     algebraically;
+//   * damped Jacobi smoothing (omega = 0.8), coarse correction scaled by ALPHA (over-correction of unsmoothed
+//     aggregation); pre- and post-smoothing are symmetric, so plain PCG applies;
+//   * levels with <= 1024 nodes are processed by ONE thread block (the whole bottom of the V-cycle in one launch),
+//     the large levels use 4 launches each; every launch is bandwidth-bound on [n][6] double records.
+// Stops at a relative residual (default 1e-10) at which the result is indistinguishable from the direct solve at the
+// parity tolerance; the iteration count is data dependent, checked on the host every few iterations.
+#include "device_utils.cuh"
+#include <vector>
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int MAX_LEVELS = 14;
+constexpr double OMEGA = 0.8;
+constexpr double ALPHA = 1.6;
+
+struct MgLevel {
+    int H, W, n;
+    const double *rsum;  // diagonal (screening) part
+    const double *wx;    // edge (p, p+1)
+    const double *wy;    // edge (p, p+W)
+    double *invd;        // 1 / (rsum + sum of incident edge weights)
+    double *x, *b, *t;   // [n][6] vectors: correction, right-hand side, scratch
+};
+
+struct MgHierarchy {
+    MgLevel lv[MAX_LEVELS];
+    int nlevels;
+    int bottom;  // first level handled by the single-block kernel
+};
+
+__device__ __forceinline__ void ld6(const double *__restrict__ v, int i, double (&o)[6])
+{
+    const double2 *q = reinterpret_cast<const double2 *>(v + (size_t)i * 6);
+    const double2 t0 = q[0], t1 = q[1], t2 = q[2];
+    o[0] = t0.x; o[1] = t0.y; o[2] = t1.x; o[3] = t1.y; o[4] = t2.x; o[5] = t2.y;
+}
+__device__ __forceinline__ void st6(double *__restrict__ v, int i, const double (&o)[6])
+{
+    double2 *q = reinterpret_cast<double2 *>(v + (size_t)i * 6);
+    q[0] = make_double2(o[0], o[1]);
+    q[1] = make_double2(o[2], o[3]);
+    q[2] = make_double2(o[4], o[5]);
+}
+
+// sum_e w_e * X_j over the 4 neighbours, X given by a functor; also returns nothing else (diag comes from invd)
+template <class GetX>
+__device__ __forceinline__ void nbr_sum(const MgLevel &L, int i, GetX getx, double (&s)[6])
+{
+    const int x = i % L.W, y = i / L.W;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s[k] = 0.0;
+    auto add = [&](int j, double w) {
+        double xj[6];
+        getx(j, xj);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s[k] += w * xj[k];
+    };
+    if (x + 1 < L.W) add(i + 1, L.wx[i]);
+    if (x > 0) add(i - 1, L.wx[i - 1]);
+    if (y + 1 < L.H) add(i + L.W, L.wy[i]);
+    if (y > 0) add(i - L.W, L.wy[i - L.W]);
+}
+
+// ---- per-node operations (shared by the grid kernels and the single-block bottom kernel)
+// two damped-Jacobi sweeps from a zero initial guess: x = S2(b)
+__device__ __forceinline__ void op_presmooth2(const MgLevel &L, int i)
+{
+    double bi[6], s[6], o[6];
+    ld6(L.b, i, bi);
+    nbr_sum(L, i, [&](int j, double (&xj)[6]) {
+        ld6(L.b, j, xj);
+        const double f = OMEGA * L.invd[j];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) xj[k] *= f;
+    }, s);
+    const double f = OMEGA * L.invd[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[k] = f * bi[k] + f * ((1.0 - OMEGA) * bi[k] + s[k]);
+    st6(L.x, i, o);
+}
+
+// residual of node i: b - M x
+__device__ __forceinline__ void op_residual(const MgLevel &L, int i, double (&r)[6])
+{
+    double bi[6], xi[6], s[6];
+    ld6(L.b, i, bi);
+    ld6(L.x, i, xi);
+    nbr_sum(L, i, [&](int j, double (&xj)[6]) { ld6(L.x, j, xj); }, s);
+    const double d = 1.0 / L.invd[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) r[k] = bi[k] - d * xi[k] + s[k];
+}
+
+// coarse right-hand side of coarse node c = sum of the fine residuals of its (up to 4) children
+__device__ __forceinline__ void op_restrict(const MgLevel &F, const MgLevel &Cc, int c)
+{
+    const int J = c % Cc.W, I = c / Cc.W;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+            const int y = 2 * I + dy, x = 2 * J + dx;
+            if (y < F.H && x < F.W) {
+                double r[6];
+                op_residual(F, y * F.W + x, r);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) acc[k] += r[k];
+            }
+        }
+    st6(Cc.b, c, acc);
+}
+
+// y = x + ALPHA * P xc ; out = y + omega D^-1 (b - M y)   (prolongation fused with the first post-smoothing sweep)
+__device__ __forceinline__ void op_prolong_smooth(const MgLevel &F, const MgLevel &Cc, int i)
+{
+    auto gety = [&](int j, double (&yj)[6]) {
+        double xc[6];
+        ld6(F.x, j, yj);
+        const int jx = j % F.W, jy = j / F.W;
+        ld6(Cc.x, (jy >> 1) * Cc.W + (jx >> 1), xc);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) yj[k] += ALPHA * xc[k];
+    };
+    double yi[6], bi[6], s[6], o[6];
+    gety(i, yi);
+    ld6(F.b, i, bi);
+    nbr_sum(F, i, gety, s);
+    const double invd = F.invd[i], d = 1.0 / invd;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[k] = yi[k] + OMEGA * invd * (bi[k] - d * yi[k] + s[k]);
+    st6(F.t, i, o);
+}
+
+// one damped-Jacobi sweep t -> x
+__device__ __forceinline__ void op_smooth_t_to_x(const MgLevel &L, int i, double (&o)[6])
+{
+    double ti[6], bi[6], s[6];
+    ld6(L.t, i, ti);
+    ld6(L.b, i, bi);
+    nbr_sum(L, i, [&](int j, double (&xj)[6]) { ld6(L.t, j, xj); }, s);
+    const double invd = L.invd[i], d = 1.0 / invd;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[k] = ti[k] + OMEGA * invd * (bi[k] - d * ti[k] + s[k]);
+    st6(L.x, i, o);
+}
+
+// ---- grid kernels for the large levels
+__global__ void __launch_bounds__(TPB) mg_presmooth2_kernel(MgLevel L)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    if (i < L.n) op_presmooth2(L, i);
+}
+__global__ void __launch_bounds__(TPB) mg_restrict_kernel(MgLevel F, MgLevel Cc)
+{
+    const int c = blockIdx.x * TPB + threadIdx.x;
+    if (c < Cc.n) op_restrict(F, Cc, c);
+}
+__global__ void __launch_bounds__(TPB) mg_prolong_smooth_kernel(MgLevel F, MgLevel Cc)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    if (i < F.n) op_prolong_smooth(F, Cc, i);
+}
+__global__ void __launch_bounds__(TPB) mg_smooth_kernel(MgLevel L)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    double o[6];
+    if (i < L.n) op_smooth_t_to_x(L, i, o);
+}
+
+// the whole bottom of the V-cycle (levels h.bottom .. nlevels-1, each <= 1024 nodes) in one block
+__global__ void __launch_bounds__(512) mg_bottom_kernel(MgHierarchy h)
+{
+    const int last = h.nlevels - 1;
+    for (int k = h.bottom; k < last; ++k) {
+        const MgLevel &L = h.lv[k];
+        for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_presmooth2(L, i);
+        __syncthreads();
+        const MgLevel &Cc = h.lv[k + 1];
+        for (int c = threadIdx.x; c < Cc.n; c += blockDim.x) op_restrict(L, Cc, c);
+        __syncthreads();
+    }
+    {   // coarsest level: a single node (or a handful): exact for n == 1, Jacobi sweeps otherwise
+        const MgLevel &L = h.lv[last];
+        if (L.n == 1) {
+            if (threadIdx.x == 0) {
+                double b[6], o[6];
+                ld6(L.b, 0, b);
+                const double invd = L.invd[0];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) o[k] = b[k] * invd;
+                st6(L.x, 0, o);
+            }
+        } else {
+            for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_presmooth2(L, i);
+        }
+        __syncthreads();
+    }
+    for (int k = last - 1; k >= h.bottom; --k) {
+        const MgLevel &L = h.lv[k];
+        const MgLevel &Cc = h.lv[k + 1];
+        for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_prolong_smooth(L, Cc, i);
+        __syncthreads();
+        for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
+            double o[6];
+            op_smooth_t_to_x(L, i, o);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- hierarchy set-up
+__global__ void mg_coarsen_kernel(MgLevel F, int Hc, int Wc, double *__restrict__ rsum, double *__restrict__ wx, double *__restrict__ wy)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Hc * Wc) return;
+    const int J = c % Wc, I = c / Wc;
+    double rs = 0.0, vx = 0.0, vy = 0.0;
+    for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+            const int y = 2 * I + dy, x = 2 * J + dx;
+            if (y < F.H && x < F.W) rs += F.rsum[y * F.W + x];
+        }
+    if (2 * J + 2 < F.W)
+        for (int dy = 0; dy < 2; ++dy) {
+            const int y = 2 * I + dy;
+            if (y < F.H) vx += F.wx[y * F.W + 2 * J + 1];
+        }
+    if (2 * I + 2 < F.H)
+        for (int dx = 0; dx < 2; ++dx) {
+            const int x = 2 * J + dx;
+            if (x < F.W) vy += F.wy[(2 * I + 1) * F.W + x];
+        }
+    rsum[c] = rs;
+    wx[c] = vx;
+    wy[c] = vy;
+}
+
+__global__ void mg_diag_kernel(MgLevel L)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.n) return;
+    const int x = i % L.W, y = i / L.W;
+    double d = L.rsum[i];
+    if (x + 1 < L.W) d += L.wx[i];
+    if (x > 0) d += L.wx[i - 1];
+    if (y + 1 < L.H) d += L.wy[i];
+    if (y > 0) d += L.wy[i - L.W];
+    L.invd[i] = 1.0 / d;
+}
+
+__global__ void mg_wls_weights_kernel(const uint8_t *__restrict__ lab, int H, int W, double lam, double alpha,
+                                      double *__restrict__ wx, double *__restrict__ wy)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= H * W) return;
+    const int x = p % W, y = p / W;
+    const double L = __dmul_rn((double)lab[(size_t)p * 3], 1.0 / 255.0);
+    double vx = 0.0, vy = 0.0;
+    if (x + 1 < W) {
+        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(pow(fabs(__dsub_rn(__dmul_rn((double)lab[(size_t)(p + 1) * 3], 1.0 / 255.0), L)), alpha), 1e-4)));
+        vx = __dmul_rn(g, g);
+    }
+    if (y + 1 < H) {
+        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(pow(fabs(__dsub_rn(__dmul_rn((double)lab[(size_t)(p + W) * 3], 1.0 / 255.0), L)), alpha), 1e-4)));
+        vy = __dmul_rn(g, g);
+    }
+    wx[p] = vx;
+    wy[p] = vy;
+}
+
+// ---- outer PCG (6 right-hand sides)
+struct PcgScalars {
+    double rz[6], rz_old[6], alpha[6], beta[6], rr[6], bb[6];
+    int iters;
+};
+
+template <int NV>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double *smem)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+        if (lane == 0) smem[k * (TPB / 32) + w] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = 0.0;
+            for (int i = 0; i < TPB / 32; ++i) s += smem[k * (TPB / 32) + i];
+            v[k] = s;
+        }
+    }
+    __syncthreads();
+}
+
+template <int NV>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials, unsigned *counter, double *smem)
+{
+    __shared__ bool last;
+    block_reduce<NV>(v, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) partials[(size_t)blockIdx.x * NV + k] = v[k];
+        __threadfence();
+        const unsigned t = atomicAdd(counter, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += TPB) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] += __ldcg(&partials[(size_t)b * NV + k]);
+    }
+    block_reduce<NV>(acc, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[k] = acc[k];
+        *counter = 0;
+        return true;
+    }
+    return false;
+}
+
+__global__ void pack6_kernel(const double *__restrict__ a, const double *__restrict__ b, int n, double *__restrict__ x)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double o[6] = {a[(size_t)i * 3], a[(size_t)i * 3 + 1], a[(size_t)i * 3 + 2], b[(size_t)i * 3], b[(size_t)i * 3 + 1], b[(size_t)i * 3 + 2]};
+    st6(x, i, o);
+}
+__global__ void unpack6_kernel(const double *__restrict__ x, int n, double *__restrict__ a, double *__restrict__ b)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double o[6];
+    ld6(x, i, o);
+    a[(size_t)i * 3] = o[0]; a[(size_t)i * 3 + 1] = o[1]; a[(size_t)i * 3 + 2] = o[2];
+    b[(size_t)i * 3] = o[3]; b[(size_t)i * 3 + 1] = o[4]; b[(size_t)i * 3 + 2] = o[5];
+}
+
+// r = W x0 - M x0 (written to level-0 b); rr, bb
+__global__ void __launch_bounds__(TPB) pcg_init_kernel(MgLevel L, const double *__restrict__ x, PcgScalars *sc, double *partials,
+                                                       unsigned *counter)
+{
+    __shared__ double smem[12 * TPB / 32];
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    double dots[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) dots[k] = 0.0;
+    if (i < L.n) {
+        double xi[6], s[6], ri[6];
+        ld6(x, i, xi);
+        nbr_sum(L, i, [&](int j, double (&xj)[6]) { ld6(x, j, xj); }, s);
+        const double d = 1.0 / L.invd[i], rg = L.rsum[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double rhs = rg * xi[k];
+            ri[k] = rhs - d * xi[k] + s[k];
+            dots[k] = ri[k] * ri[k];
+            dots[6 + k] = rhs * rhs;
+        }
+        st6(L.b, i, ri);
+    }
+    if (grid_reduce<12>(dots, partials, counter, smem)) {
+        for (int k = 0; k < 6; ++k) {
+            sc->rr[k] = dots[k];
+            sc->bb[k] = dots[6 + k];
+            sc->rz[k] = 0.0;
+            sc->rz_old[k] = 0.0;
+            sc->alpha[k] = 0.0;
+            sc->beta[k] = 0.0;
+        }
+        sc->iters = 0;
+    }
+}
+
+// rz = r.z ; beta = rz / rz_old   (z = level-0 x, r = level-0 b)
+__global__ void __launch_bounds__(TPB) pcg_rz_kernel(MgLevel L, PcgScalars *sc, double *partials, unsigned *counter)
+{
+    __shared__ double smem[6 * TPB / 32];
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    double dots[6] = {0, 0, 0, 0, 0, 0};
+    if (i < L.n) {
+        double ri[6], zi[6];
+        ld6(L.b, i, ri);
+        ld6(L.x, i, zi);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dots[k] = ri[k] * zi[k];
+    }
+    if (grid_reduce<6>(dots, partials, counter, smem)) {
+        for (int k = 0; k < 6; ++k) {
+            sc->rz_old[k] = sc->rz[k];
+            sc->rz[k] = dots[k];
+            sc->beta[k] = sc->rz_old[k] > 0.0 ? dots[k] / sc->rz_old[k] : 0.0;
+        }
+    }
+}
+
+// p = z + beta p_old ; Ap = M p ; alpha = rz / p.Ap
+__global__ void __launch_bounds__(TPB) pcg_spmv_kernel(MgLevel L, const double *__restrict__ pold, double *__restrict__ pnew,
+                                                       double *__restrict__ Ap, PcgScalars *sc, double *partials, unsigned *counter)
+{
+    __shared__ double smem[6 * TPB / 32];
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    double beta[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) beta[k] = sc->beta[k];
+    double dots[6] = {0, 0, 0, 0, 0, 0};
+    auto getp = [&](int j, double (&o)[6]) {
+        double zj[6], pj[6];
+        ld6(L.x, j, zj);
+        ld6(pold, j, pj);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o[k] = zj[k] + beta[k] * pj[k];
+    };
+    if (i < L.n) {
+        double pi[6], s[6], api[6];
+        getp(i, pi);
+        st6(pnew, i, pi);
+        nbr_sum(L, i, getp, s);
+        const double d = 1.0 / L.invd[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            api[k] = d * pi[k] - s[k];
+            dots[k] = pi[k] * api[k];
+        }
+        st6(Ap, i, api);
+    }
+    if (grid_reduce<6>(dots, partials, counter, smem)) {
+        for (int k = 0; k < 6; ++k) sc->alpha[k] = dots[k] > 0.0 ? sc->rz[k] / dots[k] : 0.0;
+    }
+}
+
+// x += alpha p ; r -= alpha Ap ; rr
+__global__ void __launch_bounds__(TPB) pcg_update_kernel(MgLevel L, double *__restrict__ x, const double *__restrict__ p,
+                                                         const double *__restrict__ Ap, PcgScalars *sc, double *partials,
+                                                         unsigned *counter)
+{
+    __shared__ double smem[6 * TPB / 32];
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    double alpha[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) alpha[k] = sc->alpha[k];
+    double dots[6] = {0, 0, 0, 0, 0, 0};
+    if (i < L.n) {
+        double xi[6], ri[6], pi[6], api[6];
+        ld6(x, i, xi);
+        ld6(L.b, i, ri);
+        ld6(p, i, pi);
+        ld6(Ap, i, api);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            xi[k] += alpha[k] * pi[k];
+            ri[k] -= alpha[k] * api[k];
+            dots[k] = ri[k] * ri[k];
+        }
+        st6(x, i, xi);
+        st6(L.b, i, ri);
+    }
+    if (grid_reduce<6>(dots, partials, counter, smem)) {
+        for (int k = 0; k < 6; ++k) sc->rr[k] = dots[k];
+        sc->iters += 1;
+    }
+}
+
+int vcycle(nct_ctx *ctx, const MgHierarchy &h)
+{
+    // down
+    for (int k = 0; k < h.bottom; ++k) {
+        const MgLevel &L = h.lv[k];
+        mg_presmooth2_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L);
+        NCT_CHECK_LAUNCH(ctx);
+        const MgLevel &Cc = h.lv[k + 1];
+        mg_restrict_kernel<<<nct_div_up(Cc.n, TPB), TPB, 0, ctx->stream>>>(L, Cc);
+        NCT_CHECK_LAUNCH(ctx);
+    }
+    mg_bottom_kernel<<<1, 512, 0, ctx->stream>>>(h);
+    NCT_CHECK_LAUNCH(ctx);
+    for (int k = h.bottom - 1; k >= 0; --k) {
+        const MgLevel &L = h.lv[k];
+        const MgLevel &Cc = h.lv[k + 1];
+        mg_prolong_smooth_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L, Cc);
+        NCT_CHECK_LAUNCH(ctx);
+        mg_smooth_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L);
+        NCT_CHECK_LAUNCH(ctx);
+    }
+    return NCT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *rough_dev, const uint8_t *cnt_lab_full_dev, int H,
+                  int W, double lam, double alpha, double rel_tol, int max_iters, int *iters_out, double *rel_res_out)
+{
+    if (!ctx) return NCT_ERR_ARG;
+    NCT_REQUIRE(ctx, a_dev && b_dev && rough_dev && cnt_lab_full_dev && H > 0 && W > 0, "bad arguments");
+    if (rel_tol <= 0) rel_tol = 1e-10;
+    if (max_iters <= 0) max_iters = 2000;
+    const int n0 = H * W;
+    // ---- level geometry
+    std::vector<int> Hs, Ws;
+    {
+        int h = H, w = W;
+        while (true) {
+            Hs.push_back(h);
+            Ws.push_back(w);
+            if (h == 1 && w == 1) break;
+            h = (h + 1) / 2;
+            w = (w + 1) / 2;
+        }
+    }
+    const int nl = (int)Hs.size();
+    NCT_REQUIRE(ctx, nl <= MAX_LEVELS, "image too large for the multigrid hierarchy");
+    size_t tot = 0, tot_c = 0;
+    for (int k = 0; k < nl; ++k) {
+        tot += (size_t)Hs[k] * Ws[k];
+        if (k > 0) tot_c += (size_t)Hs[k] * Ws[k];
+    }
+    double *coef = (double *)nct_scratch(ctx, "wls_coef", sizeof(double) * (3 * tot_c + 2 * (size_t)n0 + tot));  // rsum/wx/wy coarse, wx/wy fine, invd all
+    double *vec = (double *)nct_scratch(ctx, "wls_vec", sizeof(double) * 6 * (3 * tot + 4 * (size_t)n0));
+    const int blocks0 = nct_div_up(n0, TPB);
+    double *partials = (double *)nct_scratch(ctx, "solver_partials", sizeof(double) * 18 * (size_t)(blocks0 + 1));
+    char *misc = (char *)nct_scratch(ctx, "solver_misc", 1024);
+    if (!coef || !vec || !partials || !misc) return NCT_ERR_NOMEM;
+    PcgScalars *sc = (PcgScalars *)misc;
+    unsigned *counter = (unsigned *)(misc + 512);
+
+    MgHierarchy h;
+    h.nlevels = nl;
+    h.bottom = nl - 1;
+    double *cp = coef, *vp = vec;
+    for (int k = 0; k < nl; ++k) {
+        MgLevel &L = h.lv[k];
+        L.H = Hs[k];
+        L.W = Ws[k];
+        L.n = Hs[k] * Ws[k];
+        if (k == 0) {
+            L.rsum = rough_dev;
+            L.wx = cp; cp += L.n;
+            L.wy = cp; cp += L.n;
+        } else {
+            L.rsum = cp; cp += L.n;
+            L.wx = cp; cp += L.n;
+            L.wy = cp; cp += L.n;
+        }
+        L.invd = cp; cp += L.n;
+        L.x = vp; vp += (size_t)L.n * 6;
+        L.b = vp; vp += (size_t)L.n * 6;
+        L.t = vp; vp += (size_t)L.n * 6;
+    }
+    for (int k = 0; k < nl; ++k)
+        if (h.lv[k].n <= 1024) { h.bottom = k; break; }
+    if (h.bottom == 0) h.bottom = nl > 1 ? 1 : 0;  // level 0 always uses the grid kernels (tiny images only)
+    double *x = vp; vp += (size_t)n0 * 6;
+    double *p0 = vp; vp += (size_t)n0 * 6;
+    double *p1 = vp; vp += (size_t)n0 * 6;
+    double *Ap = vp; vp += (size_t)n0 * 6;
+
+    // ---- set-up: fine weights, Galerkin coarse operators, diagonals
+    NCT_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned), ctx->stream));
+    mg_wls_weights_kernel<<<blocks0, TPB, 0, ctx->stream>>>(cnt_lab_full_dev, H, W, lam, alpha, (double *)h.lv[0].wx, (double *)h.lv[0].wy);
+    NCT_CHECK_LAUNCH(ctx);
+    for (int k = 0; k < nl; ++k) {
+        if (k > 0) {
+            mg_coarsen_kernel<<<nct_div_up(h.lv[k].n, TPB), TPB, 0, ctx->stream>>>(h.lv[k - 1], h.lv[k].H, h.lv[k].W, (double *)h.lv[k].rsum,
+                                                                                  (double *)h.lv[k].wx, (double *)h.lv[k].wy);
+            NCT_CHECK_LAUNCH(ctx);
+        }
+        mg_diag_kernel<<<nct_div_up(h.lv[k].n, TPB), TPB, 0, ctx->stream>>>(h.lv[k]);
+        NCT_CHECK_LAUNCH(ctx);
+    }
+    pack6_kernel<<<blocks0, TPB, 0, ctx->stream>>>(a_dev, b_dev, n0, x);
+    NCT_CHECK_LAUNCH(ctx);
+    NCT_CUDA(ctx, cudaMemsetAsync(p0, 0, sizeof(double) * 6 * (size_t)n0, ctx->stream));
+    const MgLevel &L0 = h.lv[0];
+    pcg_init_kernel<<<blocks0, TPB, 0, ctx->stream>>>(L0, x, sc, partials, counter);
+    NCT_CHECK_LAUNCH(ctx);
+
+    double *pold = p0, *pnew = p1;
+    const int check_every = 4;
+    PcgScalars hs;
+    double worst = 0.0;
+    while (true) {
+        NCT_CUDA(ctx, cudaMemcpyAsync(&hs, sc, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+        NCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        worst = 0.0;
+        for (int k = 0; k < 6; ++k) {
+            const double rel = hs.bb[k] > 0.0 ? sqrt(hs.rr[k] / hs.bb[k]) : (hs.rr[k] > 0.0 ? 1.0 : 0.0);
+            if (rel > worst) worst = rel;
+        }
+        if (worst <= rel_tol || hs.iters >= max_iters) break;
+        for (int it = 0; it < check_every; ++it) {
+            int rc = vcycle(ctx, h);  // z (level-0 x) = B r (level-0 b)
+            if (rc) return rc;
+            pcg_rz_kernel<<<blocks0, TPB, 0, ctx->stream>>>(L0, sc, partials, counter);
+            NCT_CHECK_LAUNCH(ctx);
+            pcg_spmv_kernel<<<blocks0, TPB, 0, ctx->stream>>>(L0, pold, pnew, Ap, sc, partials, counter);
+            NCT_CHECK_LAUNCH(ctx);
+            pcg_update_kernel<<<blocks0, TPB, 0, ctx->stream>>>(L0, x, pnew, Ap, sc, partials, counter);
+            NCT_CHECK_LAUNCH(ctx);
+            double *t = pold; pold = pnew; pnew = t;
+        }
+    }
+    unpack6_kernel<<<blocks0, TPB, 0, ctx->stream>>>(x, n0, a_dev, b_dev);
+    NCT_CHECK_LAUNCH(ctx);
+    if (iters_out) *iters_out = hs.iters;
+    if (rel_res_out) *rel_res_out = worst;
+    if (worst > rel_tol)
+        return nct_fail(ctx, NCT_ERR_STATE, "WLS MG-PCG did not reach %.1e in %d iterations (at %.3e)", rel_tol, hs.iters, worst);
+    return NCT_OK;
+}
+
+}  // extern "C"

@@ -30,15 +30,16 @@ def test_kmeans_degenerate_inputs(ctx, dev):
     assert np.all(ctx.cluster_features(to_dev(dup, dev)).cpu().numpy() == 0)          # fewer than 10 distinct points
 
 
+@pytest.mark.parametrize("brute", [False, True])
 @pytest.mark.parametrize("lw,lh,samples,h,w", [(6, 6, 1, 6, 6), (6, 6, 2, 12, 11), (11, 13, 4, 50, 43), (44, 44, 2, 88, 88), (44, 44, 4, 175, 175)])
-def test_find_knns_bit_exact(ctx, dev, lw, lh, samples, h, w):
+def test_find_knns_bit_exact(ctx, dev, lw, lh, samples, h, w, brute):
     rng = np.random.default_rng(lw + h)
     # blobby label map, like a k-means segmentation
     base = rng.integers(0, 10, ((lh + 3) // 4, (lw + 3) // 4))
     labels = np.kron(base, np.ones((4, 4), np.int64))[:lh, :lw].astype(np.int32).ravel()
     cnt, _ = synth.pair(6, h, w)
     lab = color.bgr2lab_u8(cnt)
-    gi, gw = ctx.find_knns(to_dev(labels, dev), lw, lh, to_dev(lab, dev), samples)
+    gi, gw = ctx.find_knns(to_dev(labels, dev), lw, lh, to_dev(lab, dev), samples, brute=brute)
     ctx.synchronize()
     oi, ow = oracle.find_knns(labels, lw, lh, lab, samples)
     assert np.array_equal(gi.cpu().numpy(), oi)
@@ -55,5 +56,20 @@ def test_find_knns_full_size_level(ctx, dev):
     gi, gw = ctx.find_knns(to_dev(labels, dev), 44, 44, to_dev(lab, dev), 16)
     ctx.synchronize()
     oi, ow = oracle.find_knns(labels, 44, 44, lab, 16)
+    assert np.array_equal(gi.cpu().numpy(), oi)
+    assert np.allclose(gw.cpu().numpy(), ow, rtol=4e-16, atol=0)
+
+
+def test_find_knns_sparse_colours_and_tiny_clusters(ctx, dev):
+    """random (sparse, far apart) colours force the shell search to its whole-cluster fallback; one label covers a
+    single cell (tiny cluster path); both must still equal the oracle."""
+    rng = np.random.default_rng(5)
+    lw = lh = 8
+    labels = rng.integers(0, 3, lw * lh).astype(np.int32)
+    labels[0] = 9
+    lab = rng.integers(0, 256, (32, 32, 3), dtype=np.uint8)
+    gi, gw = ctx.find_knns(to_dev(labels, dev), lw, lh, to_dev(lab, dev), 4)
+    ctx.synchronize()
+    oi, ow = oracle.find_knns(labels, lw, lh, lab, 4)
     assert np.array_equal(gi.cpu().numpy(), oi)
     assert np.allclose(gw.cpu().numpy(), ow, rtol=4e-16, atol=0)

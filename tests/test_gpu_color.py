@@ -161,5 +161,8 @@ def test_solve_wls_matches_direct_solve(ctx, dev, H, W, lam):
     for c in range(3):
         assert relerr(ga.cpu().numpy()[..., c], oa[..., c]) < REL_TOL
         assert relerr(gb.cpu().numpy()[..., c], ob[..., c]) < REL_TOL
-    print(f"WLS {H}x{W} lam={lam}: {its} PCG iterations, rel.res {res:.2e}, "
+    ja, jb = to_dev(a, dev), to_dev(b, dev)
+    jits, jres = ctx.solve_wls(ja, jb, to_dev(rough, dev), to_dev(lab, dev), lam, 1.2, jacobi=True)
+    assert relerr(ja.cpu().numpy(), ga.cpu().numpy()) < 1e-7  # multigrid and Jacobi PCG agree
+    print(f"WLS {H}x{W} lam={lam}: {its} MG-PCG iterations (Jacobi-PCG: {jits}), rel.res {res:.2e}, "
           f"max rel.err a {max(relerr(ga.cpu().numpy()[..., c], oa[..., c]) for c in range(3)):.2e}")
