@@ -214,6 +214,10 @@ int nct_vgg19_level_dims(int h, int w, int dims[5][3]);
  * (NCT/main.cu:424-427 re-runs the whole net). */
 int nct_vgg19_features(nct_ctx *ctx, const uint8_t *bgr_dev, int h, int w, int deepest_level, float *feat_dev[5]);
 
+/* Net::CopyTrainedLayersFrom(trained_file) (caffe/net.cpp:798-815; NCT/Classifier.cpp:20): reads the conv1_1..conv5_1
+ * blobs from a binary .caffemodel (V1 `layers` or V2 `layer` records) with a built-in protobuf wire reader. */
+int nct_vgg19_load_caffemodel(nct_ctx *ctx, const char *path);
+
 /* ---------------------------------------------------------------- clustering / non-local neighbours */
 
 /* ColorTransfer::clusterFeastures (CT/ColorTransfer.cpp:355-395) = root split of cvflann's hierarchical k-means
@@ -264,6 +268,20 @@ int nct_transfer_pair(nct_ctx *ctx, const uint8_t *cnt_bgr_host, int ch, int cw,
  * cross-check of the grid search above. */
 int nct_find_knns_brute(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int nlabels, const uint8_t *lab_dev, int h,
                         int w, int samples, int *knn_id_dev, double *knn_w_dev);
+
+/* ---------------------------------------------------------------- image files / pair lists */
+
+/* imread(path) (NCT/main.cu:483,491): PNG -> malloc'ed 8-bit BGR (alpha dropped, grey / palette expanded); free with
+ * nct_png_free.  imwrite(path, bgr) (NCT/main.cu:538): 8-bit BGR -> RGB PNG. */
+int nct_png_read(const char *path, uint8_t **bgr_out, int *h_out, int *w_out);
+void nct_png_free(uint8_t *p);
+int nct_png_write(const char *path, const uint8_t *bgr, int h, int w);
+
+/* transfer_single (NCT/main.cu:456-543): runs every line `content style bds` of <input_dir>/pairs.txt whose index i
+ * satisfies i % world == rank and writes <output_dir>/<content>_<style>_<bds %2.2f>.png.  Images with a side above
+ * 1000 are shrunk first (MAX_SIZE, CT/Config.h:5).  A pair that cannot be read is reported and skipped. */
+int nct_run_pairs(nct_ctx *ctx, const char *input_dir, const char *output_dir, const nct_config *cfg, int rank, int world,
+                  int *pairs_done);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,11 @@ ABI = {
     "nct_config_default": (None, [C.POINTER(Config)]),
     "nct_transfer_pair_dev": (_i, [c_ctx_p, _p, _i, _i, _p, _i, _i, C.POINTER(Config), _p]),
     "nct_transfer_pair": (_i, [c_ctx_p, _p, _i, _i, _p, _i, _i, C.POINTER(Config), _p]),
+    "nct_vgg19_load_caffemodel": (_i, [c_ctx_p, C.c_char_p]),
+    "nct_png_read": (_i, [C.c_char_p, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(_i), C.POINTER(_i)]),
+    "nct_png_free": (None, [C.POINTER(C.c_uint8)]),
+    "nct_png_write": (_i, [C.c_char_p, _p, _i, _i]),
+    "nct_run_pairs": (_i, [c_ctx_p, C.c_char_p, C.c_char_p, C.POINTER(Config), _i, _i, C.POINTER(_i)]),
     "nct_cluster_features": (_i, [c_ctx_p, _p, _i, _i, _i, _i, _i, _p]),
     "nct_find_knns": (_i, [c_ctx_p, _p, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
     "nct_find_knns_brute": (_i, [c_ctx_p, _p, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
@@ -111,6 +116,70 @@ def load_library(path: Optional[str] = None):
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def png_read(path):
+    """imread stand-in of the CLI (no GPU needed): PNG file -> uint8 BGR numpy array"""
+    import numpy as np
+    lib = load_library()
+    buf = C.POINTER(C.c_uint8)()
+    h, w = _i(0), _i(0)
+    rc = lib.nct_png_read(path.encode(), C.byref(buf), C.byref(h), C.byref(w))
+    if rc != 0:
+        raise NctError(f"cannot read PNG {path} ({rc})")
+    out = np.ctypeslib.as_array(buf, shape=(h.value, w.value, 3)).copy()
+    lib.nct_png_free(buf)
+    return out
+
+
+def png_write(path, bgr):
+    import numpy as np
+    lib = load_library()
+    a = np.ascontiguousarray(bgr, np.uint8)
+    rc = lib.nct_png_write(path.encode(), a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1])
+    if rc != 0:
+        raise NctError(f"cannot write PNG {path} ({rc})")
+
+
+def write_caffemodel(path, weights, v1=True):
+    """Serialise {layer: (w OIHW, bias)} as a binary caffe NetParameter (V1 `layers` records like the original
+    VGG_ILSVRC_19_layers.caffemodel, or V2 `layer` records).  Used to exercise the real loader with synthetic weights."""
+    import numpy as np
+
+    def varint(v):
+        out = bytearray()
+        while True:
+            b = v & 0x7F
+            v >>= 7
+            if v:
+                out.append(b | 0x80)
+            else:
+                out.append(b)
+                return bytes(out)
+
+    def field(num, wire, payload):
+        return varint((num << 3) | wire) + (varint(len(payload)) + payload if wire == 2 else payload)
+
+    def blob(arr):
+        arr = np.ascontiguousarray(arr, np.float32)
+        shape = list(arr.shape) if arr.ndim == 4 else [1, 1, 1, arr.size]
+        if v1:
+            head = b"".join(field(i + 1, 0, varint(s)) for i, s in enumerate(shape))
+        else:
+            dims = list(arr.shape)
+            head = field(7, 2, field(1, 2, b"".join(varint(d) for d in dims)))
+        return head + field(5, 2, arr.tobytes())
+
+    out = bytearray(field(1, 2, b"VGG_ILSVRC_19_layers"))
+    for name, (w, b) in weights.items():
+        if v1:
+            layer = field(4, 2, name.encode()) + field(5, 0, varint(4)) + field(6, 2, blob(w)) + field(6, 2, blob(b))
+            out += field(2, 2, layer)
+        else:
+            layer = field(1, 2, name.encode()) + field(2, 2, b"Convolution") + field(7, 2, blob(w)) + field(7, 2, blob(b))
+            out += field(100, 2, layer)
+    with open(path, "wb") as f:
+        f.write(bytes(out))
 
 
 def make_params(C_, ah, aw, bh, bw, iters=10, rs_max=32, patch=3):
@@ -438,3 +507,15 @@ class Context:
         self._check(self.lib.nct_transfer_pair(self.h, hp(cnt_host), ch, cw, hp(stl_host), sh, sw,
                                                C.byref(cfg) if cfg is not None else None, hp(out_host)))
         return out_host
+
+    # -- files
+    def load_caffemodel(self, path):
+        """Net::CopyTrainedLayersFrom (caffe/net.cpp:798): load conv1_1..conv5_1 from a binary .caffemodel"""
+        self._check(self.lib.nct_vgg19_load_caffemodel(self.h, path.encode()))
+
+    def run_pairs(self, input_dir, output_dir, cfg=None, rank=0, world=1):
+        """transfer_single (NCT/main.cu:456-543) for the lines i % world == rank of <input_dir>/pairs.txt"""
+        done = _i(0)
+        self._check(self.lib.nct_run_pairs(self.h, input_dir.encode(), output_dir.encode(),
+                                           C.byref(cfg) if cfg is not None else None, rank, world, C.byref(done)))
+        return done.value

@@ -1,0 +1,96 @@
+// neural_color_transfer -- the reference's command line (NCT/main.cu:29-44, 546-590; NCT/CmdLine.cpp:21-57):
+//   neural_color_transfer -m <model_dir> -i <input_root> -o <out_dir> -g <gpu_id> [-bds w] [-eps e] [-nl w] [-l w] [-w l]
+// Flags may start with '-' or '/'; -h / -? / -help print the parameter list and exit with -1; an unknown flag prints
+// "Unrecognized parameter" + the list and exits with -1.  Reads <model_dir>/vgg19/VGG_ILSVRC_19_layers.caffemodel and
+// <input_root>/pairs.txt, writes <out_dir>/<content>_<style>_<bds>.png.
+// Extension: -ngpu N processes the pair list on GPUs g .. g+N-1, one worker (own context) per GPU, pair i on worker
+// i mod N; the reference is single-GPU (NCT/main.cu:563-565).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+#include "../../../include/nct.h"
+
+extern "C" int nct_vgg19_load_caffemodel(nct_ctx *ctx, const char *path);
+extern "C" int nct_run_pairs(nct_ctx *ctx, const char *input_dir, const char *output_dir, const nct_config *cfg, int rank, int world, int *pairs_done);
+
+struct Param { const char *arg; const char *desc; int kind; void *dst; };  // kind 0 string, 1 int, 2 double
+
+static bool is_arg(const char *s) { return s && (s[0] == '-' || s[0] == '/') && s[1] != 0; }
+
+static void do_help(const char *prog, const std::vector<Param> &params)
+{
+    printf("Running: %s\n", prog);
+    for (const Param &p : params) printf("    -%s %s\n", p.arg, p.desc);
+}
+
+int main(int argc, char **argv)
+{
+    nct_config cfg;
+    nct_config_default(&cfg);
+    std::string model_dir, input_dir, output_dir;
+    int gpu_id = 0, ngpu = 1;
+    std::vector<Param> params = {
+        {"m", "Directory of network models.", 0, &model_dir},
+        {"i", "Input directory of content and style images and pairs.txt.", 0, &input_dir},
+        {"o", "Output directory of result images.", 0, &output_dir},
+        {"g", "GPU ID (default: 0).", 1, &gpu_id},
+        {"bds", "Weight of reverse color in BDS voting (default: 2.0).", 2, &cfg.bds_weight},
+        {"eps", "Eps is used to avoid dividing zero (default: 0.6 with range in [0-255]).", 2, &cfg.var_eps},
+        {"nl", "Weight of nonlocal constraint (default: 2.0).", 2, &cfg.nonlocal_weight},
+        {"l", "Weight of local constraint (default: 0.125).", 2, &cfg.local_weight},
+        {"w", "Initial value of WLS weight (default: 0.024).", 2, &cfg.wls_lambda_init},
+        {"ngpu", "Number of GPUs to spread the pair list over, starting at -g (default: 1).", 1, &ngpu},
+    };
+    int i = 1;
+    while (i < argc) {
+        if (!is_arg(argv[i])) { ++i; continue; }  // stray file arguments are collected and ignored by the reference
+        const std::string a(argv[i] + 1);
+        if (a == "h" || a == "?" || a == "help") { do_help(argv[0], params); return -1; }
+        bool processed = false;
+        for (const Param &p : params) {
+            if (a != p.arg) continue;
+            if (i + 1 < argc) {
+                if (p.kind == 0) *(std::string *)p.dst = argv[i + 1];
+                else if (p.kind == 1) *(int *)p.dst = atoi(argv[i + 1]);
+                else *(double *)p.dst = atof(argv[i + 1]);
+                ++i;
+            }
+            ++i;
+            processed = true;
+            break;
+        }
+        if (!processed) {
+            printf("Unrecognized parameter: %s\n\n", argv[i]);
+            do_help(argv[0], params);
+            return -1;
+        }
+    }
+    if (ngpu < 1) ngpu = 1;
+    const std::string weights = model_dir + "/vgg19/VGG_ILSVRC_19_layers.caffemodel";
+    std::vector<nct_ctx *> ctxs((size_t)ngpu, nullptr);
+    for (int r = 0; r < ngpu; ++r) {
+        if (nct_create(gpu_id + r, &ctxs[r]) != NCT_OK) {
+            fprintf(stderr, "Error: cannot create a context on GPU %d (libnct needs an sm_100 device; there is no CPU path).\n", gpu_id + r);
+            return 1;
+        }
+        if (r == 0) printf("The number of device is: %d, set device %d.\n", ngpu, gpu_id);
+        if (nct_vgg19_load_caffemodel(ctxs[r], weights.c_str()) != NCT_OK) {
+            fprintf(stderr, "Error: %s\n", nct_last_error(ctxs[r]));
+            return 1;
+        }
+    }
+    std::vector<std::thread> workers;
+    std::vector<int> done((size_t)ngpu, 0), rcs((size_t)ngpu, 0);
+    for (int r = 0; r < ngpu; ++r)
+        workers.emplace_back([&, r]() { rcs[r] = nct_run_pairs(ctxs[r], input_dir.c_str(), output_dir.c_str(), &cfg, r, ngpu, &done[r]); });
+    for (auto &t : workers) t.join();
+    int rc = 0;
+    for (int r = 0; r < ngpu; ++r) {
+        if (rcs[r]) { fprintf(stderr, "Error: %s\n", nct_last_error(ctxs[r])); rc = 1; }
+        nct_destroy(ctxs[r]);
+    }
+    return rc;
+}

@@ -15,13 +15,18 @@
 // parity tolerance; the iteration count is data dependent, checked on the host every few iterations.
 #include "device_utils.cuh"
 #include <vector>
+#include <cstdlib>
 
 namespace {
 
 constexpr int TPB = 256;
 constexpr int MAX_LEVELS = 14;
-constexpr double OMEGA = 0.8;
-constexpr double ALPHA = 1.6;
+// smoothing weight and over-correction of the coarse-grid correction (tunable through NCT_MG_OMEGA / NCT_MG_ALPHA for
+// experiments; the defaults are the measured optimum on the 700x700 workload, profiles/r1_wls_tuning.md)
+__constant__ double c_omega = 0.8;
+__constant__ double c_alpha = 1.6;
+#define OMEGA c_omega
+#define ALPHA c_alpha
 
 struct MgLevel {
     int H, W, n;
@@ -515,6 +520,22 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
     if (rel_tol <= 0) rel_tol = 1e-10;
     if (max_iters <= 0) max_iters = 2000;
     const int n0 = H * W;
+    {
+        static bool tuned = false;
+        if (!tuned) {
+            tuned = true;
+            const char *eo = getenv("NCT_MG_OMEGA"), *ea = getenv("NCT_MG_ALPHA");
+            if (eo) { double v = atof(eo); cudaMemcpyToSymbol(c_omega, &v, sizeof(v)); }
+            if (ea) { double v = atof(ea); cudaMemcpyToSymbol(c_alpha, &v, sizeof(v)); }
+        }
+        if (!getenv("NCT_MG_ALPHA")) {
+            // measured (profiles/r1_wls_tuning.md): over-correction pays when diffusion dominates (coarse pyramid
+            // levels, lambda' >= 1), plain correction is better once the screening term matters
+            const double v = lam >= 1.0 ? 1.4 : 1.0;
+            cudaMemcpyToSymbolAsync(c_alpha, &v, sizeof(v), 0, cudaMemcpyHostToDevice, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+        }
+    }
     // ---- level geometry
     std::vector<int> Hs, Ws;
     {
@@ -623,6 +644,7 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
     NCT_CHECK_LAUNCH(ctx);
     if (iters_out) *iters_out = hs.iters;
     if (rel_res_out) *rel_res_out = worst;
+    if (getenv("NCT_WLS_VERBOSE")) fprintf(stderr, "[nct] WLS %dx%d lam=%.3f: %d MG-PCG iterations, rel.res %.2e\n", H, W, lam, hs.iters, worst);
     if (worst > rel_tol)
         return nct_fail(ctx, NCT_ERR_STATE, "WLS MG-PCG did not reach %.1e in %d iterations (at %.3e)", rel_tol, hs.iters, worst);
     return NCT_OK;

@@ -123,3 +123,51 @@ def test_bds_weight_changes_result(pctx):
 def test_pipeline_rejects_bad_input(pkg, pctx):
     with pytest.raises(pkg.NctError):
         pctx.transfer_pair(np.zeros((16, 16, 3), np.uint8), np.zeros((64, 64, 3), np.uint8))
+
+
+def test_cli_drop_in_pairs_txt_end_to_end(pkg, pctx, weights, tmp_path):
+    """The reference's surface: -m/-i/-o/-g, pairs.txt, <cnt>_<stl>_<bds>.png.  A synthetic V1 caffemodel exercises the
+    real loader; the PNGs written by the binary equal the library result for the same pair and BDS weight."""
+    import subprocess, os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "neural-color-transfer_b200", "neural_color_transfer")
+    model = tmp_path / "model" / "vgg19"
+    model.mkdir(parents=True)
+    pkg.write_caffemodel(str(model / "VGG_ILSVRC_19_layers.caffemodel"), weights, v1=True)
+    inp = tmp_path / "example"
+    (inp / "in").mkdir(parents=True)
+    pairs = []
+    for i, (h, w) in enumerate([(96, 128), (112, 80)]):
+        c, s = synth.pair(10 + i, h, w)
+        pkg.png_write(str(inp / "in" / f"in{i}.png"), c)
+        pkg.png_write(str(inp / "in" / f"tar{i}.png"), s)
+        pairs.append((c, s))
+    (inp / "pairs.txt").write_text("in/in0.png in/tar0.png 2.0\nin/in1.png in/tar1.png 0.5\nin/missing.png in/tar1.png 2.0\n")
+    out = tmp_path / "res"
+    r = subprocess.run([cli, "-m", str(tmp_path / "model"), "-i", str(inp), "-o", str(out), "-g", "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Fail reading content image" in r.stdout and r.stdout.count("Final output file") == 2
+    for i, bds in enumerate([2.0, 0.5]):
+        got = pkg.png_read(str(out / f"in{i}_tar{i}_{bds:2.2f}.png"))
+        ref = pctx.transfer_pair(pairs[i][0], pairs[i][1], pctx.default_config(bds_weight=bds))
+        assert np.array_equal(got, ref)
+
+
+def test_caffemodel_v2_records_load_too(pkg, dev, weights, tmp_path):
+    p = str(tmp_path / "v2.caffemodel")
+    pkg.write_caffemodel(p, weights, v1=False)
+    c = pkg.Context(0)
+    c.load_caffemodel(p)
+    img, _ = synth.pair(0, 64, 64)
+    import torch
+    a = c.predict(torch.from_numpy(img).to(dev), 0)
+    c.synchronize()
+    c2 = pkg.Context(0)
+    c2.load_vgg19_weights(weights)
+    b = c2.predict(torch.from_numpy(img).to(dev), 0)
+    c2.synchronize()
+    assert all(np.array_equal(x.cpu().numpy(), y.cpu().numpy()) for x, y in zip(a, b))
+    with pytest.raises(pkg.NctError):
+        c.load_caffemodel(str(tmp_path / "missing.caffemodel"))
+    c.close(); c2.close()
