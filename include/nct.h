@@ -205,6 +205,10 @@ int nct_vgg19_layer_shape(int layer, int *cin, int *cout);
 /* Caffe blob layout: weights O x I x 3 x 3, bias O (host pointers). Replaces Net::CopyTrainedLayersFrom
  * (caffe/net.cpp:798) for one layer. */
 int nct_vgg19_set_weights(nct_ctx *ctx, int layer, const float *w_oihw_host, const float *bias_host);
+/* Convolution engine: 0 = FP32 on CUDA cores (exact FP32 products, fixed summation order; default),
+ * 1 = tcgen05 tensor cores, kind::tf32 operands from TMA-staged shared memory, FP32 accumulation in TMEM
+ * (layers with Cin >= 64; conv1_1 always runs on CUDA cores). */
+int nct_vgg19_set_engine(nct_ctx *ctx, int engine);
 /* Feature-map sizes {C, H, W} per level for an h x w image under Caffe's ceil-mode pooling
  * (caffe/layers/pooling_layer.cpp:90-93); replaces the Dim outputs of Classifier::Predict (NCT/Classifier.h:30-43). */
 int nct_vgg19_level_dims(int h, int w, int dims[5][3]);

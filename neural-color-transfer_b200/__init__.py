@@ -73,6 +73,7 @@ ABI = {
     "nct_vgg19_layer_name": (C.c_char_p, [_i]),
     "nct_vgg19_layer_shape": (_i, [_i, C.POINTER(_i), C.POINTER(_i)]),
     "nct_vgg19_set_weights": (_i, [c_ctx_p, _i, _p, _p]),
+    "nct_vgg19_set_engine": (_i, [c_ctx_p, _i]),
     "nct_vgg19_level_dims": (_i, [_i, _i, C.POINTER(_i * 3)]),
     "nct_vgg19_features": (_i, [c_ctx_p, _p, _i, _i, _i, C.POINTER(_p)]),
     "nct_config_default": (None, [C.POINTER(Config)]),
@@ -454,6 +455,10 @@ class Context:
             w = np.ascontiguousarray(w, np.float32)
             b = np.ascontiguousarray(b, np.float32)
             self._check(self.lib.nct_vgg19_set_weights(self.h, i, w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))
+
+    def set_vgg_engine(self, engine):
+        """0 = FP32 CUDA cores, 1 = tcgen05 TF32 tensor cores"""
+        self._check(self.lib.nct_vgg19_set_engine(self.h, engine))
 
     def level_dims(self, h, w):
         d = ((_i * 3) * 5)()

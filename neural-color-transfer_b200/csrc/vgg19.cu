@@ -31,10 +31,15 @@ const ConvSpec kTrunk[13] = {
 }  // namespace
 
 struct VggState {
-    float *w[13] = {nullptr};   // [9][cin][cout]
+    float *w[13] = {nullptr};   // [9][cin][cout]      (CUDA-core engine)
+    float *wk[13] = {nullptr};  // [cout][9][cin]      (K-major, tensor-core engine)
     float *b[13] = {nullptr};
     bool have[13] = {false};
+    int engine = 0;             // 0 = FP32 CUDA cores, 1 = tcgen05 kind::tf32
 };
+
+int nct_conv3x3_tensorcore(nct_ctx *ctx, const float *in, const float *w_kmajor, const float *bias, float *out, int H, int W, int Cin,
+                           int Cout);
 
 namespace {
 
@@ -209,6 +214,7 @@ void nct_vgg_free(nct_ctx *ctx)
     if (!ctx || !ctx->vgg) return;
     for (int i = 0; i < 13; ++i) {
         if (ctx->vgg->w[i]) cudaFree(ctx->vgg->w[i]);
+        if (ctx->vgg->wk[i]) cudaFree(ctx->vgg->wk[i]);
         if (ctx->vgg->b[i]) cudaFree(ctx->vgg->b[i]);
     }
     delete ctx->vgg;
@@ -239,12 +245,27 @@ int nct_vgg19_set_weights(nct_ctx *ctx, int layer, const float *w_oihw_host, con
     for (int o = 0; o < cout; ++o)
         for (int i = 0; i < cin; ++i)
             for (int t = 0; t < 9; ++t) wt[((size_t)t * cin + i) * cout + o] = w_oihw_host[((size_t)o * cin + i) * 9 + t];
+    std::vector<float> wkm((size_t)9 * cin * cout);
+    for (int o = 0; o < cout; ++o)
+        for (int i = 0; i < cin; ++i)
+            for (int t = 0; t < 9; ++t) wkm[((size_t)o * 9 + t) * cin + i] = w_oihw_host[((size_t)o * cin + i) * 9 + t];
     VggState *v = ctx->vgg;
+    if (!v->wk[layer]) NCT_CUDA(ctx, cudaMalloc(&v->wk[layer], wkm.size() * sizeof(float)));
+    NCT_CUDA(ctx, cudaMemcpy(v->wk[layer], wkm.data(), wkm.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (!v->w[layer]) NCT_CUDA(ctx, cudaMalloc(&v->w[layer], wt.size() * sizeof(float)));
     if (!v->b[layer]) NCT_CUDA(ctx, cudaMalloc(&v->b[layer], cout * sizeof(float)));
     NCT_CUDA(ctx, cudaMemcpy(v->w[layer], wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
     NCT_CUDA(ctx, cudaMemcpy(v->b[layer], bias_host, cout * sizeof(float), cudaMemcpyHostToDevice));
     v->have[layer] = true;
+    return NCT_OK;
+}
+
+int nct_vgg19_set_engine(nct_ctx *ctx, int engine)
+{
+    if (!ctx) return NCT_ERR_ARG;
+    NCT_REQUIRE(ctx, engine == 0 || engine == 1, "engine must be 0 (FP32 CUDA cores) or 1 (tcgen05 TF32)");
+    if (!ctx->vgg) ctx->vgg = new VggState();
+    ctx->vgg->engine = engine;
     return NCT_OK;
 }
 
@@ -307,6 +328,11 @@ int nct_vgg19_features(nct_ctx *ctx, const uint8_t *bgr_dev, int h, int w, int d
         if (dst == cur) return nct_fail(ctx, NCT_ERR_STATE, "internal: aliasing activation buffers");
         if (i == 0) {
             conv_first_kernel<<<nct_div_up(H * W * 4, 256), 256, 0, ctx->stream>>>(cur, v->w[0], v->b[0], dst, H, W);
+        } else if (v->engine == 1) {
+            int rc = nct_conv3x3_tensorcore(ctx, cur, v->wk[i], v->b[i], dst, H, W, L.cin, L.cout);
+            if (rc) return rc;
+            cur = dst;
+            continue;
         } else {
             dim3 grid(nct_div_up(H * W, BM), L.cout / BN);
             conv3x3_kernel<<<grid, 256, 0, ctx->stream>>>(cur, v->w[i], v->b[i], dst, H, W, L.cin, L.cout);

@@ -77,3 +77,24 @@ def test_missing_weights_fail_loudly(pkg, dev):
     with pytest.raises(pkg.NctError):
         c.predict(torch.zeros((32, 32, 3), dtype=torch.uint8, device=dev))
     c.close()
+
+
+@pytest.mark.parametrize("h,w", [(64, 48), (97, 131), (256, 256)])
+def test_tensorcore_engine_matches_fp32_engine(pkg, vctx, dev, weights, h, w):
+    """tcgen05 kind::tf32 convolutions (10-bit operand mantissa, FP32 accumulate) against the FP32 CUDA-core engine:
+    every level within 5e-3 of the feature range; borders (TMA zero fill) and ragged tiles included."""
+    img, _ = synth.pair(7, h, w)
+    t = to_dev(img, dev)
+    ref = vctx.predict(t, 0)
+    vctx.synchronize()
+    c = pkg.Context(0)
+    c.load_vgg19_weights(weights)
+    c.set_vgg_engine(1)
+    got = c.predict(t, 0)
+    c.synchronize()
+    for l in range(5):
+        r, g = ref[l].cpu().numpy(), got[l].cpu().numpy()
+        err = np.abs(g - r).max() / np.abs(r).max()
+        print(f"level {l}: tf32 vs fp32 max err {err:.2e} of range, mean rel {np.abs(g - r).mean() / np.abs(r).mean():.2e}")
+        assert np.isfinite(g).all() and err < 5e-3
+    c.close()

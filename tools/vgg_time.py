@@ -6,6 +6,7 @@ import __graft_entry__ as g
 from oracle import synth
 pkg = g.load_package(); dev = torch.device("cuda:0"); stream = torch.cuda.Stream(); ctx = pkg.Context(0, stream)
 ctx.load_vgg19_weights(synth.vgg19_weights(19))
+ctx.set_vgg_engine(int(os.environ.get("NCT_VGG_ENGINE", "0")))
 side = int(sys.argv[1]) if len(sys.argv) > 1 else 700
 img = torch.from_numpy(synth.pair(0, side, side)[0]).to(dev)
 GF = {0: 355.5, 1: 346.3, 2: 110.1 + 0, 3: 55.9, 4: 1.7}
