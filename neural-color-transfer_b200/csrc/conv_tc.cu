@@ -11,9 +11,14 @@
 //   im2col buffer and no padding pass exist.  128-byte rows, SWIZZLE_128B = the canonical K-major UMMA layout.
 // * B operand = weights re-laid out once to [Cout][tap][Cin] (K-major), 2-D TMA box {32 k, BN}.
 // * Warp-specialised CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-//   warps 2-5 = epilogue (tcgen05.ld -> +bias -> ReLU -> NHWC store).  4-stage smem ring with full/empty mbarriers;
-//   tcgen05.commit releases a stage when the MMAs reading it have retired.
-// * Precision: kind::tf32 reads the FP32 operands with a 10-bit mantissa, accumulates in FP32.
+//   warps 2-5 = epilogue (tcgen05.ld -> +bias -> ReLU -> NHWC store).  Multi-stage smem ring with full/empty
+//   mbarriers; tcgen05.commit releases a stage when the MMAs reading it have retired.
+// * Precision.  kind::tf32 TRUNCATES the FP32 operands to a 10-bit mantissa (measured: tools/tf32_probe.py) and
+//   accumulates in FP32.  X3 = false: plain TF32 (~9e-3 of the feature range after 13 layers).  X3 = true ("3xTF32"):
+//   every operand x is split exactly into trunc(x) + lo(x); the products a*b_hi + a_hi*b_lo + a_lo*b_hi are three MMAs
+//   into the same accumulator (the hardware truncation of the full-precision operand IS the hi part, the lo parts are
+//   separate tensors: weights split once, activations by the producing layer's epilogue) -- FP32-level accuracy at
+//   tensor-core speed.
 #include "nct_internal.h"
 #include <cuda.h>
 #include <cstring>
@@ -22,7 +27,6 @@ namespace {
 
 constexpr int TILE_W = 16, TILE_H = 8, BM = TILE_W * TILE_H;   // 128 output pixels per CTA
 constexpr int BK = 32;                                         // 32 fp32 = 128 bytes = one swizzle row
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 4;                           // 16 KB
 constexpr int NTHREADS = 192;
 
@@ -96,13 +100,20 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <int BN>
+struct ConvMaps {
+    CUtensorMap a, a_lo, b, b_lo;
+};
+
+template <int BN, bool X3>
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float *__restrict__ bias,
-                  float *__restrict__ out, int H, int W, int Cin, int Cout, int tiles_x)
+conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const float *__restrict__ bias, float *__restrict__ out,
+                  float *__restrict__ out_lo, int H, int W, int Cin, int Cout, int tiles_x)
 {
+    constexpr int STAGES = X3 ? 3 : 4;
     constexpr int B_BYTES = BN * BK * 4;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_BYTES + B_BYTES);
+    // stage layout: A | B | (A_lo | B_lo)
+    constexpr int OFF_B = A_BYTES, OFF_ALO = A_BYTES + B_BYTES, OFF_BLO = 2 * A_BYTES + B_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t bar_base = base + STAGES * STAGE_BYTES;            // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
@@ -144,10 +155,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (kb >= STAGES) mbar_wait(empty_bar(s), (uint32_t)(((kb / STAGES) - 1) & 1));
                 const int tap = kb / kchunks, kc = (kb % kchunks) * BK;
                 const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                const uint32_t a_dst = base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                const uint32_t st = base + s * STAGE_BYTES;
                 mbar_expect_tx(full_bar(s), (uint32_t)STAGE_BYTES);
-                tma_load_3d(a_dst, &tmA, full_bar(s), kc, tile_x0 + dx, tile_y0 + dy);
-                tma_load_2d(b_dst, &tmB, full_bar(s), kb * BK, n0);
+                tma_load_3d(st, &maps.a, full_bar(s), kc, tile_x0 + dx, tile_y0 + dy);
+                tma_load_2d(st + OFF_B, &maps.b, full_bar(s), kb * BK, n0);
+                if (X3) {
+                    tma_load_3d(st + OFF_ALO, &maps.a_lo, full_bar(s), kc, tile_x0 + dx, tile_y0 + dy);
+                    tma_load_2d(st + OFF_BLO, &maps.b_lo, full_bar(s), kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -158,13 +173,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int s = kb % STAGES;
                 mbar_wait(full_bar(s), (uint32_t)((kb / STAGES) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = base + s * STAGE_BYTES, b_addr = a_addr + A_BYTES;
-                const uint64_t adesc = make_desc_sw128(a_addr), bdesc = make_desc_sw128(b_addr);
+                const uint32_t st = base + s * STAGE_BYTES;
+                const uint64_t adesc = make_desc_sw128(st), bdesc = make_desc_sw128(st + OFF_B);
+                const uint64_t alo = make_desc_sw128(st + OFF_ALO), blo = make_desc_sw128(st + OFF_BLO);
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {  // UMMA_K = 8 for tf32: advance 32 bytes inside the 128-byte swizzle row
-                    umma_tf32(tmem_base, adesc + (uint64_t)((k * 32) >> 4), bdesc + (uint64_t)((k * 32) >> 4), idesc, (kb | k) != 0);
+                    const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                    if (X3) {  // small terms first, then the main product
+                        umma_tf32(tmem_base, alo + adv, bdesc + adv, idesc, (kb | k) != 0);
+                        umma_tf32(tmem_base, adesc + adv, blo + adv, idesc, 1u);
+                        umma_tf32(tmem_base, adesc + adv, bdesc + adv, idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_base, adesc + adv, bdesc + adv, idesc, (kb | k) != 0);
+                    }
                 }
-                umma_commit(empty_bar(s));                 // frees the smem stage once these MMAs have read it
+                umma_commit(empty_bar(s));                     // frees the smem stage once these MMAs have read it
                 if (kb == KB - 1) umma_commit(tmem_full_bar);  // accumulator complete
             }
         }
@@ -176,7 +199,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int m = lg * 32 + lane;                      // pixel index inside the tile = TMEM lane
         const int x = tile_x0 + (m % TILE_W), y = tile_y0 + (m / TILE_W);
         const bool valid = x < W && y < H;
-        float *dst = out + ((size_t)y * W + x) * Cout + n0;
+        const size_t off = ((size_t)y * W + x) * Cout + n0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
@@ -201,7 +224,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     o.y = fmaxf(__uint_as_float(r[j + 1]) + bb.y, 0.f);
                     o.z = fmaxf(__uint_as_float(r[j + 2]) + bb.z, 0.f);
                     o.w = fmaxf(__uint_as_float(r[j + 3]) + bb.w, 0.f);
-                    *reinterpret_cast<float4 *>(dst + c0 + j) = o;
+                    *reinterpret_cast<float4 *>(out + off + c0 + j) = o;
+                    if (X3) {  // residual of the tensor core's operand truncation, exact in FP32
+                        float4 l;
+                        l.x = o.x - __uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u);
+                        l.y = o.y - __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u);
+                        l.z = o.z - __uint_as_float(__float_as_uint(o.z) & 0xFFFFE000u);
+                        l.w = o.w - __uint_as_float(__float_as_uint(o.w) & 0xFFFFE000u);
+                        *reinterpret_cast<float4 *>(out_lo + off + c0 + j) = l;
+                    }
                 }
             }
         }
@@ -211,6 +242,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// lo(x) = x - trunc_tf32(x) elementwise (weights once; activations that did not come out of the tensor-core epilogue)
+__global__ void tf32_residual_kernel(const float *__restrict__ x, float *__restrict__ lo, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float v = x[i];
+        lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     }
 }
 
@@ -230,46 +271,70 @@ EncodeTiledFn get_encode_fn()
     return fn;
 }
 
+int encode_act(nct_ctx *ctx, EncodeTiledFn encode, CUtensorMap *m, const float *ptr, int H, int W, int C)
+{
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4};
+    cuuint32_t box[3] = {BK, TILE_W, TILE_H};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return nct_fail(ctx, NCT_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
+    return NCT_OK;
+}
+
+int encode_wgt(nct_ctx *ctx, EncodeTiledFn encode, CUtensorMap *m, const float *ptr, int Cin, int Cout, int BN)
+{
+    cuuint64_t dims[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)9 * Cin * 4};
+    cuuint32_t box[2] = {BK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return nct_fail(ctx, NCT_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    return NCT_OK;
+}
+
+template <int BN, bool X3>
+int launch(nct_ctx *ctx, const ConvMaps &maps, const float *bias, float *out, float *out_lo, int H, int W, int Cin, int Cout)
+{
+    constexpr int STAGES = X3 ? 3 : 4;
+    const int tiles_x = nct_div_up(W, TILE_W), tiles_y = nct_div_up(H, TILE_H);
+    dim3 grid(tiles_x * tiles_y, Cout / BN);
+    const size_t smem = (size_t)STAGES * (X3 ? 2 : 1) * (A_BYTES + BN * BK * 4) + 8 * (2 * STAGES + 2) + 1024;
+    NCT_CUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3x3_tc_kernel<BN, X3><<<grid, NTHREADS, smem, ctx->stream>>>(maps, bias, out, out_lo, H, W, Cin, Cout, tiles_x);
+    NCT_CHECK_LAUNCH(ctx);
+    return NCT_OK;
+}
+
 }  // namespace
 
-// in: NHWC FP32 [H][W][Cin]; w_kmajor: [Cout][9*Cin] (k = tap*Cin + c); out: NHWC [H][W][Cout] = relu(conv + bias)
-int nct_conv3x3_tensorcore(nct_ctx *ctx, const float *in, const float *w_kmajor, const float *bias, float *out, int H, int W, int Cin,
-                           int Cout)
+int nct_tf32_residual(nct_ctx *ctx, const float *x, float *lo, size_t n)
+{
+    tf32_residual_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(x, lo, n);
+    NCT_CHECK_LAUNCH(ctx);
+    return NCT_OK;
+}
+
+// in: NHWC FP32 [H][W][Cin]; w_kmajor: [Cout][9*Cin] (k = tap*Cin + c); out: NHWC [H][W][Cout] = relu(conv + bias).
+// in_lo / w_lo / out_lo non-null selects the 3xTF32 variant (in_lo = in - trunc(in), w_lo likewise; out_lo is produced).
+int nct_conv3x3_tensorcore(nct_ctx *ctx, const float *in, const float *in_lo, const float *w_kmajor, const float *w_lo, const float *bias,
+                           float *out, float *out_lo, int H, int W, int Cin, int Cout)
 {
     NCT_REQUIRE(ctx, Cin % BK == 0 && Cin >= 64, "tensor-core conv needs Cin %% 32 == 0 and >= 64 (got %d)", Cin);
     NCT_REQUIRE(ctx, Cout % 64 == 0, "tensor-core conv needs Cout %% 64 == 0 (got %d)", Cout);
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) return nct_fail(ctx, NCT_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const bool x3 = in_lo && w_lo && out_lo;
     const int BN = (Cout % 128 == 0) ? 128 : 64;
-    CUtensorMap tmA, tmB;
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H};
-        cuuint64_t strides[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4};
-        cuuint32_t box[3] = {BK, TILE_W, TILE_H};
-        cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return nct_fail(ctx, NCT_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
-    }
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)9 * Cin, (cuuint64_t)Cout};
-        cuuint64_t strides[1] = {(cuuint64_t)9 * Cin * 4};
-        cuuint32_t box[2] = {BK, (cuuint32_t)BN};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w_kmajor, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return nct_fail(ctx, NCT_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
-    }
-    const int tiles_x = nct_div_up(W, TILE_W), tiles_y = nct_div_up(H, TILE_H);
-    dim3 grid(tiles_x * tiles_y, Cout / BN);
-    const size_t smem = (size_t)STAGES * (A_BYTES + BN * BK * 4) + 8 * (2 * STAGES + 2) + 1024;
-    if (BN == 128) {
-        NCT_CUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv3x3_tc_kernel<128><<<grid, NTHREADS, smem, ctx->stream>>>(tmA, tmB, bias, out, H, W, Cin, Cout, tiles_x);
-    } else {
-        NCT_CUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv3x3_tc_kernel<64><<<grid, NTHREADS, smem, ctx->stream>>>(tmA, tmB, bias, out, H, W, Cin, Cout, tiles_x);
-    }
-    NCT_CHECK_LAUNCH(ctx);
-    return NCT_OK;
+    ConvMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc = encode_act(ctx, encode, &maps.a, in, H, W, Cin);
+    if (!rc) rc = encode_wgt(ctx, encode, &maps.b, w_kmajor, Cin, Cout, BN);
+    if (!rc && x3) rc = encode_act(ctx, encode, &maps.a_lo, in_lo, H, W, Cin);
+    if (!rc && x3) rc = encode_wgt(ctx, encode, &maps.b_lo, w_lo, Cin, Cout, BN);
+    if (rc) return rc;
+    if (BN == 128) return x3 ? launch<128, true>(ctx, maps, bias, out, out_lo, H, W, Cin, Cout) : launch<128, false>(ctx, maps, bias, out, out_lo, H, W, Cin, Cout);
+    return x3 ? launch<64, true>(ctx, maps, bias, out, out_lo, H, W, Cin, Cout) : launch<64, false>(ctx, maps, bias, out, out_lo, H, W, Cin, Cout);
 }
