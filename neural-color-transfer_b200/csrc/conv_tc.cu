@@ -15,10 +15,11 @@
 //   mbarriers; tcgen05.commit releases a stage when the MMAs reading it have retired.
 // * Precision.  kind::tf32 TRUNCATES the FP32 operands to a 10-bit mantissa (measured: tools/tf32_probe.py) and
 //   accumulates in FP32.  X3 = false: plain TF32 (~9e-3 of the feature range after 13 layers).  X3 = true ("3xTF32"):
-//   every operand x is split exactly into trunc(x) + lo(x); the products a*b_hi + a_hi*b_lo + a_lo*b_hi are three MMAs
-//   into the same accumulator (the hardware truncation of the full-precision operand IS the hi part, the lo parts are
-//   separate tensors: weights split once, activations by the producing layer's epilogue) -- FP32-level accuracy at
-//   tensor-core speed.
+//   every operand x is split exactly into hi = rne_tf32(x) and lo = x - hi (weights once on the host, activations by the
+//   producing layer's epilogue); a_lo*b_hi + a_hi*b_lo + a_hi*b_hi are three MMAs into the same accumulator.  hi is
+//   exactly representable, so the hardware truncation only touches the last bit of the lo parts: FP32-level accuracy
+//   at tensor-core speed.  (A first version that let the hardware truncate the full-precision operand and stored
+//   only the truncation remainder was biased: 1.9e-4 of the feature range after 13 layers.)
 #include "nct_internal.h"
 #include <cuda.h>
 #include <cstring>
@@ -100,6 +101,24 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// round-to-nearest-even to TF32's 11 significant bits (finite inputs)
+__host__ __device__ __forceinline__ float tf32_rne(float v)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(v);
+    b += 0x00000FFFu + ((b >> 13) & 1u);
+    return __uint_as_float(b & 0xFFFFE000u);
+#else
+    uint32_t b;
+    memcpy(&b, &v, 4);
+    b += 0x00000FFFu + ((b >> 13) & 1u);
+    b &= 0xFFFFE000u;
+    float r;
+    memcpy(&r, &b, 4);
+    return r;
+#endif
+}
+
 struct ConvMaps {
     CUtensorMap a, a_lo, b, b_lo;
 };
@@ -107,7 +126,7 @@ struct ConvMaps {
 template <int BN, bool X3>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const float *__restrict__ bias, float *__restrict__ out,
-                  float *__restrict__ out_lo, int H, int W, int Cin, int Cout, int tiles_x)
+                  float *__restrict__ out_hi, float *__restrict__ out_lo, int H, int W, int Cin, int Cout, int tiles_x)
 {
     constexpr int STAGES = X3 ? 3 : 4;
     constexpr int B_BYTES = BN * BK * 4;
@@ -224,13 +243,14 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const float *__restrict
                     o.y = fmaxf(__uint_as_float(r[j + 1]) + bb.y, 0.f);
                     o.z = fmaxf(__uint_as_float(r[j + 2]) + bb.z, 0.f);
                     o.w = fmaxf(__uint_as_float(r[j + 3]) + bb.w, 0.f);
-                    *reinterpret_cast<float4 *>(out + off + c0 + j) = o;
-                    if (X3) {  // residual of the tensor core's operand truncation, exact in FP32
-                        float4 l;
-                        l.x = o.x - __uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u);
-                        l.y = o.y - __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u);
-                        l.z = o.z - __uint_as_float(__float_as_uint(o.z) & 0xFFFFE000u);
-                        l.w = o.w - __uint_as_float(__float_as_uint(o.w) & 0xFFFFE000u);
+                    if (out) *reinterpret_cast<float4 *>(out + off + c0 + j) = o;
+                    if (X3) {  // exact split o = hi + lo, hi = o rounded to TF32 (so the tensor core reads it unchanged)
+                        float4 hh, l;
+                        hh.x = tf32_rne(o.x); l.x = o.x - hh.x;
+                        hh.y = tf32_rne(o.y); l.y = o.y - hh.y;
+                        hh.z = tf32_rne(o.z); l.z = o.z - hh.z;
+                        hh.w = tf32_rne(o.w); l.w = o.w - hh.w;
+                        *reinterpret_cast<float4 *>(out_hi + off + c0 + j) = hh;
                         *reinterpret_cast<float4 *>(out_lo + off + c0 + j) = l;
                     }
                 }
@@ -245,13 +265,14 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const float *__restrict
     }
 }
 
-// lo(x) = x - trunc_tf32(x) elementwise (weights once; activations that did not come out of the tensor-core epilogue)
-__global__ void tf32_residual_kernel(const float *__restrict__ x, float *__restrict__ lo, size_t n)
+// exact split x = hi + lo with hi = rne_tf32(x) (activations that did not come out of the tensor-core epilogue)
+__global__ void tf32_split_kernel(const float *__restrict__ x, float *__restrict__ hi, float *__restrict__ lo, size_t n)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        const float v = x[i];
-        lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        const float v = x[i], h = tf32_rne(v);
+        hi[i] = h;
+        lo[i] = v - h;
     }
 }
 
@@ -296,37 +317,48 @@ int encode_wgt(nct_ctx *ctx, EncodeTiledFn encode, CUtensorMap *m, const float *
 }
 
 template <int BN, bool X3>
-int launch(nct_ctx *ctx, const ConvMaps &maps, const float *bias, float *out, float *out_lo, int H, int W, int Cin, int Cout)
+int launch(nct_ctx *ctx, const ConvMaps &maps, const float *bias, float *out, float *out_hi, float *out_lo, int H, int W, int Cin, int Cout)
 {
     constexpr int STAGES = X3 ? 3 : 4;
     const int tiles_x = nct_div_up(W, TILE_W), tiles_y = nct_div_up(H, TILE_H);
     dim3 grid(tiles_x * tiles_y, Cout / BN);
     const size_t smem = (size_t)STAGES * (X3 ? 2 : 1) * (A_BYTES + BN * BK * 4) + 8 * (2 * STAGES + 2) + 1024;
     NCT_CUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv3x3_tc_kernel<BN, X3><<<grid, NTHREADS, smem, ctx->stream>>>(maps, bias, out, out_lo, H, W, Cin, Cout, tiles_x);
+    conv3x3_tc_kernel<BN, X3><<<grid, NTHREADS, smem, ctx->stream>>>(maps, bias, out, out_hi, out_lo, H, W, Cin, Cout, tiles_x);
     NCT_CHECK_LAUNCH(ctx);
     return NCT_OK;
 }
 
 }  // namespace
 
-int nct_tf32_residual(nct_ctx *ctx, const float *x, float *lo, size_t n)
+int nct_tf32_split(nct_ctx *ctx, const float *x, float *hi, float *lo, size_t n)
 {
-    tf32_residual_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(x, lo, n);
+    tf32_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(x, hi, lo, n);
     NCT_CHECK_LAUNCH(ctx);
     return NCT_OK;
 }
 
+void nct_tf32_split_host(const float *x, float *hi, float *lo, size_t n)
+{
+    for (size_t i = 0; i < n; ++i) {
+        hi[i] = tf32_rne(x[i]);
+        lo[i] = x[i] - hi[i];
+    }
+}
+
 // in: NHWC FP32 [H][W][Cin]; w_kmajor: [Cout][9*Cin] (k = tap*Cin + c); out: NHWC [H][W][Cout] = relu(conv + bias).
-// in_lo / w_lo / out_lo non-null selects the 3xTF32 variant (in_lo = in - trunc(in), w_lo likewise; out_lo is produced).
+// Plain TF32: in / w are the FP32 tensors (truncated by the hardware), in_lo = w_lo = out_hi = out_lo = NULL.
+// 3xTF32: in / w are the TF32-rounded hi parts, in_lo / w_lo the exact remainders; out_hi / out_lo receive the split of the
+// result, out (the full FP32 result) may be NULL when nobody needs it.
 int nct_conv3x3_tensorcore(nct_ctx *ctx, const float *in, const float *in_lo, const float *w_kmajor, const float *w_lo, const float *bias,
-                           float *out, float *out_lo, int H, int W, int Cin, int Cout)
+                           float *out, float *out_hi, float *out_lo, int H, int W, int Cin, int Cout)
 {
     NCT_REQUIRE(ctx, Cin % BK == 0 && Cin >= 64, "tensor-core conv needs Cin %% 32 == 0 and >= 64 (got %d)", Cin);
     NCT_REQUIRE(ctx, Cout % 64 == 0, "tensor-core conv needs Cout %% 64 == 0 (got %d)", Cout);
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) return nct_fail(ctx, NCT_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-    const bool x3 = in_lo && w_lo && out_lo;
+    const bool x3 = in_lo && w_lo && out_lo && out_hi;
+    NCT_REQUIRE(ctx, x3 || out, "plain TF32 conv needs an output buffer");
     const int BN = (Cout % 128 == 0) ? 128 : 64;
     ConvMaps maps;
     memset(&maps, 0, sizeof(maps));
@@ -335,6 +367,6 @@ int nct_conv3x3_tensorcore(nct_ctx *ctx, const float *in, const float *in_lo, co
     if (!rc && x3) rc = encode_act(ctx, encode, &maps.a_lo, in_lo, H, W, Cin);
     if (!rc && x3) rc = encode_wgt(ctx, encode, &maps.b_lo, w_lo, Cin, Cout, BN);
     if (rc) return rc;
-    if (BN == 128) return x3 ? launch<128, true>(ctx, maps, bias, out, out_lo, H, W, Cin, Cout) : launch<128, false>(ctx, maps, bias, out, out_lo, H, W, Cin, Cout);
-    return x3 ? launch<64, true>(ctx, maps, bias, out, out_lo, H, W, Cin, Cout) : launch<64, false>(ctx, maps, bias, out, out_lo, H, W, Cin, Cout);
+    if (BN == 128) return x3 ? launch<128, true>(ctx, maps, bias, out, out_hi, out_lo, H, W, Cin, Cout) : launch<128, false>(ctx, maps, bias, out, out_hi, out_lo, H, W, Cin, Cout);
+    return x3 ? launch<64, true>(ctx, maps, bias, out, out_hi, out_lo, H, W, Cin, Cout) : launch<64, false>(ctx, maps, bias, out, out_hi, out_lo, H, W, Cin, Cout);
 }

@@ -33,15 +33,17 @@ const ConvSpec kTrunk[13] = {
 struct VggState {
     float *w[13] = {nullptr};   // [9][cin][cout]      (CUDA-core engine)
     float *wk[13] = {nullptr};  // [cout][9][cin]      (K-major, tensor-core engines)
-    float *wk_lo[13] = {nullptr};  // wk - trunc_tf32(wk)  (3xTF32 engine)
+    float *wk_hi[13] = {nullptr};  // rne_tf32(wk)         (3xTF32 engine)
+    float *wk_lo[13] = {nullptr};  // wk - wk_hi
     float *b[13] = {nullptr};
     bool have[13] = {false};
     int engine = 0;             // 0 = FP32 CUDA cores, 1 = tcgen05 kind::tf32, 2 = tcgen05 3xTF32 (FP32-accurate)
 };
 
 int nct_conv3x3_tensorcore(nct_ctx *ctx, const float *in, const float *in_lo, const float *w_kmajor, const float *w_lo, const float *bias,
-                           float *out, float *out_lo, int H, int W, int Cin, int Cout);
-int nct_tf32_residual(nct_ctx *ctx, const float *x, float *lo, size_t n);
+                           float *out, float *out_hi, float *out_lo, int H, int W, int Cin, int Cout);
+int nct_tf32_split(nct_ctx *ctx, const float *x, float *hi, float *lo, size_t n);
+void nct_tf32_split_host(const float *x, float *hi, float *lo, size_t n);
 
 namespace {
 
@@ -218,6 +220,7 @@ void nct_vgg_free(nct_ctx *ctx)
         if (ctx->vgg->w[i]) cudaFree(ctx->vgg->w[i]);
         if (ctx->vgg->wk[i]) cudaFree(ctx->vgg->wk[i]);
         if (ctx->vgg->wk_lo[i]) cudaFree(ctx->vgg->wk_lo[i]);
+        if (ctx->vgg->wk_hi[i]) cudaFree(ctx->vgg->wk_hi[i]);
         if (ctx->vgg->b[i]) cudaFree(ctx->vgg->b[i]);
     }
     delete ctx->vgg;
@@ -255,16 +258,14 @@ int nct_vgg19_set_weights(nct_ctx *ctx, int layer, const float *w_oihw_host, con
     VggState *v = ctx->vgg;
     if (!v->wk[layer]) NCT_CUDA(ctx, cudaMalloc(&v->wk[layer], wkm.size() * sizeof(float)));
     NCT_CUDA(ctx, cudaMemcpy(v->wk[layer], wkm.data(), wkm.size() * sizeof(float), cudaMemcpyHostToDevice));
-    for (float &x : wkm) {  // residual of the tensor core's operand truncation (exact)
-        uint32_t bits;
-        memcpy(&bits, &x, 4);
-        bits &= 0xFFFFE000u;
-        float hi;
-        memcpy(&hi, &bits, 4);
-        x = x - hi;
+    {   // exact hi/lo split for the 3xTF32 engine
+        std::vector<float> hi(wkm.size()), lo(wkm.size());
+        nct_tf32_split_host(wkm.data(), hi.data(), lo.data(), wkm.size());
+        if (!v->wk_hi[layer]) NCT_CUDA(ctx, cudaMalloc(&v->wk_hi[layer], wkm.size() * sizeof(float)));
+        if (!v->wk_lo[layer]) NCT_CUDA(ctx, cudaMalloc(&v->wk_lo[layer], wkm.size() * sizeof(float)));
+        NCT_CUDA(ctx, cudaMemcpy(v->wk_hi[layer], hi.data(), wkm.size() * sizeof(float), cudaMemcpyHostToDevice));
+        NCT_CUDA(ctx, cudaMemcpy(v->wk_lo[layer], lo.data(), wkm.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
-    if (!v->wk_lo[layer]) NCT_CUDA(ctx, cudaMalloc(&v->wk_lo[layer], wkm.size() * sizeof(float)));
-    NCT_CUDA(ctx, cudaMemcpy(v->wk_lo[layer], wkm.data(), wkm.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (!v->w[layer]) NCT_CUDA(ctx, cudaMalloc(&v->w[layer], wt.size() * sizeof(float)));
     if (!v->b[layer]) NCT_CUDA(ctx, cudaMalloc(&v->b[layer], cout * sizeof(float)));
     NCT_CUDA(ctx, cudaMemcpy(v->w[layer], wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -319,20 +320,26 @@ int nct_vgg19_features(nct_ctx *ctx, const uint8_t *bgr_dev, int h, int w, int d
     // 3xTF32: every activation travels with its truncation residual
     const bool x3 = v->engine == 2;
     float *lo_bufs[2] = {nullptr, nullptr}, *lo_feat[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float *hi_bufs[2] = {nullptr, nullptr}, *hi_feat[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (x3) {
         lo_bufs[0] = (float *)nct_scratch(ctx, "vgg_act0_lo", sizeof(float) * max_act);
         lo_bufs[1] = (float *)nct_scratch(ctx, "vgg_act1_lo", sizeof(float) * max_act);
+        hi_bufs[0] = (float *)nct_scratch(ctx, "vgg_act0_hi", sizeof(float) * max_act);
+        hi_bufs[1] = (float *)nct_scratch(ctx, "vgg_act1_hi", sizeof(float) * max_act);
+        if (!hi_bufs[0] || !hi_bufs[1]) return NCT_ERR_NOMEM;
         int dims[5][3];
         nct_vgg19_level_dims(h, w, dims);
         char name[32];
         for (int l = deepest_level; l <= 4; ++l) {
             snprintf(name, sizeof(name), "vgg_feat_lo%d", l);
             lo_feat[l] = (float *)nct_scratch(ctx, name, sizeof(float) * (size_t)dims[l][0] * dims[l][1] * dims[l][2]);
-            if (!lo_feat[l]) return NCT_ERR_NOMEM;
+            snprintf(name, sizeof(name), "vgg_feat_hi%d", l);
+            hi_feat[l] = (float *)nct_scratch(ctx, name, sizeof(float) * (size_t)dims[l][0] * dims[l][1] * dims[l][2]);
+            if (!lo_feat[l] || !hi_feat[l]) return NCT_ERR_NOMEM;
         }
         if (!lo_bufs[0] || !lo_bufs[1]) return NCT_ERR_NOMEM;
     }
-    const float *cur_lo = nullptr;
+    const float *cur_lo = nullptr, *cur_hi = nullptr;
     preprocess_kernel<<<nct_div_up(h * w, 256), 256, 0, ctx->stream>>>(bgr_dev, inp, h * w);
     NCT_CHECK_LAUNCH(ctx);
 
@@ -350,10 +357,11 @@ int nct_vgg19_features(nct_ctx *ctx, const uint8_t *bgr_dev, int h, int w, int d
             maxpool_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(cur, dst, H, W, L.cin, Ho, Wo);
             NCT_CHECK_LAUNCH(ctx);
             if (x3) {
-                float *dlo = lo_bufs[flip ^ 1];
-                int rc = nct_tf32_residual(ctx, dst, dlo, (size_t)Ho * Wo * L.cin);
+                float *dlo = lo_bufs[flip ^ 1], *dhi = hi_bufs[flip ^ 1];
+                int rc = nct_tf32_split(ctx, dst, dhi, dlo, (size_t)Ho * Wo * L.cin);
                 if (rc) return rc;
                 cur_lo = dlo;
+                cur_hi = dhi;
             }
             cur = dst;
             H = Ho;
@@ -361,16 +369,18 @@ int nct_vgg19_features(nct_ctx *ctx, const uint8_t *bgr_dev, int h, int w, int d
         }
         float *dst = (L.level >= 0) ? feat_dev[L.level] : bufs[flip];
         float *dst_lo = x3 ? ((L.level >= 0) ? lo_feat[L.level] : lo_bufs[flip]) : nullptr;
+        float *dst_hi = x3 ? ((L.level >= 0) ? hi_feat[L.level] : hi_bufs[flip]) : nullptr;
         if (L.level < 0) flip ^= 1;
         if (dst == cur) return nct_fail(ctx, NCT_ERR_STATE, "internal: aliasing activation buffers");
         if (i == 0) {
             conv_first_kernel<<<nct_div_up(H * W * 4, 256), 256, 0, ctx->stream>>>(cur, v->w[0], v->b[0], dst, H, W);
         } else if (v->engine >= 1) {
-            int rc = nct_conv3x3_tensorcore(ctx, cur, x3 ? cur_lo : nullptr, v->wk[i], x3 ? v->wk_lo[i] : nullptr, v->b[i], dst, dst_lo, H, W,
-                                            L.cin, L.cout);
+            int rc = nct_conv3x3_tensorcore(ctx, x3 ? cur_hi : cur, x3 ? cur_lo : nullptr, x3 ? v->wk_hi[i] : v->wk[i],
+                                            x3 ? v->wk_lo[i] : nullptr, v->b[i], dst, dst_hi, dst_lo, H, W, L.cin, L.cout);
             if (rc) return rc;
             cur = dst;
             cur_lo = dst_lo;
+            cur_hi = dst_hi;
             continue;
         } else {
             dim3 grid(nct_div_up(H * W, BM), L.cout / BN);
@@ -378,9 +388,10 @@ int nct_vgg19_features(nct_ctx *ctx, const uint8_t *bgr_dev, int h, int w, int d
         }
         NCT_CHECK_LAUNCH(ctx);
         if (x3 && i == 0) {  // conv1_1 runs on CUDA cores: split its output here
-            int rc = nct_tf32_residual(ctx, dst, dst_lo, (size_t)H * W * L.cout);
+            int rc = nct_tf32_split(ctx, dst, dst_hi, dst_lo, (size_t)H * W * L.cout);
             if (rc) return rc;
             cur_lo = dst_lo;
+            cur_hi = dst_hi;
         }
         cur = dst;
     }
