@@ -32,6 +32,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 PM_CHANNELS = [512, 512, 256, 128, 64]
+ENGINE_NAME = {0: "fp32 CUDA cores", 1: "tcgen05 kind::tf32", 2: "tcgen05 3xTF32 (hi/lo split, 2e-4 of the feature range vs fp32)"}
+ENGINE_DTYPE = {0: "f32", 1: "tf32", 2: "tf32x3"}
 
 
 def read_peaks():
@@ -145,6 +147,7 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     ctx = pkg.Context(local, stream)
     ctx.load_vgg19_weights(synth.vgg19_weights(19))
+    ctx.set_vgg_engine(args.vgg_engine)
     side = args.side
     npairs = 2  # two distinct pairs per rank, alternated, so no step re-reads the previous step's data
     pairs = [synth.pair(rank * npairs + j, side, side) for j in range(npairs)]
@@ -204,6 +207,21 @@ def run_ours(args):
         prof = ctx.profile_report()
         ctx.profile(False)
 
+        # ---- the same steps with the FP32 CUDA-core convolution engine (the engine the 1e-4 VGG parity test pins)
+        fp32_ms = None
+        if args.vgg_engine != 0:
+            ctx.set_vgg_engine(0)
+            ctx.transfer_pair_dev(*dev_pairs[0], cfg, out_dev)
+            stream.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for i in range(args.steps):
+                ctx.transfer_pair_dev(*dev_pairs[i % npairs], cfg, out_dev)
+            f1.record(stream)
+            stream.synchronize()
+            fp32_ms = f0.elapsed_time(f1)
+            ctx.set_vgg_engine(args.vgg_engine)
+
         # ---- end to end through the host-buffer C-ABI entry point (pinned host buffers, H2D + D2H inside)
         for i in range(min(args.warmup, 2)):
             ctx.transfer_pair(*pin_pairs[i % npairs], cfg, out_pin)
@@ -215,10 +233,10 @@ def run_ours(args):
         e2e_s = time.perf_counter() - t0
         barrier()
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s * 1e3, fp32_ms or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, fp32_ms = float(t[0]), float(t[1]), float(t[2])
     mp_per_step = world * side * side / 1e6
     value = mp_per_step * args.steps / (dev_ms / 1e3)
     e2e = mp_per_step * args.steps / (e2e_ms / 1e3)
@@ -232,10 +250,11 @@ def run_ours(args):
         line = {
             "metric": "MP/s full L=5->1 pipeline", "value": round(value, 4), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 2), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (features, PatchMatch) / f64 (colour solves) / u8 (images)", "data": "synthetic",
+            "vs_baseline": None, "dtype": ENGINE_DTYPE[args.vgg_engine] + " (VGG) / f32 (PatchMatch) / f64 (colour solves) / u8 (images)",
+            "data": "synthetic",
             "config": {"workload": f"single {side}x{side} pair per GPU per step, full L=5->1 pyramid, BDS=2.0 (BASELINE configs[1])",
                        "pairs_per_step": world, "l2_policy": "inputs larger than L2: ~1.1 GB working set per pair, two alternating pairs",
-                       "vgg_weights": "synthetic He-normal (seed 19)", "collective": "NCCL gather of result images to rank 0" if world > 1 else "none"},
+                       "vgg_weights": "synthetic He-normal (seed 19)", "vgg_engine": ENGINE_NAME[args.vgg_engine], "collective": "NCCL gather of result images to rank 0" if world > 1 else "none"},
             "e2e": {"value": round(e2e, 4), "unit": "MP/s", "h2d_bytes_per_step": 2 * side * side * 3, "d2h_bytes_per_step": side * side * 3,
                     "ms_per_step": round(e2e_ms / args.steps, 2)},
             "gpu_launches": int(launches),
@@ -247,6 +266,8 @@ def run_ours(args):
             "stage_ms_per_step": {k: round(v[0] / args.steps, 2) for k, v in prof.items()},
             "clocks": sampler.summary(),
         }
+        if fp32_ms:
+            line["value_fp32_conv_engine"] = round(mp_per_step * args.steps / (fp32_ms / 1e3), 4)
         if world == 1 and not args.no_cpu_baseline:
             threads = len(os.sched_getaffinity(0))
             mps, dt, stages = cpu_pipeline_mps(args.cpu_side, "canonical", threads)
@@ -268,6 +289,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-side", type=int, default=256, help="side of the bounded CPU sample pair")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--vgg-engine", type=int, default=2, choices=[0, 1, 2],
+                    help="convolution engine: 0 fp32 CUDA cores, 1 tcgen05 tf32, 2 tcgen05 3xTF32 (default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

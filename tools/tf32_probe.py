@@ -28,9 +28,10 @@ for frac in (0.25, 0.75):
 # ---- (2) pipeline: engine 1 vs engine 0
 wts = synth.vgg19_weights(19)
 outs = []
-for eng in (0, 1):
+for eng in (0, 1, 2):
     ctx = pkg.Context(0); ctx.load_vgg19_weights(wts); ctx.set_vgg_engine(eng)
     c, s = synth.pair(0, 700, 700)
     outs.append(ctx.transfer_pair(c, s)); ctx.close()
-print(json.dumps(dict(test="pipeline 700^2 tf32 vs fp32 engine", psnr=pipeline.psnr(outs[0], outs[1]),
-                      mean_abs=float(np.abs(outs[0].astype(int) - outs[1].astype(int)).mean()))))
+for k, name in ((1, "tf32"), (2, "3xtf32")):
+    print(json.dumps(dict(test=f"pipeline 700^2 {name} vs fp32 engine", psnr=pipeline.psnr(outs[0], outs[k]),
+                          mean_abs=float(np.abs(outs[0].astype(int) - outs[k].astype(int)).mean()))))
