@@ -185,17 +185,16 @@ __device__ __forceinline__ void load_query(QueryPatch<C> &q, const float *__rest
     }
 }
 
-// canonical-order patch distance (oracle decision D2); all lanes return the same value
+// candidate patch rows -> registers (all loads of a candidate are issued back to back)
 template <int C>
-__device__ __forceinline__ float eval_dist(const QueryPatch<C> &q, const float *__restrict__ b, int bx, int by,
-                                           int bw, int bh, int lane)
+__device__ __forceinline__ void load_cand(const QueryPatch<C> &q, const float *__restrict__ b, int bx, int by, int bw, int bh,
+                                          int lane, float4 (&bv)[PMTraits<C>::PPL * PMTraits<C>::VPL], unsigned &valid)
 {
     using T = PMTraits<C>;
-    const unsigned valid = q.amask & patch_mask(bx, by, bw, bh);
+    valid = q.amask & patch_mask(bx, by, bw, bh);
     const int j = (T::GROUPS == 1) ? lane : (lane % T::V);
     const int g = (T::GROUPS == 1) ? 0 : lane / T::V;
     const float *b_base = b + ((size_t)by * bw + bx) * C + j * 4;
-    float4 bv[T::PPL * T::VPL];
 #pragma unroll
     for (int i = 0; i < T::PPL; ++i) {
         const int pi = i * T::GROUPS + g;
@@ -208,6 +207,15 @@ __device__ __forceinline__ float eval_dist(const QueryPatch<C> &q, const float *
             bv[i * T::VPL + k] = v;
         }
     }
+}
+
+// canonical-order patch distance (oracle decision D2) from loaded rows; all lanes return the same value
+template <int C>
+__device__ __forceinline__ float reduce_cand(const QueryPatch<C> &q, const float4 (&bv)[PMTraits<C>::PPL * PMTraits<C>::VPL],
+                                             unsigned valid, int lane)
+{
+    using T = PMTraits<C>;
+    const int g = (T::GROUPS == 1) ? 0 : lane / T::V;
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < T::PPL; ++i) {
@@ -230,7 +238,19 @@ __device__ __forceinline__ float eval_dist(const QueryPatch<C> &q, const float *
 }
 
 template <int C>
-__global__ void __launch_bounds__(256) pm_step_kernel(const PMStep s)
+__device__ __forceinline__ float eval_dist(const QueryPatch<C> &q, const float *__restrict__ b, int bx, int by,
+                                           int bw, int bh, int lane)
+{
+    float4 bv[PMTraits<C>::PPL * PMTraits<C>::VPL];
+    unsigned valid;
+    load_cand<C>(q, b, bx, by, bw, bh, lane, bv, valid);
+    return reduce_cand<C>(q, bv, valid, lane);
+}
+
+// 128-thread CTAs (4 queries); C <= 128 is capped at 128 registers so that 4 CTAs = 16 warps stay resident per SM,
+// each with up to BATCH x PPL x VPL row loads in flight
+template <int C>
+__global__ void __launch_bounds__(128, (C <= 128) ? 4 : 1) pm_step_kernel(const PMStep s)
 {
     const int lane = threadIdx.x & 31;
     const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -283,13 +303,24 @@ __global__ void __launch_bounds__(256) pm_step_kernel(const PMStep s)
             }
         }
     }
+    // the distances do not depend on each other: issue the row loads of BATCH candidates before the first FMA
+    // (memory-level parallelism; the kernel is latency-bound, profiles/r1_pm_step_ncu.md)
+    constexpr int BATCH = (C <= 64) ? 4 : (C == 128 ? 2 : 1);
     float dc[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        dc[k] = 0.f;
-        if (use[k]) {
-            dc[k] = eval_dist<C>(q, D.b, int_to_x(cand[k]), int_to_y(cand[k]), bw, bh, lane);
-            n_eval++;
+    for (int k0 = 0; k0 < 4; k0 += BATCH) {
+        float4 bv[BATCH][PMTraits<C>::PPL * PMTraits<C>::VPL];
+        unsigned valid[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j)
+            if (use[k0 + j]) load_cand<C>(q, D.b, int_to_x(cand[k0 + j]), int_to_y(cand[k0 + j]), bw, bh, lane, bv[j], valid[j]);
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            dc[k0 + j] = 0.f;
+            if (use[k0 + j]) {
+                dc[k0 + j] = reduce_cand<C>(q, bv[j], valid[j], lane);
+                n_eval++;
+            }
         }
     }
 #pragma unroll
@@ -335,7 +366,7 @@ __global__ void __launch_bounds__(256) pm_step_kernel(const PMStep s)
 
 // iters == 0: only the initial distance (NCT/GeneralizedPatchMatch.cu:710-712)
 template <int C>
-__global__ void __launch_bounds__(256) pm_init_dist_kernel(const PMStep s)
+__global__ void __launch_bounds__(128) pm_init_dist_kernel(const PMStep s)
 {
     const int lane = threadIdx.x & 31;
     const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -354,11 +385,11 @@ __global__ void __launch_bounds__(256) pm_init_dist_kernel(const PMStep s)
 template <int C>
 int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1, int ndir)
 {
-    const int warps_per_block = 8;
+    const int warps_per_block = 4;
     const int blocks = nct_div_up(s.nq_total, warps_per_block);
     s.counters = ctx->pm_count_evals ? ctx->pm_counters : nullptr;
     if (iters == 0) {
-        pm_init_dist_kernel<C><<<blocks, 256, 0, ctx->stream>>>(s);
+        pm_init_dist_kernel<C><<<blocks, 128, 0, ctx->stream>>>(s);
         NCT_CHECK_LAUNCH(ctx);
         return NCT_OK;
     }
@@ -377,7 +408,7 @@ int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1
                 s.d[d].nnf_in = (step & 1) ? tmp[d] : user[d];
                 s.d[d].nnf_out = (step & 1) ? user[d] : tmp[d];
             }
-            pm_step_kernel<C><<<blocks, 256, 0, ctx->stream>>>(s);
+            pm_step_kernel<C><<<blocks, 128, 0, ctx->stream>>>(s);
             NCT_CHECK_LAUNCH(ctx);
         }
     return NCT_OK;
