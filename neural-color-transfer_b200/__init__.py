@@ -17,7 +17,7 @@ import os
 from typing import Optional, Sequence
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnct.so")
+LIB_PATH = os.environ.get("NCT_LIB") or os.path.join(_HERE, "libnct.so")  # NCT_LIB: experiment builds only
 
 c_ctx_p = C.c_void_p
 _i, _f, _d, _p, _ll = C.c_int, C.c_float, C.c_double, C.c_void_p, C.c_longlong

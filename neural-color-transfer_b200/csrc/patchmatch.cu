@@ -86,6 +86,20 @@ __global__ void xorwow_table_kernel(float *__restrict__ out, int ncols, int ndra
 }
 
 // ------------------------------------------------------------------ PatchMatch step
+// tuning knobs (overridable with -D for experiments; defaults = measured best, profiles/r1_pm_tuning.md)
+#ifndef PM_A_REGS_MAXC
+#define PM_A_REGS_MAXC 256   // keep the query patch in registers up to this channel count
+#endif
+#ifndef PM_BATCH_SMALL
+#define PM_BATCH_SMALL 1     // propagation candidates whose row loads are issued together for C <= 64 (C == 128: half)
+#endif
+#ifndef PM_TPB
+#define PM_TPB 128
+#endif
+#ifndef PM_MINB_SMALL
+#define PM_MINB_SMALL 6      // __launch_bounds__ min CTAs/SM for C <= 128 (caps registers at 85)
+#endif
+
 struct PMDir {
     const float *a;          // query features   [ah][aw][C]
     const float *b;          // target features  [bh][bw][C]
@@ -114,7 +128,7 @@ struct PMTraits {
     static constexpr int VPL = (V >= 32) ? V / 32 : 1;     // vectors per lane per pixel
     static constexpr int GROUPS = (V >= 32) ? 1 : 32 / V;  // patch pixels processed side by side
     static constexpr int PPL = (9 + GROUPS - 1) / GROUPS;  // patch pixels per lane
-    static constexpr bool A_IN_REGS = (C <= 256);
+    static constexpr bool A_IN_REGS = (C <= PM_A_REGS_MAXC);
 };
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
@@ -247,10 +261,8 @@ __device__ __forceinline__ float eval_dist(const QueryPatch<C> &q, const float *
     return reduce_cand<C>(q, bv, valid, lane);
 }
 
-// 128-thread CTAs (4 queries); C <= 128 is capped at 128 registers so that 4 CTAs = 16 warps stay resident per SM,
-// each with up to BATCH x PPL x VPL row loads in flight
 template <int C>
-__global__ void __launch_bounds__(128, (C <= 128) ? 4 : 1) pm_step_kernel(const PMStep s)
+__global__ void __launch_bounds__(PM_TPB, (C <= 128) ? PM_MINB_SMALL : 1) pm_step_kernel(const PMStep s)
 {
     const int lane = threadIdx.x & 31;
     const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -305,7 +317,7 @@ __global__ void __launch_bounds__(128, (C <= 128) ? 4 : 1) pm_step_kernel(const 
     }
     // the distances do not depend on each other: issue the row loads of BATCH candidates before the first FMA
     // (memory-level parallelism; the kernel is latency-bound, profiles/r1_pm_step_ncu.md)
-    constexpr int BATCH = (C <= 64) ? 4 : (C == 128 ? 2 : 1);
+    constexpr int BATCH = (C <= 64) ? PM_BATCH_SMALL : (C == 128 ? (PM_BATCH_SMALL > 1 ? PM_BATCH_SMALL / 2 : 1) : 1);
     float dc[4];
 #pragma unroll
     for (int k0 = 0; k0 < 4; k0 += BATCH) {
@@ -366,7 +378,7 @@ __global__ void __launch_bounds__(128, (C <= 128) ? 4 : 1) pm_step_kernel(const 
 
 // iters == 0: only the initial distance (NCT/GeneralizedPatchMatch.cu:710-712)
 template <int C>
-__global__ void __launch_bounds__(128) pm_init_dist_kernel(const PMStep s)
+__global__ void __launch_bounds__(PM_TPB) pm_init_dist_kernel(const PMStep s)
 {
     const int lane = threadIdx.x & 31;
     const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -385,11 +397,11 @@ __global__ void __launch_bounds__(128) pm_init_dist_kernel(const PMStep s)
 template <int C>
 int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1, int ndir)
 {
-    const int warps_per_block = 4;
+    const int warps_per_block = PM_TPB / 32;
     const int blocks = nct_div_up(s.nq_total, warps_per_block);
     s.counters = ctx->pm_count_evals ? ctx->pm_counters : nullptr;
     if (iters == 0) {
-        pm_init_dist_kernel<C><<<blocks, 128, 0, ctx->stream>>>(s);
+        pm_init_dist_kernel<C><<<blocks, PM_TPB, 0, ctx->stream>>>(s);
         NCT_CHECK_LAUNCH(ctx);
         return NCT_OK;
     }
@@ -408,7 +420,7 @@ int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1
                 s.d[d].nnf_in = (step & 1) ? tmp[d] : user[d];
                 s.d[d].nnf_out = (step & 1) ? user[d] : tmp[d];
             }
-            pm_step_kernel<C><<<blocks, 128, 0, ctx->stream>>>(s);
+            pm_step_kernel<C><<<blocks, PM_TPB, 0, ctx->stream>>>(s);
             NCT_CHECK_LAUNCH(ctx);
         }
     return NCT_OK;
