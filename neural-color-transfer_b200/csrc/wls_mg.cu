@@ -3,12 +3,13 @@
 // Replaces solve_WLS_roughness_cpu + solve_direct_cpu / MKL PARDISO (CT/ColorTransfer.cpp:951-1125,
 // CT/SparseSolver_CPU.cpp:104-286): the reference factorises the 490k x 490k SPD matrix on the CPU at every level.
 // Here: CG in FP64 preconditioned by one symmetric V(2,2)-cycle of an aggregation multigrid:
-//   * coarse grids by 2x2 aggregation down to a single node; the coarse operators are the exact Galerkin products
-//     P^T M P for piecewise-constant P -- again 5-point graph Laplacians (edge weight = sum of the fine edges
-//     crossing two aggregates) plus the summed diagonal, so strongly varying edge weights (1e0..1e5) are handled
-//     algebraically;
-//   * damped Jacobi smoothing (omega = 0.8), coarse correction scaled by ALPHA (over-correction of unsmoothed
-//     aggregation); pre- and post-smoothing are symmetric, so plain PCG applies;
+//   * coarse grids by 2x2 cell aggregation down to a single node; coarse operators stay 5-point graph Laplacians:
+//     diagonal = sum over the aggregate, edge weight = 1/2 x (sum of the fine edges crossing two aggregates) -- the
+//     piecewise-constant Galerkin product with the 2-D rediscretisation factor, so strongly varying edge weights
+//     (1e0..1e5) are coarsened algebraically;
+//   * transfer operators: cell-centred linear interpolation P (9/16, 3/16, 3/16, 1/16) and R = P^T.  (The first
+//     version used piecewise-constant P with over-correction: 60-150 PCG iterations, profiles/r1_wls_tuning.md.)
+//   * damped Jacobi smoothing (omega = 0.8), symmetric V(2,2), so plain PCG applies;
 //   * levels with <= 1024 nodes are processed by ONE thread block (the whole bottom of the V-cycle in one launch),
 //     the large levels use 4 launches each; every launch is bandwidth-bound on [n][6] double records.
 // Stops at a relative residual (default 1e-10) at which the result is indistinguishable from the direct solve at the
@@ -24,7 +25,8 @@ constexpr int MAX_LEVELS = 14;
 // smoothing weight and over-correction of the coarse-grid correction (tunable through NCT_MG_OMEGA / NCT_MG_ALPHA for
 // experiments; the defaults are the measured optimum on the 700x700 workload, profiles/r1_wls_tuning.md)
 __constant__ double c_omega = 0.8;
-__constant__ double c_alpha = 1.6;
+__constant__ double c_alpha = 1.0;
+__constant__ double c_edge_scale = 0.5;  // coarse edge weight = scale x (sum of the fine edges crossing two aggregates)
 #define OMEGA c_omega
 #define ALPHA c_alpha
 
@@ -106,34 +108,70 @@ __device__ __forceinline__ void op_residual(const MgLevel &L, int i, double (&r)
     for (int k = 0; k < 6; ++k) r[k] = bi[k] - d * xi[k] + s[k];
 }
 
-// coarse right-hand side of coarse node c = sum of the fine residuals of its (up to 4) children
+// interpolation weight of fine index x towards coarse index J (cell-centred linear interpolation; at the border the
+// missing neighbour's weight folds into the parent, so that restriction = prolongation^T exactly)
+__device__ __forceinline__ double pw(int x, int J, int nc)
+{
+    const int Jp = x >> 1;
+    int Jn = Jp + ((x & 1) ? 1 : -1);
+    Jn = min(max(Jn, 0), nc - 1);
+    return (Jp == J ? 0.75 : 0.0) + (Jn == J ? 0.25 : 0.0);
+}
+
+// t = b - M x (residual), one node
+__device__ __forceinline__ void op_residual_to_t(const MgLevel &L, int i)
+{
+    double r[6];
+    op_residual(L, i, r);
+    st6(L.t, i, r);
+}
+
+// coarse right-hand side = P^T r: gather of the 4 x 4 fine residuals around the aggregate with weights pw(y) * pw(x)
 __device__ __forceinline__ void op_restrict(const MgLevel &F, const MgLevel &Cc, int c)
 {
     const int J = c % Cc.W, I = c / Cc.W;
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (int dy = 0; dy < 2; ++dy)
-        for (int dx = 0; dx < 2; ++dx) {
-            const int y = 2 * I + dy, x = 2 * J + dx;
-            if (y < F.H && x < F.W) {
-                double r[6];
-                op_residual(F, y * F.W + x, r);
+    for (int y = 2 * I - 1; y <= 2 * I + 2; ++y) {
+        if (y < 0 || y >= F.H) continue;
+        const double wy = pw(y, I, Cc.H);
+        if (wy == 0.0) continue;
+        for (int x = 2 * J - 1; x <= 2 * J + 2; ++x) {
+            if (x < 0 || x >= F.W) continue;
+            const double w = wy * pw(x, J, Cc.W);
+            if (w == 0.0) continue;
+            double r[6];
+            ld6(F.t, y * F.W + x, r);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) acc[k] += r[k];
-            }
+            for (int k = 0; k < 6; ++k) acc[k] += w * r[k];
         }
+    }
     st6(Cc.b, c, acc);
+}
+
+// (P xc) at fine node j
+__device__ __forceinline__ void prolong_at(const MgLevel &F, const MgLevel &Cc, int j, double (&o)[6])
+{
+    const int x = j % F.W, y = j / F.W;
+    const int Jp = x >> 1, Ip = y >> 1;
+    const int Jn = min(max(Jp + ((x & 1) ? 1 : -1), 0), Cc.W - 1), In = min(max(Ip + ((y & 1) ? 1 : -1), 0), Cc.H - 1);
+    double c00[6], c01[6], c10[6], c11[6];
+    ld6(Cc.x, Ip * Cc.W + Jp, c00);
+    ld6(Cc.x, Ip * Cc.W + Jn, c01);
+    ld6(Cc.x, In * Cc.W + Jp, c10);
+    ld6(Cc.x, In * Cc.W + Jn, c11);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[k] = 0.5625 * c00[k] + 0.1875 * c01[k] + 0.1875 * c10[k] + 0.0625 * c11[k];
 }
 
 // y = x + ALPHA * P xc ; out = y + omega D^-1 (b - M y)   (prolongation fused with the first post-smoothing sweep)
 __device__ __forceinline__ void op_prolong_smooth(const MgLevel &F, const MgLevel &Cc, int i)
 {
     auto gety = [&](int j, double (&yj)[6]) {
-        double xc[6];
+        double pc[6];
         ld6(F.x, j, yj);
-        const int jx = j % F.W, jy = j / F.W;
-        ld6(Cc.x, (jy >> 1) * Cc.W + (jx >> 1), xc);
+        prolong_at(F, Cc, j, pc);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) yj[k] += ALPHA * xc[k];
+        for (int k = 0; k < 6; ++k) yj[k] += ALPHA * pc[k];
     };
     double yi[6], bi[6], s[6], o[6];
     gety(i, yi);
@@ -164,6 +202,11 @@ __global__ void __launch_bounds__(TPB) mg_presmooth2_kernel(MgLevel L)
     const int i = blockIdx.x * TPB + threadIdx.x;
     if (i < L.n) op_presmooth2(L, i);
 }
+__global__ void __launch_bounds__(TPB) mg_residual_kernel(MgLevel L)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    if (i < L.n) op_residual_to_t(L, i);
+}
 __global__ void __launch_bounds__(TPB) mg_restrict_kernel(MgLevel F, MgLevel Cc)
 {
     const int c = blockIdx.x * TPB + threadIdx.x;
@@ -188,6 +231,8 @@ __global__ void __launch_bounds__(512) mg_bottom_kernel(MgHierarchy h)
     for (int k = h.bottom; k < last; ++k) {
         const MgLevel &L = h.lv[k];
         for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_presmooth2(L, i);
+        __syncthreads();
+        for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_residual_to_t(L, i);
         __syncthreads();
         const MgLevel &Cc = h.lv[k + 1];
         for (int c = threadIdx.x; c < Cc.n; c += blockDim.x) op_restrict(L, Cc, c);
@@ -245,8 +290,8 @@ __global__ void mg_coarsen_kernel(MgLevel F, int Hc, int Wc, double *__restrict_
             if (x < F.W) vy += F.wy[(2 * I + 1) * F.W + x];
         }
     rsum[c] = rs;
-    wx[c] = vx;
-    wy[c] = vy;
+    wx[c] = c_edge_scale * vx;
+    wy[c] = c_edge_scale * vy;
 }
 
 __global__ void mg_diag_kernel(MgLevel L)
@@ -491,6 +536,8 @@ int vcycle(nct_ctx *ctx, const MgHierarchy &h)
         const MgLevel &L = h.lv[k];
         mg_presmooth2_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L);
         NCT_CHECK_LAUNCH(ctx);
+        mg_residual_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L);
+        NCT_CHECK_LAUNCH(ctx);
         const MgLevel &Cc = h.lv[k + 1];
         mg_restrict_kernel<<<nct_div_up(Cc.n, TPB), TPB, 0, ctx->stream>>>(L, Cc);
         NCT_CHECK_LAUNCH(ctx);
@@ -528,12 +575,13 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
             if (eo) { double v = atof(eo); cudaMemcpyToSymbol(c_omega, &v, sizeof(v)); }
             if (ea) { double v = atof(ea); cudaMemcpyToSymbol(c_alpha, &v, sizeof(v)); }
         }
-        if (!getenv("NCT_MG_ALPHA")) {
-            // measured (profiles/r1_wls_tuning.md): over-correction pays when diffusion dominates (coarse pyramid
-            // levels, lambda' >= 1), plain correction is better once the screening term matters
-            const double v = lam >= 1.0 ? 1.4 : 1.0;
-            cudaMemcpyToSymbolAsync(c_alpha, &v, sizeof(v), 0, cudaMemcpyHostToDevice, ctx->stream);
-            cudaStreamSynchronize(ctx->stream);
+        {
+            static bool tuned2 = false;
+            if (!tuned2) {
+                tuned2 = true;
+                const char *es = getenv("NCT_MG_EDGE_SCALE");
+                if (es) { double v = atof(es); cudaMemcpyToSymbol(c_edge_scale, &v, sizeof(v)); }
+            }
         }
     }
     // ---- level geometry
