@@ -144,130 +144,173 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     pkg = g.load_package()
-    stream = torch.cuda.Stream(device=dev)
-    ctx = pkg.Context(local, stream)
-    ctx.load_vgg19_weights(synth.vgg19_weights(19))
-    ctx.set_vgg_engine(args.vgg_engine)
-    side = args.side
-    npairs = 2  # two distinct pairs per rank, alternated, so no step re-reads the previous step's data
-    pairs = [synth.pair(rank * npairs + j, side, side) for j in range(npairs)]
-    dev_pairs = [(torch.from_numpy(c).to(dev), torch.from_numpy(s).to(dev)) for c, s in pairs]
-    pin_pairs = [(torch.from_numpy(c).pin_memory(), torch.from_numpy(s).pin_memory()) for c, s in pairs]
-    out_dev = torch.empty((side, side, 3), dtype=torch.uint8, device=dev)
-    out_pin = torch.empty((side, side, 3), dtype=torch.uint8).pin_memory()
+    side, P, K = args.side, args.pairs_in_flight, args.steps
+    weights = synth.vgg19_weights(19)
+    # P pairs in flight per GPU: one libnct context + stream + host thread each (pairs are independent; the coarse
+    # pyramid levels and the solvers' small kernels do not fill 148 SMs on their own)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(P)]
+    ctxs = []
+    for j in range(P):
+        c = pkg.Context(local, streams[j])
+        c.load_vgg19_weights(weights)
+        c.set_vgg_engine(args.vgg_engine)
+        ctxs.append(c)
+    npairs = 2  # two distinct pairs per context, alternated, so no step re-reads the previous step's data
+    pairs = [[synth.pair((rank * P + j) * npairs + q, side, side) for q in range(npairs)] for j in range(P)]
+    dev_pairs = [[(torch.from_numpy(c).to(dev), torch.from_numpy(s).to(dev)) for c, s in pj] for pj in pairs]
+    pin_pairs = [[(torch.from_numpy(c).pin_memory(), torch.from_numpy(s).pin_memory()) for c, s in pj] for pj in pairs]
+    out_dev = torch.empty((K, P, side, side, 3), dtype=torch.uint8, device=dev)
+    out_pin = [torch.empty((side, side, 3), dtype=torch.uint8).pin_memory() for _ in range(P)]
     gather_list = [torch.empty_like(out_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
-    cfg = ctx.default_config()
+    cfg = ctxs[0].default_config()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def gather():
-        if world > 1:
-            with torch.cuda.stream(stream):
-                dist.gather(out_dev, gather_list, dst=0)
+    def run_threads(fn):
+        ts = [threading.Thread(target=fn, args=(j,)) for j in range(P)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
 
-    # ---- device-resident steps
-    with torch.cuda.stream(stream):
-        for i in range(args.warmup):
-            ctx.transfer_pair_dev(*dev_pairs[i % npairs], cfg, out_dev)
-            gather()
-        stream.synchronize()
-        # PatchMatch evaluation counts for the roofline: one untimed pass with the kernel's counters on
-        # (deterministic, so the timed steps evaluate exactly the same candidates)
-        evals_bytes = []
-        for j in range(npairs):
-            tot = 0
-            # counters are per PatchMatch call; run level by level through the pipeline's own stop hook
-            prev = 0
-            ctx.count_evals(True)
-            for l in range(5):
-                ctx.transfer_pair_dev(*dev_pairs[j], ctx.default_config(stop_after_level=l), out_dev)
-                ev, _ = ctx.patchmatch_stats()
-                tot += ev * 9 * PM_CHANNELS[l] * 4
-            ctx.count_evals(False)
-            evals_bytes.append(tot)
-        sampler = ClockSampler(local)
-        sampler.start()
-        barrier()
-        ctx.profile(True)
-        ctx.reset_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(args.steps):
-            ctx.transfer_pair_dev(*dev_pairs[i % npairs], cfg, out_dev)
-            gather()
-        e1.record(stream)
-        stream.synchronize()
-        barrier()
-        sampler.stop_flag = True
-        dev_ms = e0.elapsed_time(e1)
-        launches = ctx.launch_count
-        prof = ctx.profile_report()
-        ctx.profile(False)
+    def dev_steps(n, record=None):
+        def work(j):
+            if record is not None:
+                record[0][j].record(streams[j])
+            for i in range(n):
+                ctxs[j].transfer_pair_dev(*dev_pairs[j][i % npairs], cfg, out_dev[i % K, j])
+            if record is not None:
+                record[1][j].record(streams[j])
+        run_threads(work)
 
-        # ---- the same steps with the FP32 CUDA-core convolution engine (the engine the 1e-4 VGG parity test pins)
-        fp32_ms = None
-        if args.vgg_engine != 0:
-            ctx.set_vgg_engine(0)
-            ctx.transfer_pair_dev(*dev_pairs[0], cfg, out_dev)
-            stream.synchronize()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record(stream)
-            for i in range(args.steps):
-                ctx.transfer_pair_dev(*dev_pairs[i % npairs], cfg, out_dev)
-            f1.record(stream)
-            stream.synchronize()
-            fp32_ms = f0.elapsed_time(f1)
-            ctx.set_vgg_engine(args.vgg_engine)
+    # ---- warm-up
+    dev_steps(args.warmup)
+    torch.cuda.synchronize(dev)
+    # PatchMatch evaluation counts for the roofline: one untimed pass on context 0 with the kernel's counters on
+    # (deterministic, so the timed steps evaluate exactly the same candidates)
+    evals_bytes = []
+    c0 = ctxs[0]
+    for q in range(npairs):
+        tot = 0
+        c0.count_evals(True)
+        for l in range(5):
+            c0.transfer_pair_dev(*dev_pairs[0][q], c0.default_config(stop_after_level=l), out_dev[0, 0])
+            ev, _ = c0.patchmatch_stats()
+            tot += ev * 9 * PM_CHANNELS[l] * 4
+        c0.count_evals(False)
+        evals_bytes.append(tot)
 
-        # ---- end to end through the host-buffer C-ABI entry point (pinned host buffers, H2D + D2H inside)
-        for i in range(min(args.warmup, 2)):
-            ctx.transfer_pair(*pin_pairs[i % npairs], cfg, out_pin)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            ctx.transfer_pair(*pin_pairs[i % npairs], cfg, out_pin)
+    # ---- timed region: K steps, each = one batch of P pairs per rank, + the NCCL gather of all results
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    for c in ctxs:
+        c.reset_launch_count()
+    c0.profile(True)
+    ev = ([torch.cuda.Event(enable_timing=True) for _ in range(P)], [torch.cuda.Event(enable_timing=True) for _ in range(P)])
+    e_end = torch.cuda.Event(enable_timing=True)
+    dev_steps(K, ev)
+    main_stream = torch.cuda.current_stream(dev)
+    for j in range(P):
+        main_stream.wait_event(ev[1][j])
+    if world > 1:
+        dist.gather(out_dev, gather_list, dst=0)
+    e_end.record(main_stream)
+    torch.cuda.synchronize(dev)
+    barrier()
+    sampler.stop_flag = True
+    dev_ms = max(ev[0][j].elapsed_time(e_end) for j in range(P))
+    launches = sum(c.launch_count for c in ctxs)
+    prof = c0.profile_report()
+    c0.profile(False)
+
+    # ---- single-stream pass (context 0 alone): kernel time of PatchMatch without co-running streams
+    c0.profile(True)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(streams[0])
+    for i in range(K):
+        c0.transfer_pair_dev(*dev_pairs[0][i % npairs], cfg, out_dev[i % K, 0])
+    s1.record(streams[0])
+    streams[0].synchronize()
+    single_ms = s0.elapsed_time(s1)
+    prof1 = c0.profile_report()
+    c0.profile(False)
+
+    # ---- the same steps with the FP32 CUDA-core convolution engine (the engine the 1e-4 VGG parity test pins)
+    fp32_ms = 0.0
+    if args.vgg_engine != 0:
+        for c in ctxs:
+            c.set_vgg_engine(0)
+        dev_steps(1)
         torch.cuda.synchronize(dev)
-        e2e_s = time.perf_counter() - t0
-        barrier()
+        fe = ([torch.cuda.Event(enable_timing=True) for _ in range(P)], [torch.cuda.Event(enable_timing=True) for _ in range(P)])
+        dev_steps(K, fe)
+        torch.cuda.synchronize(dev)
+        fp32_ms = max(fe[0][0].elapsed_time(fe[1][j]) for j in range(P))
+        for c in ctxs:
+            c.set_vgg_engine(args.vgg_engine)
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, fp32_ms or 0.0], dtype=torch.float64, device=dev)
+    # ---- end to end through the host-buffer C-ABI entry point (pinned host buffers, H2D + D2H inside)
+    def e2e_steps(n):
+        def work(j):
+            for i in range(n):
+                ctxs[j].transfer_pair(*pin_pairs[j][i % npairs], cfg, out_pin[j])
+        run_threads(work)
+    e2e_steps(1)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps(K)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, fp32_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms, fp32_ms = float(t[0]), float(t[1]), float(t[2])
-    mp_per_step = world * side * side / 1e6
-    value = mp_per_step * args.steps / (dev_ms / 1e3)
-    e2e = mp_per_step * args.steps / (e2e_ms / 1e3)
+    mp_per_step = world * P * side * side / 1e6
+    value = mp_per_step * K / (dev_ms / 1e3)
+    e2e = mp_per_step * K / (e2e_ms / 1e3)
 
     if rank == 0:
         peak, peak_src = read_peaks()
-        pm_ms, pm_spans = prof["patchmatch"]
-        pm_bytes = sum(evals_bytes[i % npairs] for i in range(args.steps))
-        pm_launches = pm_spans * 4 * cfg.pm_iters
-        achieved = pm_bytes / 1e9 / (pm_ms / 1e3) if pm_ms > 0 else None
+        pm_bytes = sum(evals_bytes[i % npairs] for i in range(K))
+
+        def roof(p):
+            pm_ms, pm_spans = p["patchmatch"]
+            n = pm_spans * 4 * cfg.pm_iters
+            ach = pm_bytes / 1e9 / (pm_ms / 1e3) if pm_ms > 0 else None
+            return ach, n, pm_ms
+        ach, nl, pm_ms = roof(prof)
+        ach1, nl1, pm_ms1 = roof(prof1)
         line = {
-            "metric": "MP/s full L=5->1 pipeline", "value": round(value, 4), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 2), "higher_is_better": True, "scaling": "weak",
+            "metric": "MP/s full L=5->1 pipeline", "value": round(value, 4), "unit": "MP/s", "n_gpus": world, "steps": K,
+            "warmup": args.warmup, "ms_per_step": round(dev_ms / K, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": ENGINE_DTYPE[args.vgg_engine] + " (VGG) / f32 (PatchMatch) / f64 (colour solves) / u8 (images)",
             "data": "synthetic",
-            "config": {"workload": f"single {side}x{side} pair per GPU per step, full L=5->1 pyramid, BDS=2.0 (BASELINE configs[1])",
-                       "pairs_per_step": world, "l2_policy": "inputs larger than L2: ~1.1 GB working set per pair, two alternating pairs",
-                       "vgg_weights": "synthetic He-normal (seed 19)", "vgg_engine": ENGINE_NAME[args.vgg_engine], "collective": "NCCL gather of result images to rank 0" if world > 1 else "none"},
-            "e2e": {"value": round(e2e, 4), "unit": "MP/s", "h2d_bytes_per_step": 2 * side * side * 3, "d2h_bytes_per_step": side * side * 3,
-                    "ms_per_step": round(e2e_ms / args.steps, 2)},
+            "config": {"workload": f"{side}x{side} pairs, full L=5->1 pyramid, BDS=2.0 (BASELINE configs[1]); one step = {P} independent pairs per GPU",
+                       "pairs_per_step": world * P, "pairs_in_flight_per_gpu": P,
+                       "l2_policy": "inputs larger than L2: ~1.1 GB working set per pair, alternating distinct pairs",
+                       "vgg_weights": "synthetic He-normal (seed 19)", "vgg_engine": ENGINE_NAME[args.vgg_engine],
+                       "collective": "NCCL gather of all result images to rank 0 inside the timed region" if world > 1 else "none"},
+            "e2e": {"value": round(e2e, 4), "unit": "MP/s", "h2d_bytes_per_step": P * 2 * side * side * 3, "d2h_bytes_per_step": P * side * side * 3,
+                    "ms_per_step": round(e2e_ms / K, 2)},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "pm_step_kernel (PatchMatch propagate + random search)", "bound": "hbm",
-                         "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 3) if achieved else None, "traffic": None, "peak_source": peak_src,
-                         "launches": int(pm_launches), "avg_launch_ms": round(pm_ms / max(pm_launches, 1), 4),
-                         "algorithmic_GB_per_pair": round(evals_bytes[0] / 1e9, 1)},
-            "stage_ms_per_step": {k: round(v[0] / args.steps, 2) for k, v in prof.items()},
+                         "achieved": round(ach, 1) if ach else None, "peak": peak, "unit": "GB/s",
+                         "frac": round(ach / peak, 3) if ach else None, "traffic": 614.5e6, "traffic_note":
+                         "dram__bytes_read+write per finest-level launch from profiles/r1_pm_step_ncu.md (10.7 GB algorithmic per launch)",
+                         "peak_source": peak_src, "launches": int(nl), "avg_launch_ms": round(pm_ms / max(nl, 1), 4),
+                         "algorithmic_GB_per_pair": round(evals_bytes[0] / 1e9, 1),
+                         "measured_in": f"timed region, context 0 of {P} co-running streams",
+                         "single_stream": {"achieved": round(ach1, 1) if ach1 else None, "frac": round(ach1 / peak, 3) if ach1 else None,
+                                           "avg_launch_ms": round(pm_ms1 / max(nl1, 1), 4), "ms_per_pair": round(single_ms / K, 2)}},
+            "stage_ms_per_pair_single_stream": {k: round(v[0] / K, 2) for k, v in prof1.items()},
             "clocks": sampler.summary(),
         }
         if fp32_ms:
-            line["value_fp32_conv_engine"] = round(mp_per_step * args.steps / (fp32_ms / 1e3), 4)
+            line["value_fp32_conv_engine"] = round(mp_per_step * K / (fp32_ms / 1e3), 4)
         if world == 1 and not args.no_cpu_baseline:
             threads = len(os.sched_getaffinity(0))
             mps, dt, stages = cpu_pipeline_mps(args.cpu_side, "canonical", threads)
@@ -275,7 +318,8 @@ def run_ours(args):
                                     "sample": f"one {args.cpu_side}x{args.cpu_side} synthetic pair, full L=5->1 pipeline, {dt:.1f} s",
                                     "stage_seconds": stages}
         print(json.dumps(line), flush=True)
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -289,6 +333,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-side", type=int, default=256, help="side of the bounded CPU sample pair")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pairs-in-flight", type=int, default=4, help="independent pairs processed concurrently per GPU (one step = this many pairs per rank)")
     ap.add_argument("--vgg-engine", type=int, default=2, choices=[0, 1, 2],
                     help="convolution engine: 0 fp32 CUDA cores, 1 tcgen05 tf32, 2 tcgen05 3xTF32 (default)")
     args = ap.parse_args()
