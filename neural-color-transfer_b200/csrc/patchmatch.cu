@@ -376,6 +376,207 @@ __global__ void __launch_bounds__(PM_TPB, (C <= 128) ? PM_MINB_SMALL : 1) pm_ste
     }
 }
 
+// ------------------------------------------------------------------ half-warp-per-query step kernel (C = 64, 128)
+// The finest levels are instruction-issue bound (profiles/r1_pm_tuning.md): of ~200 issued instructions per candidate
+// only 20 are FMAs.  Here a warp serves TWO queries: 16 lanes x float4 cover one 64-channel pixel row, so each lane
+// walks all nine patch pixels of its query (C = 128: two vectors per pixel) and every address / validity / dedup
+// instruction is shared by two queries.  The canonical reduction order (oracle D2) is preserved exactly: the two
+// 16-slot groups of the 32-slot order live in two accumulators per lane -- C = 64: patch pixels of even / odd index,
+// C = 128: vector j / vector j + 16 -- their sum is the butterfly's xor-16 step, the xor 8, 4, 2, 1 steps stay inside
+// the half warp.
+template <int C>
+struct HWTraits {
+    static constexpr int NV = C / 64;          // float4 vectors per lane per pixel (1 or 2)
+    static constexpr bool A_IN_REGS = (C == 64);
+};
+
+template <int C>
+struct HWQuery {
+    float4 a[HWTraits<C>::A_IN_REGS ? 9 : 1];
+    const float *a_base;
+    int aw;
+    unsigned amask;
+};
+
+template <int C>
+__device__ __forceinline__ float hw_eval(const HWQuery<C> &q, const float *__restrict__ b, int bx, int by, int bw, int bh, int j,
+                                         unsigned hmask)
+{
+    constexpr int NV = HWTraits<C>::NV;
+    const unsigned valid = q.amask & patch_mask(bx, by, bw, bh);
+    const float *b_base = b + ((size_t)by * bw + bx) * C + j * 4;
+    float4 bv[9 * NV];
+#pragma unroll
+    for (int pi = 0; pi < 9; ++pi) {
+        const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+        const bool ok = (valid >> pi) & 1u;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) v = ldg4(b_base + ((ptrdiff_t)dy * bw + dx) * C + k * 64);
+            bv[pi * NV + k] = v;
+        }
+    }
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int pi = 0; pi < 9; ++pi) {
+        const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+        if ((valid >> pi) & 1u) {
+            if (NV == 1) {
+                float4 av;
+                if (HWTraits<C>::A_IN_REGS) av = q.a[pi];
+                else av = ldg4(q.a_base + ((ptrdiff_t)dy * q.aw + dx) * C);
+                if (pi & 1) acc1 = fma4(av, bv[pi], acc1);
+                else acc0 = fma4(av, bv[pi], acc0);
+            } else {
+                const float4 a0 = ldg4(q.a_base + ((ptrdiff_t)dy * q.aw + dx) * C);
+                const float4 a1 = ldg4(q.a_base + ((ptrdiff_t)dy * q.aw + dx) * C + 64);
+                acc0 = fma4(a0, bv[pi * NV], acc0);
+                acc1 = fma4(a1, bv[pi * NV + 1], acc1);
+            }
+        }
+    }
+    float acc = __fadd_rn(acc0, acc1);  // == the xor-16 step of the 32-slot butterfly
+    acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 8));
+    acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 4));
+    acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 2));
+    acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 1));
+    return __fdiv_rn(-acc, (float)__popc(valid));
+}
+
+template <int C>
+__global__ void __launch_bounds__(128, 4) pm_step_hw_kernel(const PMStep s)
+{
+    const int lane = threadIdx.x & 31, half = lane >> 4, j = lane & 15;
+    const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+    const int qidx = (int)(((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5) * 2 + half);
+    if (qidx >= s.nq_total) return;  // whole half warps leave together; the shuffles below only name the own half
+    const int dsel = qidx >= s.nq0 ? 1 : 0;
+    const PMDir &D = s.d[dsel];
+    const int p = qidx - (dsel ? s.nq0 : 0);
+    const int aw = D.aw, ah = D.ah, bw = D.bw, bh = D.bh;
+    const int ax = p % aw, ay = p / aw;
+
+    HWQuery<C> q;
+    q.aw = aw;
+    q.amask = patch_mask(ax, ay, aw, ah);
+    q.a_base = D.a + ((size_t)ay * aw + ax) * C + j * 4;
+    if (HWTraits<C>::A_IN_REGS) {
+#pragma unroll
+        for (int pi = 0; pi < 9; ++pi) {
+            const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((q.amask >> pi) & 1u) v = ldg4(q.a_base + ((ptrdiff_t)dy * aw + dx) * C);
+            q.a[pi] = v;
+        }
+    }
+
+    const uint32_t v0 = D.nnf_in[p];
+    int xbest = int_to_x(v0), ybest = int_to_y(v0);
+    float dbest;
+    unsigned n_eval = 0, n_ref = 0;
+    if (s.first) {
+        dbest = hw_eval<C>(q, D.b, xbest, ybest, bw, bh, j, hmask);
+        n_eval++;
+        n_ref++;
+    } else {
+        dbest = D.nnd[p];
+    }
+
+    const int jump = s.jump;
+    uint32_t cand[4];
+    bool use[4];
+    {
+        const int qx[4] = {ax - jump, ax + jump, ax, ax};
+        const int qy[4] = {ay, ay, ay - jump, ay + jump};
+        const int sx[4] = {jump, -jump, 0, 0};
+        const int sy[4] = {0, 0, jump, -jump};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            use[k] = false;
+            cand[k] = 0;
+            if (qx[k] >= 0 && qx[k] < aw && qy[k] >= 0 && qy[k] < ah) {
+                const uint32_t vp = D.nnf_in[qy[k] * aw + qx[k]];
+                const int xp = int_to_x(vp) + sx[k], yp = int_to_y(vp) + sy[k];
+                if (yp >= 0 && yp < bh && xp >= 0 && xp < bw) {
+                    n_ref++;
+                    cand[k] = xy_to_int(xp, yp);
+                    bool dup = (cand[k] == v0);
+#pragma unroll
+                    for (int t = 0; t < k; ++t) dup = dup || (use[t] && cand[t] == cand[k]);
+                    use[k] = !dup;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (use[k]) {  // uniform inside a half warp
+            const float d = hw_eval<C>(q, D.b, int_to_x(cand[k]), int_to_y(cand[k]), bw, bh, j, hmask);
+            n_eval++;
+            if (d < dbest) {
+                dbest = d;
+                xbest = int_to_x(cand[k]);
+                ybest = int_to_y(cand[k]);
+            }
+        }
+    }
+    if (s.do_random) {
+        const float *u = D.rng + (size_t)ax * D.ndraws + (size_t)s.iter * 2 * D.n_mag;
+        int m = 0;
+        for (int mag = D.rs_start; mag >= 1; mag /= 2, ++m) {
+            const int xmin = max(xbest - mag, 0), xmax = min(xbest + mag + 1, bw);
+            const int ymin = max(ybest - mag, 0), ymax = min(ybest + mag + 1, bh);
+            const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
+            const int xp = xmin + (int)(__fmul_rn(u1, (float)(xmax - xmin))) % (xmax - xmin);
+            const int yp = ymin + (int)(__fmul_rn(u2, (float)(ymax - ymin))) % (ymax - ymin);
+            n_ref++;
+            if (xp == xbest && yp == ybest) continue;
+            n_eval++;
+            const float d = hw_eval<C>(q, D.b, xp, yp, bw, bh, j, hmask);
+            if (__fadd_rn(d, FLT_MIN) < dbest) {
+                dbest = d;
+                xbest = xp;
+                ybest = yp;
+            }
+        }
+    }
+    if (j == 0) {
+        D.nnf_out[p] = xy_to_int(xbest, ybest);
+        D.nnd[p] = dbest;
+        if (s.counters) {
+            atomicAdd(&s.counters[0], (unsigned long long)n_eval);
+            atomicAdd(&s.counters[1], (unsigned long long)n_ref);
+        }
+    }
+}
+
+template <int C>
+struct UseHalfWarp { static constexpr bool value = (C == 64 || C == 128); };
+
+template <int C, bool HW = UseHalfWarp<C>::value>
+struct StepLauncher {
+    static void go(const PMStep &s, cudaStream_t st)
+    {
+        const int blocks = nct_div_up(s.nq_total, PM_TPB / 32);
+        pm_step_kernel<C><<<blocks, PM_TPB, 0, st>>>(s);
+    }
+};
+template <int C>
+struct StepLauncher<C, true> {
+    static void go(const PMStep &s, cudaStream_t st)
+    {
+        static const bool legacy = getenv("NCT_PM_LEGACY") != nullptr;  // A/B switch for profiling
+        if (legacy) {
+            const int blocks = nct_div_up(s.nq_total, PM_TPB / 32);
+            pm_step_kernel<C><<<blocks, PM_TPB, 0, st>>>(s);
+        } else {
+            const int blocks = nct_div_up(s.nq_total, 8);  // 128 threads = 4 warps = 8 queries
+            pm_step_hw_kernel<C><<<blocks, 128, 0, st>>>(s);
+        }
+    }
+};
+
 // iters == 0: only the initial distance (NCT/GeneralizedPatchMatch.cu:710-712)
 template <int C>
 __global__ void __launch_bounds__(PM_TPB) pm_init_dist_kernel(const PMStep s)
@@ -420,7 +621,7 @@ int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1
                 s.d[d].nnf_in = (step & 1) ? tmp[d] : user[d];
                 s.d[d].nnf_out = (step & 1) ? user[d] : tmp[d];
             }
-            pm_step_kernel<C><<<blocks, PM_TPB, 0, ctx->stream>>>(s);
+            StepLauncher<C>::go(s, ctx->stream);
             NCT_CHECK_LAUNCH(ctx);
         }
     return NCT_OK;
