@@ -159,17 +159,22 @@ __global__ void nl_rev_fill_kernel(const uint32_t *__restrict__ sorted_vals, con
     rev_w2[t] = w2[flat];
 }
 
+// CG vectors are [pixel][6] records (a0 a1 a2 b0 b1 b2, 48 bytes): a neighbour gather touches two 32-byte sectors
+// (the first version kept the a and b blocks apart and recomputed p = r + beta p_old per neighbour: 8 sectors)
 __device__ __forceinline__ void load6(const double *__restrict__ v, int n, int i, double (&o)[6])
 {
-    const double *pa = v + (size_t)i * 3, *pb = v + (size_t)(n + i) * 3;
-    o[0] = pa[0]; o[1] = pa[1]; o[2] = pa[2];
-    o[3] = pb[0]; o[4] = pb[1]; o[5] = pb[2];
+    (void)n;
+    const double2 *q = reinterpret_cast<const double2 *>(v + (size_t)i * 6);
+    const double2 t0 = q[0], t1 = q[1], t2 = q[2];
+    o[0] = t0.x; o[1] = t0.y; o[2] = t1.x; o[3] = t1.y; o[4] = t2.x; o[5] = t2.y;
 }
 __device__ __forceinline__ void store6(double *__restrict__ v, int n, int i, const double (&o)[6])
 {
-    double *pa = v + (size_t)i * 3, *pb = v + (size_t)(n + i) * 3;
-    pa[0] = o[0]; pa[1] = o[1]; pa[2] = o[2];
-    pb[0] = o[3]; pb[1] = o[4]; pb[2] = o[5];
+    (void)n;
+    double2 *q = reinterpret_cast<double2 *>(v + (size_t)i * 6);
+    q[0] = make_double2(o[0], o[1]);
+    q[1] = make_double2(o[2], o[3]);
+    q[2] = make_double2(o[4], o[5]);
 }
 
 // y = (A^T A) x at pixel i, x given through a functor returning the 6 values of a pixel
@@ -245,27 +250,31 @@ __global__ void __launch_bounds__(TPB) nl_init_kernel(NlSystem S, const double *
     }
 }
 
-// p = r + beta p_old ; Ap = (A^T A) p ; alpha = r1 / (p.Ap)
-__global__ void __launch_bounds__(TPB) nl_spmv_kernel(NlSystem S, const double *__restrict__ r, const double *__restrict__ pold,
-                                                      double *__restrict__ pnew, double *__restrict__ Ap, NlScalars *sc,
+// p = beta p + r (in place, element-wise)
+__global__ void __launch_bounds__(TPB) nl_pupdate_kernel(int n, const double *__restrict__ r, double *__restrict__ p, const NlScalars *sc)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    const double beta[3] = {sc->beta[0], sc->beta[1], sc->beta[2]};
+    double ri[6], pi[6];
+    load6(r, n, i, ri);
+    load6(p, n, i, pi);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pi[k] = __dadd_rn(__dmul_rn(beta[k % 3], pi[k]), ri[k]);
+    store6(p, n, i, pi);
+}
+
+// Ap = (A^T A) p ; alpha = r1 / (p.Ap)
+__global__ void __launch_bounds__(TPB) nl_spmv_kernel(NlSystem S, const double *__restrict__ p, double *__restrict__ Ap, NlScalars *sc,
                                                       double *partials, unsigned *counter)
 {
     __shared__ double smem[3 * TPB / 32];
     const int i = blockIdx.x * TPB + threadIdx.x;
-    const double beta[3] = {sc->beta[0], sc->beta[1], sc->beta[2]};
     double dots[3] = {0.0, 0.0, 0.0};
-    auto getp = [&](int j, double (&o)[6]) {
-        double rj[6], pj[6];
-        load6(r, S.n, j, rj);
-        load6(pold, S.n, j, pj);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) o[k] = __dadd_rn(__dmul_rn(beta[k % 3], pj[k]), rj[k]);
-    };
     if (i < S.n) {
         double pi[6], api[6];
-        getp(i, pi);
-        store6(pnew, S.n, i, pi);
-        nl_apply(S, i, pi, getp, api);
+        load6(p, S.n, i, pi);
+        nl_apply(S, i, pi, [&](int j, double (&o)[6]) { load6(p, S.n, j, o); }, api);
         store6(Ap, S.n, i, api);
 #pragma unroll
         for (int c = 0; c < 3; ++c) dots[c] = __dadd_rn(__dmul_rn(pi[c], api[c]), __dmul_rn(pi[3 + c], api[3 + c]));
@@ -315,18 +324,20 @@ __global__ void __launch_bounds__(TPB) nl_update_kernel(int n, double *__restric
 
 __global__ void pack_ab_kernel(const double *__restrict__ a, const double *__restrict__ b, int n3, double *__restrict__ x)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = pixel * 3 + channel
     if (i < n3) {
-        x[i] = a[i];
-        x[n3 + i] = b[i];
+        const int px = i / 3, c = i % 3;
+        x[(size_t)px * 6 + c] = a[i];
+        x[(size_t)px * 6 + 3 + c] = b[i];
     }
 }
 __global__ void unpack_ab_kernel(const double *__restrict__ x, int n3, double *__restrict__ a, double *__restrict__ b)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n3) {
-        a[i] = x[i];
-        b[i] = x[n3 + i];
+        const int px = i / 3, c = i % 3;
+        a[i] = x[(size_t)px * 6 + c];
+        b[i] = x[(size_t)px * 6 + 3 + c];
     }
 }
 
@@ -601,13 +612,14 @@ int nct_solve_nonlocal(nct_ctx *ctx, double *a_dev, double *b_dev, const double 
     const int maxit = layer == 4 ? 50 : 100;  // CT/ColorTransfer.cpp:917
     nl_init_kernel<<<blocks, TPB, 0, ctx->stream>>>(S, x, r, p0, sc, tol2, partials, counter);
     NCT_CHECK_LAUNCH(ctx);
-    double *pold = p0, *pnew = p1;
+    (void)p1;
     for (int k = 1; k <= maxit; ++k) {
-        nl_spmv_kernel<<<blocks, TPB, 0, ctx->stream>>>(S, r, pold, pnew, Ap, sc, partials, counter);
+        nl_pupdate_kernel<<<blocks, TPB, 0, ctx->stream>>>(n, r, p0, sc);
         NCT_CHECK_LAUNCH(ctx);
-        nl_update_kernel<<<blocks, TPB, 0, ctx->stream>>>(n, x, r, pnew, Ap, sc, tol2, partials, counter);
+        nl_spmv_kernel<<<blocks, TPB, 0, ctx->stream>>>(S, p0, Ap, sc, partials, counter);
         NCT_CHECK_LAUNCH(ctx);
-        double *t = pold; pold = pnew; pnew = t;
+        nl_update_kernel<<<blocks, TPB, 0, ctx->stream>>>(n, x, r, p0, Ap, sc, tol2, partials, counter);
+        NCT_CHECK_LAUNCH(ctx);
     }
     unpack_ab_kernel<<<nct_div_up(n3, TPB), TPB, 0, ctx->stream>>>(x, n3, a_dev, b_dev);
     NCT_CHECK_LAUNCH(ctx);

@@ -1,42 +1,45 @@
-// Multigrid-preconditioned CG for the full-resolution WLS system (diag(rough) + L_g) x = diag(rough) x0, 6 right-hand sides.
+// Full-resolution WLS system (diag(rough) + L_g) x = diag(rough) x0, 6 right-hand sides: multigrid-preconditioned CG.
 //
 // Replaces solve_WLS_roughness_cpu + solve_direct_cpu / MKL PARDISO (CT/ColorTransfer.cpp:951-1125,
 // CT/SparseSolver_CPU.cpp:104-286): the reference factorises the 490k x 490k SPD matrix on the CPU at every level.
-// Here: CG in FP64 preconditioned by one symmetric V(2,2)-cycle of an aggregation multigrid:
-//   * coarse grids by 2x2 cell aggregation down to a single node; coarse operators stay 5-point graph Laplacians:
-//     diagonal = sum over the aggregate, edge weight = 1/2 x (sum of the fine edges crossing two aggregates) -- the
-//     piecewise-constant Galerkin product with the 2-D rediscretisation factor, so strongly varying edge weights
-//     (1e0..1e5) are coarsened algebraically;
-//   * transfer operators: cell-centred linear interpolation P (9/16, 3/16, 3/16, 1/16) and R = P^T.  (The first
-//     version used piecewise-constant P with over-correction: 60-150 PCG iterations, profiles/r1_wls_tuning.md.)
-//   * damped Jacobi smoothing (omega = 0.8), symmetric V(2,2), so plain PCG applies;
-//   * levels with <= 1024 nodes are processed by ONE thread block (the whole bottom of the V-cycle in one launch),
-//     the large levels use 4 launches each; every launch is bandwidth-bound on [n][6] double records.
-// Stops at a relative residual (default 1e-10) at which the result is indistinguishable from the direct solve at the
-// parity tolerance; the iteration count is data dependent, checked on the host every few iterations.
+//
+// Structure
+//   * CG in FP64 (x, r, p, Ap and every scalar; the operator is applied with FP64 weights), so the attainable
+//     accuracy is that of an FP64 solve: it stops at a relative residual (default 1e-8 in the pipeline) at which the
+//     maps agree with the direct solve far below the parity tolerance.
+//   * Preconditioner: ONE symmetric V(2,2) multigrid cycle evaluated in FP32 -- it only has to be a fixed SPD
+//     approximation of M^-1, and it is 3/4 of the traffic of an iteration, so its vectors are 24-byte instead of
+//     48-byte records (the all-FP64 first version moved 176 GB of DRAM traffic per 700x700 pair).  CG hands it
+//     (float) r and reads z back as floats; r.z is fused into the V-cycle's last smoothing sweep.
+//   * Multigrid: 2x2 cell aggregation down to a single node; coarse operators stay 5-point graph Laplacians
+//     (diagonal = sum over the aggregate, edge weight = 1/2 x sum of the fine edges crossing two aggregates: the
+//     piecewise-constant Galerkin product with the 2-D rediscretisation factor, so edge weights spanning 1e0..1e5
+//     are coarsened algebraically); transfers = cell-centred linear interpolation P (9/16, 3/16, 3/16, 1/16) and
+//     R = P^T; damped Jacobi (omega = 0.8).  Levels with <= 1024 nodes run in ONE thread block.
+//   * Iteration counts are data dependent; the host reads the scalars back every few iterations.
 #include "device_utils.cuh"
-#include <vector>
 #include <cstdlib>
+#include <vector>
 
 namespace {
 
 constexpr int TPB = 256;
 constexpr int MAX_LEVELS = 14;
-// smoothing weight and over-correction of the coarse-grid correction (tunable through NCT_MG_OMEGA / NCT_MG_ALPHA for
-// experiments; the defaults are the measured optimum on the 700x700 workload, profiles/r1_wls_tuning.md)
-__constant__ double c_omega = 0.8;
-__constant__ double c_alpha = 1.0;
-__constant__ double c_edge_scale = 0.5;  // coarse edge weight = scale x (sum of the fine edges crossing two aggregates)
+// tunable through NCT_MG_OMEGA / NCT_MG_EDGE_SCALE for experiments; the defaults are the measured optimum on the
+// 700x700 workload (profiles/r1_wls_tuning.md)
+__constant__ float c_omega = 0.8f;
+__constant__ float c_edge_scale = 0.5f;
 #define OMEGA c_omega
-#define ALPHA c_alpha
+
+typedef float T;  // precision of the preconditioner
 
 struct MgLevel {
     int H, W, n;
-    const double *rsum;  // diagonal (screening) part
-    const double *wx;    // edge (p, p+1)
-    const double *wy;    // edge (p, p+W)
-    double *invd;        // 1 / (rsum + sum of incident edge weights)
-    double *x, *b, *t;   // [n][6] vectors: correction, right-hand side, scratch
+    const T *rsum;  // diagonal (screening) part
+    const T *wx;    // edge (p, p+1)
+    const T *wy;    // edge (p, p+W)
+    T *invd;        // 1 / (rsum + sum of incident edge weights)
+    T *x, *b, *t;   // [n][6] vectors: correction, right-hand side, scratch
 };
 
 struct MgHierarchy {
@@ -45,6 +48,25 @@ struct MgHierarchy {
     int bottom;  // first level handled by the single-block kernel
 };
 
+// the FP64 operator of the outer CG
+struct FineOp {
+    int H, W, n;
+    const double *rough, *wx, *wy;
+};
+
+__device__ __forceinline__ void ld6(const float *__restrict__ v, int i, float (&o)[6])
+{
+    const float2 *q = reinterpret_cast<const float2 *>(v + (size_t)i * 6);
+    const float2 t0 = q[0], t1 = q[1], t2 = q[2];
+    o[0] = t0.x; o[1] = t0.y; o[2] = t1.x; o[3] = t1.y; o[4] = t2.x; o[5] = t2.y;
+}
+__device__ __forceinline__ void st6(float *__restrict__ v, int i, const float (&o)[6])
+{
+    float2 *q = reinterpret_cast<float2 *>(v + (size_t)i * 6);
+    q[0] = make_float2(o[0], o[1]);
+    q[1] = make_float2(o[2], o[3]);
+    q[2] = make_float2(o[4], o[5]);
+}
 __device__ __forceinline__ void ld6(const double *__restrict__ v, int i, double (&o)[6])
 {
     const double2 *q = reinterpret_cast<const double2 *>(v + (size_t)i * 6);
@@ -59,15 +81,15 @@ __device__ __forceinline__ void st6(double *__restrict__ v, int i, const double 
     q[2] = make_double2(o[4], o[5]);
 }
 
-// sum_e w_e * X_j over the 4 neighbours, X given by a functor; also returns nothing else (diag comes from invd)
+// sum_e w_e * X_j over the 4 neighbours, X given by a functor
 template <class GetX>
-__device__ __forceinline__ void nbr_sum(const MgLevel &L, int i, GetX getx, double (&s)[6])
+__device__ __forceinline__ void nbr_sum(const MgLevel &L, int i, GetX getx, T (&s)[6])
 {
     const int x = i % L.W, y = i / L.W;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) s[k] = 0.0;
-    auto add = [&](int j, double w) {
-        double xj[6];
+    for (int k = 0; k < 6; ++k) s[k] = 0;
+    auto add = [&](int j, T w) {
+        T xj[6];
         getx(j, xj);
 #pragma unroll
         for (int k = 0; k < 6; ++k) s[k] += w * xj[k];
@@ -78,68 +100,83 @@ __device__ __forceinline__ void nbr_sum(const MgLevel &L, int i, GetX getx, doub
     if (y > 0) add(i - L.W, L.wy[i - L.W]);
 }
 
+// FP64 version on the fine operator; also returns the diagonal
+template <class GetX>
+__device__ __forceinline__ double nbr_sum64(const FineOp &F, int i, GetX getx, double (&s)[6])
+{
+    const int x = i % F.W, y = i / F.W;
+    double diag = F.rough[i];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s[k] = 0.0;
+    auto add = [&](int j, double w) {
+        double xj[6];
+        getx(j, xj);
+        diag += w;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s[k] += w * xj[k];
+    };
+    if (x + 1 < F.W) add(i + 1, F.wx[i]);
+    if (x > 0) add(i - 1, F.wx[i - 1]);
+    if (y + 1 < F.H) add(i + F.W, F.wy[i]);
+    if (y > 0) add(i - F.W, F.wy[i - F.W]);
+    return diag;
+}
+
 // ---- per-node operations (shared by the grid kernels and the single-block bottom kernel)
 // two damped-Jacobi sweeps from a zero initial guess: x = S2(b)
 __device__ __forceinline__ void op_presmooth2(const MgLevel &L, int i)
 {
-    double bi[6], s[6], o[6];
+    T bi[6], s[6], o[6];
     ld6(L.b, i, bi);
-    nbr_sum(L, i, [&](int j, double (&xj)[6]) {
+    nbr_sum(L, i, [&](int j, T (&xj)[6]) {
         ld6(L.b, j, xj);
-        const double f = OMEGA * L.invd[j];
+        const T f = OMEGA * L.invd[j];
 #pragma unroll
         for (int k = 0; k < 6; ++k) xj[k] *= f;
     }, s);
-    const double f = OMEGA * L.invd[i];
+    const T f = OMEGA * L.invd[i];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) o[k] = f * bi[k] + f * ((1.0 - OMEGA) * bi[k] + s[k]);
+    for (int k = 0; k < 6; ++k) o[k] = f * bi[k] + f * ((T(1) - OMEGA) * bi[k] + s[k]);
     st6(L.x, i, o);
 }
 
-// residual of node i: b - M x
-__device__ __forceinline__ void op_residual(const MgLevel &L, int i, double (&r)[6])
+// t = b - M x
+__device__ __forceinline__ void op_residual_to_t(const MgLevel &L, int i)
 {
-    double bi[6], xi[6], s[6];
+    T bi[6], xi[6], s[6], r[6];
     ld6(L.b, i, bi);
     ld6(L.x, i, xi);
-    nbr_sum(L, i, [&](int j, double (&xj)[6]) { ld6(L.x, j, xj); }, s);
-    const double d = 1.0 / L.invd[i];
+    nbr_sum(L, i, [&](int j, T (&xj)[6]) { ld6(L.x, j, xj); }, s);
+    const T d = T(1) / L.invd[i];
 #pragma unroll
     for (int k = 0; k < 6; ++k) r[k] = bi[k] - d * xi[k] + s[k];
+    st6(L.t, i, r);
 }
 
 // interpolation weight of fine index x towards coarse index J (cell-centred linear interpolation; at the border the
 // missing neighbour's weight folds into the parent, so that restriction = prolongation^T exactly)
-__device__ __forceinline__ double pw(int x, int J, int nc)
+__device__ __forceinline__ T pw(int x, int J, int nc)
 {
     const int Jp = x >> 1;
     int Jn = Jp + ((x & 1) ? 1 : -1);
     Jn = min(max(Jn, 0), nc - 1);
-    return (Jp == J ? 0.75 : 0.0) + (Jn == J ? 0.25 : 0.0);
-}
-
-// t = b - M x (residual), one node
-__device__ __forceinline__ void op_residual_to_t(const MgLevel &L, int i)
-{
-    double r[6];
-    op_residual(L, i, r);
-    st6(L.t, i, r);
+    return (Jp == J ? T(0.75) : T(0)) + (Jn == J ? T(0.25) : T(0));
 }
 
 // coarse right-hand side = P^T r: gather of the 4 x 4 fine residuals around the aggregate with weights pw(y) * pw(x)
 __device__ __forceinline__ void op_restrict(const MgLevel &F, const MgLevel &Cc, int c)
 {
     const int J = c % Cc.W, I = c / Cc.W;
-    double acc[6] = {0, 0, 0, 0, 0, 0};
+    T acc[6] = {0, 0, 0, 0, 0, 0};
     for (int y = 2 * I - 1; y <= 2 * I + 2; ++y) {
         if (y < 0 || y >= F.H) continue;
-        const double wy = pw(y, I, Cc.H);
-        if (wy == 0.0) continue;
+        const T wy = pw(y, I, Cc.H);
+        if (wy == T(0)) continue;
         for (int x = 2 * J - 1; x <= 2 * J + 2; ++x) {
             if (x < 0 || x >= F.W) continue;
-            const double w = wy * pw(x, J, Cc.W);
-            if (w == 0.0) continue;
-            double r[6];
+            const T w = wy * pw(x, J, Cc.W);
+            if (w == T(0)) continue;
+            T r[6];
             ld6(F.t, y * F.W + x, r);
 #pragma unroll
             for (int k = 0; k < 6; ++k) acc[k] += w * r[k];
@@ -149,190 +186,54 @@ __device__ __forceinline__ void op_restrict(const MgLevel &F, const MgLevel &Cc,
 }
 
 // (P xc) at fine node j
-__device__ __forceinline__ void prolong_at(const MgLevel &F, const MgLevel &Cc, int j, double (&o)[6])
+__device__ __forceinline__ void prolong_at(const MgLevel &F, const MgLevel &Cc, int j, T (&o)[6])
 {
     const int x = j % F.W, y = j / F.W;
     const int Jp = x >> 1, Ip = y >> 1;
     const int Jn = min(max(Jp + ((x & 1) ? 1 : -1), 0), Cc.W - 1), In = min(max(Ip + ((y & 1) ? 1 : -1), 0), Cc.H - 1);
-    double c00[6], c01[6], c10[6], c11[6];
+    T c00[6], c01[6], c10[6], c11[6];
     ld6(Cc.x, Ip * Cc.W + Jp, c00);
     ld6(Cc.x, Ip * Cc.W + Jn, c01);
     ld6(Cc.x, In * Cc.W + Jp, c10);
     ld6(Cc.x, In * Cc.W + Jn, c11);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) o[k] = 0.5625 * c00[k] + 0.1875 * c01[k] + 0.1875 * c10[k] + 0.0625 * c11[k];
+    for (int k = 0; k < 6; ++k) o[k] = T(0.5625) * c00[k] + T(0.1875) * c01[k] + T(0.1875) * c10[k] + T(0.0625) * c11[k];
 }
 
-// y = x + ALPHA * P xc ; out = y + omega D^-1 (b - M y)   (prolongation fused with the first post-smoothing sweep)
+// y = x + P xc ; t = y + omega D^-1 (b - M y)   (prolongation fused with the first post-smoothing sweep)
 __device__ __forceinline__ void op_prolong_smooth(const MgLevel &F, const MgLevel &Cc, int i)
 {
-    auto gety = [&](int j, double (&yj)[6]) {
-        double pc[6];
+    auto gety = [&](int j, T (&yj)[6]) {
+        T pc[6];
         ld6(F.x, j, yj);
         prolong_at(F, Cc, j, pc);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) yj[k] += ALPHA * pc[k];
+        for (int k = 0; k < 6; ++k) yj[k] += pc[k];
     };
-    double yi[6], bi[6], s[6], o[6];
+    T yi[6], bi[6], s[6], o[6];
     gety(i, yi);
     ld6(F.b, i, bi);
     nbr_sum(F, i, gety, s);
-    const double invd = F.invd[i], d = 1.0 / invd;
+    const T invd = F.invd[i], d = T(1) / invd;
 #pragma unroll
     for (int k = 0; k < 6; ++k) o[k] = yi[k] + OMEGA * invd * (bi[k] - d * yi[k] + s[k]);
     st6(F.t, i, o);
 }
 
-// one damped-Jacobi sweep t -> x
-__device__ __forceinline__ void op_smooth_t_to_x(const MgLevel &L, int i, double (&o)[6])
+// one damped-Jacobi sweep t -> x; leaves b_i and the new x_i in registers for the fused r.z
+__device__ __forceinline__ void op_smooth_t_to_x(const MgLevel &L, int i, T (&bi)[6], T (&o)[6])
 {
-    double ti[6], bi[6], s[6];
+    T ti[6], s[6];
     ld6(L.t, i, ti);
     ld6(L.b, i, bi);
-    nbr_sum(L, i, [&](int j, double (&xj)[6]) { ld6(L.t, j, xj); }, s);
-    const double invd = L.invd[i], d = 1.0 / invd;
+    nbr_sum(L, i, [&](int j, T (&xj)[6]) { ld6(L.t, j, xj); }, s);
+    const T invd = L.invd[i], d = T(1) / invd;
 #pragma unroll
     for (int k = 0; k < 6; ++k) o[k] = ti[k] + OMEGA * invd * (bi[k] - d * ti[k] + s[k]);
     st6(L.x, i, o);
 }
 
-// ---- grid kernels for the large levels
-__global__ void __launch_bounds__(TPB) mg_presmooth2_kernel(MgLevel L)
-{
-    const int i = blockIdx.x * TPB + threadIdx.x;
-    if (i < L.n) op_presmooth2(L, i);
-}
-__global__ void __launch_bounds__(TPB) mg_residual_kernel(MgLevel L)
-{
-    const int i = blockIdx.x * TPB + threadIdx.x;
-    if (i < L.n) op_residual_to_t(L, i);
-}
-__global__ void __launch_bounds__(TPB) mg_restrict_kernel(MgLevel F, MgLevel Cc)
-{
-    const int c = blockIdx.x * TPB + threadIdx.x;
-    if (c < Cc.n) op_restrict(F, Cc, c);
-}
-__global__ void __launch_bounds__(TPB) mg_prolong_smooth_kernel(MgLevel F, MgLevel Cc)
-{
-    const int i = blockIdx.x * TPB + threadIdx.x;
-    if (i < F.n) op_prolong_smooth(F, Cc, i);
-}
-__global__ void __launch_bounds__(TPB) mg_smooth_kernel(MgLevel L)
-{
-    const int i = blockIdx.x * TPB + threadIdx.x;
-    double o[6];
-    if (i < L.n) op_smooth_t_to_x(L, i, o);
-}
-
-// the whole bottom of the V-cycle (levels h.bottom .. nlevels-1, each <= 1024 nodes) in one block
-__global__ void __launch_bounds__(512) mg_bottom_kernel(MgHierarchy h)
-{
-    const int last = h.nlevels - 1;
-    for (int k = h.bottom; k < last; ++k) {
-        const MgLevel &L = h.lv[k];
-        for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_presmooth2(L, i);
-        __syncthreads();
-        for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_residual_to_t(L, i);
-        __syncthreads();
-        const MgLevel &Cc = h.lv[k + 1];
-        for (int c = threadIdx.x; c < Cc.n; c += blockDim.x) op_restrict(L, Cc, c);
-        __syncthreads();
-    }
-    {   // coarsest level: a single node (or a handful): exact for n == 1, Jacobi sweeps otherwise
-        const MgLevel &L = h.lv[last];
-        if (L.n == 1) {
-            if (threadIdx.x == 0) {
-                double b[6], o[6];
-                ld6(L.b, 0, b);
-                const double invd = L.invd[0];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) o[k] = b[k] * invd;
-                st6(L.x, 0, o);
-            }
-        } else {
-            for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_presmooth2(L, i);
-        }
-        __syncthreads();
-    }
-    for (int k = last - 1; k >= h.bottom; --k) {
-        const MgLevel &L = h.lv[k];
-        const MgLevel &Cc = h.lv[k + 1];
-        for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_prolong_smooth(L, Cc, i);
-        __syncthreads();
-        for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
-            double o[6];
-            op_smooth_t_to_x(L, i, o);
-        }
-        __syncthreads();
-    }
-}
-
-// ---- hierarchy set-up
-__global__ void mg_coarsen_kernel(MgLevel F, int Hc, int Wc, double *__restrict__ rsum, double *__restrict__ wx, double *__restrict__ wy)
-{
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= Hc * Wc) return;
-    const int J = c % Wc, I = c / Wc;
-    double rs = 0.0, vx = 0.0, vy = 0.0;
-    for (int dy = 0; dy < 2; ++dy)
-        for (int dx = 0; dx < 2; ++dx) {
-            const int y = 2 * I + dy, x = 2 * J + dx;
-            if (y < F.H && x < F.W) rs += F.rsum[y * F.W + x];
-        }
-    if (2 * J + 2 < F.W)
-        for (int dy = 0; dy < 2; ++dy) {
-            const int y = 2 * I + dy;
-            if (y < F.H) vx += F.wx[y * F.W + 2 * J + 1];
-        }
-    if (2 * I + 2 < F.H)
-        for (int dx = 0; dx < 2; ++dx) {
-            const int x = 2 * J + dx;
-            if (x < F.W) vy += F.wy[(2 * I + 1) * F.W + x];
-        }
-    rsum[c] = rs;
-    wx[c] = c_edge_scale * vx;
-    wy[c] = c_edge_scale * vy;
-}
-
-__global__ void mg_diag_kernel(MgLevel L)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L.n) return;
-    const int x = i % L.W, y = i / L.W;
-    double d = L.rsum[i];
-    if (x + 1 < L.W) d += L.wx[i];
-    if (x > 0) d += L.wx[i - 1];
-    if (y + 1 < L.H) d += L.wy[i];
-    if (y > 0) d += L.wy[i - L.W];
-    L.invd[i] = 1.0 / d;
-}
-
-__global__ void mg_wls_weights_kernel(const uint8_t *__restrict__ lab, int H, int W, double lam, double alpha,
-                                      double *__restrict__ wx, double *__restrict__ wy)
-{
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= H * W) return;
-    const int x = p % W, y = p / W;
-    const double L = __dmul_rn((double)lab[(size_t)p * 3], 1.0 / 255.0);
-    double vx = 0.0, vy = 0.0;
-    if (x + 1 < W) {
-        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(pow(fabs(__dsub_rn(__dmul_rn((double)lab[(size_t)(p + 1) * 3], 1.0 / 255.0), L)), alpha), 1e-4)));
-        vx = __dmul_rn(g, g);
-    }
-    if (y + 1 < H) {
-        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(pow(fabs(__dsub_rn(__dmul_rn((double)lab[(size_t)(p + W) * 3], 1.0 / 255.0), L)), alpha), 1e-4)));
-        vy = __dmul_rn(g, g);
-    }
-    wx[p] = vx;
-    wy[p] = vy;
-}
-
-// ---- outer PCG (6 right-hand sides)
-struct PcgScalars {
-    double rz[6], rz_old[6], alpha[6], beta[6], rr[6], bb[6];
-    int iters;
-};
-
+// ---- deterministic reductions (block tree + "last block done")
 template <int NV>
 __device__ __forceinline__ void block_reduce(double (&v)[NV], double *smem)
 {
@@ -387,6 +288,168 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials, u
     return false;
 }
 
+struct PcgScalars {
+    double rz[6], rz_old[6], alpha[6], beta[6], rr[6], bb[6];
+    int iters;
+};
+
+// ---- grid kernels for the large levels
+__global__ void __launch_bounds__(TPB) mg_presmooth2_kernel(MgLevel L)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    if (i < L.n) op_presmooth2(L, i);
+}
+__global__ void __launch_bounds__(TPB) mg_residual_kernel(MgLevel L)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    if (i < L.n) op_residual_to_t(L, i);
+}
+__global__ void __launch_bounds__(TPB) mg_restrict_kernel(MgLevel F, MgLevel Cc)
+{
+    const int c = blockIdx.x * TPB + threadIdx.x;
+    if (c < Cc.n) op_restrict(F, Cc, c);
+}
+__global__ void __launch_bounds__(TPB) mg_prolong_smooth_kernel(MgLevel F, MgLevel Cc)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    if (i < F.n) op_prolong_smooth(F, Cc, i);
+}
+__global__ void __launch_bounds__(TPB) mg_smooth_kernel(MgLevel L)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    T b[6], o[6];
+    if (i < L.n) op_smooth_t_to_x(L, i, b, o);
+}
+// last kernel of the V-cycle at level 0: z = smoothed x, fused with rz = r.z and beta = rz / rz_old
+// (r here is the FP32 copy the preconditioner was applied to, so rz = r32^T B r32 exactly)
+__global__ void __launch_bounds__(TPB) mg_smooth_rz_kernel(MgLevel L, PcgScalars *sc, double *partials, unsigned *counter)
+{
+    __shared__ double smem[6 * TPB / 32];
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    double dots[6] = {0, 0, 0, 0, 0, 0};
+    if (i < L.n) {
+        T z[6], r[6];
+        op_smooth_t_to_x(L, i, r, z);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dots[k] = (double)r[k] * (double)z[k];
+    }
+    if (grid_reduce<6>(dots, partials, counter, smem)) {
+        for (int k = 0; k < 6; ++k) {
+            sc->rz_old[k] = sc->rz[k];
+            sc->rz[k] = dots[k];
+            sc->beta[k] = sc->rz_old[k] > 0.0 ? dots[k] / sc->rz_old[k] : 0.0;
+        }
+    }
+}
+
+// the whole bottom of the V-cycle (levels h.bottom .. nlevels-1, each <= 1024 nodes) in one block
+__global__ void __launch_bounds__(512) mg_bottom_kernel(MgHierarchy h)
+{
+    const int last = h.nlevels - 1;
+    for (int k = h.bottom; k < last; ++k) {
+        const MgLevel &L = h.lv[k];
+        for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_presmooth2(L, i);
+        __syncthreads();
+        for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_residual_to_t(L, i);
+        __syncthreads();
+        const MgLevel &Cc = h.lv[k + 1];
+        for (int c = threadIdx.x; c < Cc.n; c += blockDim.x) op_restrict(L, Cc, c);
+        __syncthreads();
+    }
+    {   // coarsest level: a single node (exact) or a handful (Jacobi sweeps)
+        const MgLevel &L = h.lv[last];
+        if (L.n == 1) {
+            if (threadIdx.x == 0) {
+                T b[6], o[6];
+                ld6(L.b, 0, b);
+                const T invd = L.invd[0];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) o[k] = b[k] * invd;
+                st6(L.x, 0, o);
+            }
+        } else {
+            for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_presmooth2(L, i);
+        }
+        __syncthreads();
+    }
+    for (int k = last - 1; k >= h.bottom; --k) {
+        const MgLevel &L = h.lv[k];
+        const MgLevel &Cc = h.lv[k + 1];
+        for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_prolong_smooth(L, Cc, i);
+        __syncthreads();
+        for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
+            T b[6], o[6];
+            op_smooth_t_to_x(L, i, b, o);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- hierarchy set-up
+__global__ void mg_coarsen_kernel(MgLevel F, int Hc, int Wc, T *__restrict__ rsum, T *__restrict__ wx, T *__restrict__ wy)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Hc * Wc) return;
+    const int J = c % Wc, I = c / Wc;
+    T rs = 0, vx = 0, vy = 0;
+    for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+            const int y = 2 * I + dy, x = 2 * J + dx;
+            if (y < F.H && x < F.W) rs += F.rsum[y * F.W + x];
+        }
+    if (2 * J + 2 < F.W)
+        for (int dy = 0; dy < 2; ++dy) {
+            const int y = 2 * I + dy;
+            if (y < F.H) vx += F.wx[y * F.W + 2 * J + 1];
+        }
+    if (2 * I + 2 < F.H)
+        for (int dx = 0; dx < 2; ++dx) {
+            const int x = 2 * J + dx;
+            if (x < F.W) vy += F.wy[(2 * I + 1) * F.W + x];
+        }
+    rsum[c] = rs;
+    wx[c] = c_edge_scale * vx;
+    wy[c] = c_edge_scale * vy;
+}
+
+__global__ void mg_diag_kernel(MgLevel L)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.n) return;
+    const int x = i % L.W, y = i / L.W;
+    T d = L.rsum[i];
+    if (x + 1 < L.W) d += L.wx[i];
+    if (x > 0) d += L.wx[i - 1];
+    if (y + 1 < L.H) d += L.wy[i];
+    if (y > 0) d += L.wy[i - L.W];
+    L.invd[i] = T(1) / d;
+}
+
+// fine-level edge weights in FP64 (the operator CG solves with) plus FP32 copies for the preconditioner
+__global__ void wls_weights_kernel(const uint8_t *__restrict__ lab, const double *__restrict__ rough, int H, int W, double lam,
+                                   double alpha, double *__restrict__ wx, double *__restrict__ wy, T *__restrict__ fr, T *__restrict__ fwx,
+                                   T *__restrict__ fwy)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= H * W) return;
+    const int x = p % W, y = p / W;
+    const double L = __dmul_rn((double)lab[(size_t)p * 3], 1.0 / 255.0);
+    double vx = 0.0, vy = 0.0;
+    if (x + 1 < W) {
+        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(pow(fabs(__dsub_rn(__dmul_rn((double)lab[(size_t)(p + 1) * 3], 1.0 / 255.0), L)), alpha), 1e-4)));
+        vx = __dmul_rn(g, g);
+    }
+    if (y + 1 < H) {
+        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(pow(fabs(__dsub_rn(__dmul_rn((double)lab[(size_t)(p + W) * 3], 1.0 / 255.0), L)), alpha), 1e-4)));
+        vy = __dmul_rn(g, g);
+    }
+    wx[p] = vx;
+    wy[p] = vy;
+    fr[p] = (T)rough[p];
+    fwx[p] = (T)vx;
+    fwy[p] = (T)vy;
+}
+
 __global__ void pack6_kernel(const double *__restrict__ a, const double *__restrict__ b, int n, double *__restrict__ x)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -404,28 +467,32 @@ __global__ void unpack6_kernel(const double *__restrict__ x, int n, double *__re
     b[(size_t)i * 3] = o[3]; b[(size_t)i * 3 + 1] = o[4]; b[(size_t)i * 3 + 2] = o[5];
 }
 
-// r = W x0 - M x0 (written to level-0 b); rr, bb
-__global__ void __launch_bounds__(TPB) pcg_init_kernel(MgLevel L, const double *__restrict__ x, PcgScalars *sc, double *partials,
-                                                       unsigned *counter)
+// ---- CG (FP64, 6 right-hand sides)
+// r = W x0 - M x0 ; r32 = (float) r -> level-0 right-hand side of the preconditioner ; rr, bb
+__global__ void __launch_bounds__(TPB) pcg_init_kernel(FineOp F, const double *__restrict__ x, double *__restrict__ r, T *__restrict__ r32,
+                                                       PcgScalars *sc, double *partials, unsigned *counter)
 {
     __shared__ double smem[12 * TPB / 32];
     const int i = blockIdx.x * TPB + threadIdx.x;
     double dots[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) dots[k] = 0.0;
-    if (i < L.n) {
+    if (i < F.n) {
         double xi[6], s[6], ri[6];
+        T rf[6];
         ld6(x, i, xi);
-        nbr_sum(L, i, [&](int j, double (&xj)[6]) { ld6(x, j, xj); }, s);
-        const double d = 1.0 / L.invd[i], rg = L.rsum[i];
+        const double d = nbr_sum64(F, i, [&](int j, double (&xj)[6]) { ld6(x, j, xj); }, s);
+        const double rg = F.rough[i];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             const double rhs = rg * xi[k];
             ri[k] = rhs - d * xi[k] + s[k];
+            rf[k] = (T)ri[k];
             dots[k] = ri[k] * ri[k];
             dots[6 + k] = rhs * rhs;
         }
-        st6(L.b, i, ri);
+        st6(r, i, ri);
+        st6(r32, i, rf);
     }
     if (grid_reduce<12>(dots, partials, counter, smem)) {
         for (int k = 0; k < 6; ++k) {
@@ -440,31 +507,10 @@ __global__ void __launch_bounds__(TPB) pcg_init_kernel(MgLevel L, const double *
     }
 }
 
-// rz = r.z ; beta = rz / rz_old   (z = level-0 x, r = level-0 b)
-__global__ void __launch_bounds__(TPB) pcg_rz_kernel(MgLevel L, PcgScalars *sc, double *partials, unsigned *counter)
-{
-    __shared__ double smem[6 * TPB / 32];
-    const int i = blockIdx.x * TPB + threadIdx.x;
-    double dots[6] = {0, 0, 0, 0, 0, 0};
-    if (i < L.n) {
-        double ri[6], zi[6];
-        ld6(L.b, i, ri);
-        ld6(L.x, i, zi);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) dots[k] = ri[k] * zi[k];
-    }
-    if (grid_reduce<6>(dots, partials, counter, smem)) {
-        for (int k = 0; k < 6; ++k) {
-            sc->rz_old[k] = sc->rz[k];
-            sc->rz[k] = dots[k];
-            sc->beta[k] = sc->rz_old[k] > 0.0 ? dots[k] / sc->rz_old[k] : 0.0;
-        }
-    }
-}
-
-// p = z + beta p_old ; Ap = M p ; alpha = rz / p.Ap
-__global__ void __launch_bounds__(TPB) pcg_spmv_kernel(MgLevel L, const double *__restrict__ pold, double *__restrict__ pnew,
-                                                       double *__restrict__ Ap, PcgScalars *sc, double *partials, unsigned *counter)
+// p = z + beta p_old ; Ap = M p ; alpha = rz / p.Ap      (z = level-0 x of the hierarchy, FP32)
+__global__ void __launch_bounds__(TPB) pcg_spmv_kernel(FineOp F, const T *__restrict__ z, const double *__restrict__ pold,
+                                                       double *__restrict__ pnew, double *__restrict__ Ap, PcgScalars *sc,
+                                                       double *partials, unsigned *counter)
 {
     __shared__ double smem[6 * TPB / 32];
     const int i = blockIdx.x * TPB + threadIdx.x;
@@ -473,18 +519,18 @@ __global__ void __launch_bounds__(TPB) pcg_spmv_kernel(MgLevel L, const double *
     for (int k = 0; k < 6; ++k) beta[k] = sc->beta[k];
     double dots[6] = {0, 0, 0, 0, 0, 0};
     auto getp = [&](int j, double (&o)[6]) {
-        double zj[6], pj[6];
-        ld6(L.x, j, zj);
+        T zj[6];
+        double pj[6];
+        ld6(z, j, zj);
         ld6(pold, j, pj);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) o[k] = zj[k] + beta[k] * pj[k];
+        for (int k = 0; k < 6; ++k) o[k] = (double)zj[k] + beta[k] * pj[k];
     };
-    if (i < L.n) {
+    if (i < F.n) {
         double pi[6], s[6], api[6];
         getp(i, pi);
         st6(pnew, i, pi);
-        nbr_sum(L, i, getp, s);
-        const double d = 1.0 / L.invd[i];
+        const double d = nbr_sum64(F, i, getp, s);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             api[k] = d * pi[k] - s[k];
@@ -497,10 +543,10 @@ __global__ void __launch_bounds__(TPB) pcg_spmv_kernel(MgLevel L, const double *
     }
 }
 
-// x += alpha p ; r -= alpha Ap ; rr
-__global__ void __launch_bounds__(TPB) pcg_update_kernel(MgLevel L, double *__restrict__ x, const double *__restrict__ p,
-                                                         const double *__restrict__ Ap, PcgScalars *sc, double *partials,
-                                                         unsigned *counter)
+// x += alpha p ; r -= alpha Ap ; r32 = (float) r ; rr
+__global__ void __launch_bounds__(TPB) pcg_update_kernel(int n, double *__restrict__ x, double *__restrict__ r, T *__restrict__ r32,
+                                                         const double *__restrict__ p, const double *__restrict__ Ap, PcgScalars *sc,
+                                                         double *partials, unsigned *counter)
 {
     __shared__ double smem[6 * TPB / 32];
     const int i = blockIdx.x * TPB + threadIdx.x;
@@ -508,20 +554,23 @@ __global__ void __launch_bounds__(TPB) pcg_update_kernel(MgLevel L, double *__re
 #pragma unroll
     for (int k = 0; k < 6; ++k) alpha[k] = sc->alpha[k];
     double dots[6] = {0, 0, 0, 0, 0, 0};
-    if (i < L.n) {
+    if (i < n) {
         double xi[6], ri[6], pi[6], api[6];
+        T rf[6];
         ld6(x, i, xi);
-        ld6(L.b, i, ri);
+        ld6(r, i, ri);
         ld6(p, i, pi);
         ld6(Ap, i, api);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             xi[k] += alpha[k] * pi[k];
             ri[k] -= alpha[k] * api[k];
+            rf[k] = (T)ri[k];
             dots[k] = ri[k] * ri[k];
         }
         st6(x, i, xi);
-        st6(L.b, i, ri);
+        st6(r, i, ri);
+        st6(r32, i, rf);
     }
     if (grid_reduce<6>(dots, partials, counter, smem)) {
         for (int k = 0; k < 6; ++k) sc->rr[k] = dots[k];
@@ -529,9 +578,9 @@ __global__ void __launch_bounds__(TPB) pcg_update_kernel(MgLevel L, double *__re
     }
 }
 
-int vcycle(nct_ctx *ctx, const MgHierarchy &h)
+// z (level-0 x) = B r32 (level-0 b); rz and beta come out of its last kernel
+int vcycle(nct_ctx *ctx, const MgHierarchy &h, PcgScalars *sc, double *partials, unsigned *counter)
 {
-    // down
     for (int k = 0; k < h.bottom; ++k) {
         const MgLevel &L = h.lv[k];
         mg_presmooth2_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L);
@@ -549,7 +598,8 @@ int vcycle(nct_ctx *ctx, const MgHierarchy &h)
         const MgLevel &Cc = h.lv[k + 1];
         mg_prolong_smooth_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L, Cc);
         NCT_CHECK_LAUNCH(ctx);
-        mg_smooth_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L);
+        if (k == 0) mg_smooth_rz_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L, sc, partials, counter);
+        else mg_smooth_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L);
         NCT_CHECK_LAUNCH(ctx);
     }
     return NCT_OK;
@@ -571,17 +621,9 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
         static bool tuned = false;
         if (!tuned) {
             tuned = true;
-            const char *eo = getenv("NCT_MG_OMEGA"), *ea = getenv("NCT_MG_ALPHA");
-            if (eo) { double v = atof(eo); cudaMemcpyToSymbol(c_omega, &v, sizeof(v)); }
-            if (ea) { double v = atof(ea); cudaMemcpyToSymbol(c_alpha, &v, sizeof(v)); }
-        }
-        {
-            static bool tuned2 = false;
-            if (!tuned2) {
-                tuned2 = true;
-                const char *es = getenv("NCT_MG_EDGE_SCALE");
-                if (es) { double v = atof(es); cudaMemcpyToSymbol(c_edge_scale, &v, sizeof(v)); }
-            }
+            const char *eo = getenv("NCT_MG_OMEGA"), *es = getenv("NCT_MG_EDGE_SCALE");
+            if (eo) { float v = (float)atof(eo); cudaMemcpyToSymbol(c_omega, &v, sizeof(v)); }
+            if (es) { float v = (float)atof(es); cudaMemcpyToSymbol(c_edge_scale, &v, sizeof(v)); }
         }
     }
     // ---- level geometry
@@ -597,39 +639,33 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
         }
     }
     const int nl = (int)Hs.size();
-    NCT_REQUIRE(ctx, nl <= MAX_LEVELS, "image too large for the multigrid hierarchy");
-    size_t tot = 0, tot_c = 0;
-    for (int k = 0; k < nl; ++k) {
-        tot += (size_t)Hs[k] * Ws[k];
-        if (k > 0) tot_c += (size_t)Hs[k] * Ws[k];
-    }
-    double *coef = (double *)nct_scratch(ctx, "wls_coef", sizeof(double) * (3 * tot_c + 2 * (size_t)n0 + tot));  // rsum/wx/wy coarse, wx/wy fine, invd all
-    double *vec = (double *)nct_scratch(ctx, "wls_vec", sizeof(double) * 6 * (3 * tot + 4 * (size_t)n0));
+    NCT_REQUIRE(ctx, nl >= 2 && nl <= MAX_LEVELS, "image size outside the multigrid hierarchy's range");
+    size_t tot = 0;
+    for (int k = 0; k < nl; ++k) tot += (size_t)Hs[k] * Ws[k];
+    double *dcoef = (double *)nct_scratch(ctx, "wls_dcoef", sizeof(double) * 2 * (size_t)n0);    // FP64 wx, wy of level 0
+    T *coef = (T *)nct_scratch(ctx, "wls_fcoef", sizeof(T) * 4 * tot);                           // rsum, wx, wy, invd per level
+    T *vec = (T *)nct_scratch(ctx, "wls_fvec", sizeof(T) * 6 * 3 * tot);                         // x, b, t per level
+    double *dvec = (double *)nct_scratch(ctx, "wls_dvec", sizeof(double) * 6 * 5 * (size_t)n0);  // x, r, p0, p1, Ap
     const int blocks0 = nct_div_up(n0, TPB);
     double *partials = (double *)nct_scratch(ctx, "solver_partials", sizeof(double) * 18 * (size_t)(blocks0 + 1));
     char *misc = (char *)nct_scratch(ctx, "solver_misc", 1024);
-    if (!coef || !vec || !partials || !misc) return NCT_ERR_NOMEM;
+    if (!dcoef || !coef || !vec || !dvec || !partials || !misc) return NCT_ERR_NOMEM;
     PcgScalars *sc = (PcgScalars *)misc;
     unsigned *counter = (unsigned *)(misc + 512);
+    static_assert(sizeof(PcgScalars) <= 512, "scalar block too large");
 
     MgHierarchy h;
     h.nlevels = nl;
     h.bottom = nl - 1;
-    double *cp = coef, *vp = vec;
+    T *cp = coef, *vp = vec;
     for (int k = 0; k < nl; ++k) {
         MgLevel &L = h.lv[k];
         L.H = Hs[k];
         L.W = Ws[k];
         L.n = Hs[k] * Ws[k];
-        if (k == 0) {
-            L.rsum = rough_dev;
-            L.wx = cp; cp += L.n;
-            L.wy = cp; cp += L.n;
-        } else {
-            L.rsum = cp; cp += L.n;
-            L.wx = cp; cp += L.n;
-            L.wy = cp; cp += L.n;
-        }
+        L.rsum = cp; cp += L.n;
+        L.wx = cp; cp += L.n;
+        L.wy = cp; cp += L.n;
         L.invd = cp; cp += L.n;
         L.x = vp; vp += (size_t)L.n * 6;
         L.b = vp; vp += (size_t)L.n * 6;
@@ -637,20 +673,19 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
     }
     for (int k = 0; k < nl; ++k)
         if (h.lv[k].n <= 1024) { h.bottom = k; break; }
-    if (h.bottom == 0) h.bottom = nl > 1 ? 1 : 0;  // level 0 always uses the grid kernels (tiny images only)
-    double *x = vp; vp += (size_t)n0 * 6;
-    double *p0 = vp; vp += (size_t)n0 * 6;
-    double *p1 = vp; vp += (size_t)n0 * 6;
-    double *Ap = vp; vp += (size_t)n0 * 6;
+    if (h.bottom == 0) h.bottom = 1;  // level 0 always uses the grid kernels (tiny images only)
+    double *x = dvec, *r = dvec + (size_t)n0 * 6, *p0 = dvec + (size_t)n0 * 12, *p1 = dvec + (size_t)n0 * 18, *Ap = dvec + (size_t)n0 * 24;
+    double *wx64 = dcoef, *wy64 = dcoef + n0;
 
-    // ---- set-up: fine weights, Galerkin coarse operators, diagonals
+    // ---- set-up: fine weights, coarse operators, diagonals
     NCT_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned), ctx->stream));
-    mg_wls_weights_kernel<<<blocks0, TPB, 0, ctx->stream>>>(cnt_lab_full_dev, H, W, lam, alpha, (double *)h.lv[0].wx, (double *)h.lv[0].wy);
+    wls_weights_kernel<<<blocks0, TPB, 0, ctx->stream>>>(cnt_lab_full_dev, rough_dev, H, W, lam, alpha, wx64, wy64, (T *)h.lv[0].rsum,
+                                                         (T *)h.lv[0].wx, (T *)h.lv[0].wy);
     NCT_CHECK_LAUNCH(ctx);
     for (int k = 0; k < nl; ++k) {
         if (k > 0) {
-            mg_coarsen_kernel<<<nct_div_up(h.lv[k].n, TPB), TPB, 0, ctx->stream>>>(h.lv[k - 1], h.lv[k].H, h.lv[k].W, (double *)h.lv[k].rsum,
-                                                                                  (double *)h.lv[k].wx, (double *)h.lv[k].wy);
+            mg_coarsen_kernel<<<nct_div_up(h.lv[k].n, TPB), TPB, 0, ctx->stream>>>(h.lv[k - 1], h.lv[k].H, h.lv[k].W, (T *)h.lv[k].rsum,
+                                                                                  (T *)h.lv[k].wx, (T *)h.lv[k].wy);
             NCT_CHECK_LAUNCH(ctx);
         }
         mg_diag_kernel<<<nct_div_up(h.lv[k].n, TPB), TPB, 0, ctx->stream>>>(h.lv[k]);
@@ -660,7 +695,8 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
     NCT_CHECK_LAUNCH(ctx);
     NCT_CUDA(ctx, cudaMemsetAsync(p0, 0, sizeof(double) * 6 * (size_t)n0, ctx->stream));
     const MgLevel &L0 = h.lv[0];
-    pcg_init_kernel<<<blocks0, TPB, 0, ctx->stream>>>(L0, x, sc, partials, counter);
+    const FineOp F{H, W, n0, rough_dev, wx64, wy64};
+    pcg_init_kernel<<<blocks0, TPB, 0, ctx->stream>>>(F, x, r, L0.b, sc, partials, counter);
     NCT_CHECK_LAUNCH(ctx);
 
     double *pold = p0, *pnew = p1;
@@ -677,13 +713,11 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
         }
         if (worst <= rel_tol || hs.iters >= max_iters) break;
         for (int it = 0; it < check_every; ++it) {
-            int rc = vcycle(ctx, h);  // z (level-0 x) = B r (level-0 b)
+            int rc = vcycle(ctx, h, sc, partials, counter);
             if (rc) return rc;
-            pcg_rz_kernel<<<blocks0, TPB, 0, ctx->stream>>>(L0, sc, partials, counter);
+            pcg_spmv_kernel<<<blocks0, TPB, 0, ctx->stream>>>(F, L0.x, pold, pnew, Ap, sc, partials, counter);
             NCT_CHECK_LAUNCH(ctx);
-            pcg_spmv_kernel<<<blocks0, TPB, 0, ctx->stream>>>(L0, pold, pnew, Ap, sc, partials, counter);
-            NCT_CHECK_LAUNCH(ctx);
-            pcg_update_kernel<<<blocks0, TPB, 0, ctx->stream>>>(L0, x, pnew, Ap, sc, partials, counter);
+            pcg_update_kernel<<<blocks0, TPB, 0, ctx->stream>>>(n0, x, r, L0.b, pnew, Ap, sc, partials, counter);
             NCT_CHECK_LAUNCH(ctx);
             double *t = pold; pold = pnew; pnew = t;
         }
