@@ -191,7 +191,7 @@ def run_ours(args):
     # (deterministic, so the timed steps evaluate exactly the same candidates)
     evals_bytes = []
     c0 = ctxs[0]
-    for q in range(npairs):
+    for q in range(0 if os.environ.get("NCT_BENCH_PROFILE") else npairs):
         tot = 0
         c0.count_evals(True)
         for l in range(5):
@@ -210,6 +210,7 @@ def run_ours(args):
     c0.profile(True)
     ev = ([torch.cuda.Event(enable_timing=True) for _ in range(P)], [torch.cuda.Event(enable_timing=True) for _ in range(P)])
     e_end = torch.cuda.Event(enable_timing=True)
+    nvtx_id = torch.cuda.nvtx.range_start("timed")  # process-wide start/end range: `ncu --nvtx --nvtx-include "timed"` lists exactly the timed launches
     dev_steps(K, ev)
     main_stream = torch.cuda.current_stream(dev)
     for j in range(P):
@@ -218,12 +219,21 @@ def run_ours(args):
         dist.gather(out_dev, gather_list, dst=0)
     e_end.record(main_stream)
     torch.cuda.synchronize(dev)
+    torch.cuda.nvtx.range_end(nvtx_id)
     barrier()
     sampler.stop_flag = True
     dev_ms = max(ev[0][j].elapsed_time(e_end) for j in range(P))
     launches = sum(c.launch_count for c in ctxs)
     prof = c0.profile_report()
     c0.profile(False)
+
+    if os.environ.get("NCT_BENCH_PROFILE"):
+        # launch-list mode for `ncu` (profiles/): the warm-up and the timed region only, no auxiliary passes
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "ms_per_step": round(dev_ms / K, 2), "gpu_launches": int(launches)}), flush=True)
+        for c in ctxs:
+            c.close()
+        return
 
     # ---- single-stream pass (context 0 alone): kernel time of PatchMatch without co-running streams
     c0.profile(True)
@@ -337,7 +347,8 @@ def main():
     ap.add_argument("--vgg-engine", type=int, default=2, choices=[0, 1, 2],
                     help="convolution engine: 0 fp32 CUDA cores, 1 tcgen05 tf32, 2 tcgen05 3xTF32 (default)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if not os.environ.get("NCT_BENCH_PROFILE"):  # (launch-list mode under ncu may use a shorter warm-up)
+        args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
     else:

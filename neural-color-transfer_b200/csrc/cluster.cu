@@ -314,7 +314,8 @@ __global__ void __launch_bounds__(KNN_TPB) knn_cluster_kernel(const uint32_t *__
 }
 
 __global__ void knn_merge_kernel(const uint32_t *__restrict__ mask, const int *__restrict__ pos, const unsigned long long *__restrict__ pair_top,
-                                 int lw, int w, int n, int samples, int K, int *__restrict__ knn_id, double *__restrict__ knn_w)
+                                 int lw, int w, int n, int samples, int K, int *__restrict__ knn_id, double *__restrict__ knn_w,
+                                 const double *__restrict__ wtab)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -335,9 +336,8 @@ __global__ void knn_merge_kernel(const uint32_t *__restrict__ mask, const int *_
     for (int i = 0; i < 8; ++i) {
         const unsigned long long k = top.key[i];
         if (k != ~0ull) {
-            const double d = __ddiv_rn(__dsqrt_rn((double)(uint32_t)(k >> 32)), 255.0);
             knn_id[(size_t)p * 8 + i] = (int)(uint32_t)(k & 0xffffffffull);
-            knn_w[(size_t)p * 8 + i] = exp(__dsub_rn(1.0, __ddiv_rn(d, 3.0)));
+            knn_w[(size_t)p * 8 + i] = wtab[(uint32_t)(k >> 32)];  // exp(1 - sqrt(D2)/255/3), host-libm table
         } else {
             knn_id[(size_t)p * 8 + i] = -1;
             knn_w[(size_t)p * 8 + i] = 0.0;
@@ -405,6 +405,8 @@ int nct_find_knns_brute(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int
     NCT_REQUIRE(ctx, nlabels >= 1 && nlabels <= MAXK && samples >= 1, "bad cluster count / samples");
     NCT_REQUIRE(ctx, (long long)lw * samples >= w && (long long)lh * samples >= h, "label grid %dx%d x %d does not cover the %dx%d image", lw, lh, samples, w, h);
     const int n = h * w, K = nlabels;
+    const double *wtab = nct_knn_weight_table(ctx);
+    if (!wtab) return NCT_ERR_NOMEM;
     const size_t KN = (size_t)K * n;
     NCT_REQUIRE(ctx, KN < (1ull << 31), "image too large");
     uint32_t *mask = (uint32_t *)nct_scratch(ctx, "knn_mask", sizeof(uint32_t) * (size_t)lw * lh);
@@ -431,7 +433,7 @@ int nct_find_knns_brute(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int
     const int max_blocks = (int)(max_pairs / KNN_TPB) + K + 1;
     knn_cluster_kernel<<<max_blocks, KNN_TPB, 0, ctx->stream>>>(mem_lab, mem_id, off, blk_start, K, pair_top);
     NCT_CHECK_LAUNCH(ctx);
-    knn_merge_kernel<<<nct_div_up(n, 128), 128, 0, ctx->stream>>>(mask, pos, pair_top, lw, w, n, samples, K, knn_id_dev, knn_w_dev);
+    knn_merge_kernel<<<nct_div_up(n, 128), 128, 0, ctx->stream>>>(mask, pos, pair_top, lw, w, n, samples, K, knn_id_dev, knn_w_dev, wtab);
     NCT_CHECK_LAUNCH(ctx);
     return NCT_OK;
 }

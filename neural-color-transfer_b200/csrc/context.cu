@@ -2,6 +2,7 @@
 // Replaces the device setup of NCT/main.cu:562-570 (cudaSetDevice/cudaDeviceReset/
 // cudaMemGetInfo) and the per-level cudaMalloc/cudaFree churn of NCT/main.cu:238-326.
 #include "nct_internal.h"
+#include <cmath>
 
 int nct_fail(nct_ctx *ctx, int code, const char *fmt, ...)
 {
@@ -35,6 +36,49 @@ void *nct_scratch(nct_ctx *ctx, const char *name, size_t bytes)
     b.ptr = p;
     b.bytes = want;
     return p;
+}
+
+const double *nct_pow_table(nct_ctx *ctx, double alpha)
+{
+    double *dev = (double *)nct_scratch(ctx, "tab_pow", sizeof(double) * 65536);
+    if (!dev) return nullptr;
+    if (ctx->pow_alpha != alpha || ctx->pow_host.empty()) {
+        // queued kernels may still read the previous table / the host staging vector
+        cudaStreamSynchronize(ctx->stream);
+        ctx->pow_host.resize(65536);
+        for (int l0 = 0; l0 < 256; ++l0)
+            for (int l1 = 0; l1 < 256; ++l1) {
+                volatile double a = (double)l1 * (1.0 / 255.0), b = (double)l0 * (1.0 / 255.0);  // volatile: no contraction
+                volatile double d = a - b;
+                ctx->pow_host[l0 * 256 + l1] = pow(fabs(d), alpha);
+            }
+        if (cudaMemcpy(dev, ctx->pow_host.data(), sizeof(double) * 65536, cudaMemcpyHostToDevice) != cudaSuccess) {
+            nct_fail(ctx, NCT_ERR_CUDA, "upload of the pow table failed");
+            return nullptr;
+        }
+        ctx->pow_alpha = alpha;
+    }
+    return dev;
+}
+
+const double *nct_knn_weight_table(nct_ctx *ctx)
+{
+    const int n = 3 * 255 * 255 + 1;
+    double *dev = (double *)nct_scratch(ctx, "tab_knnw", sizeof(double) * n);
+    if (!dev) return nullptr;
+    if (ctx->knnw_host.empty()) {
+        ctx->knnw_host.resize(n);
+        for (int i = 0; i < n; ++i) {
+            volatile double d = sqrt((double)i) / 255.0;
+            volatile double q = d / 3.0;
+            ctx->knnw_host[i] = exp(1.0 - q);
+        }
+        if (cudaMemcpy(dev, ctx->knnw_host.data(), sizeof(double) * n, cudaMemcpyHostToDevice) != cudaSuccess) {
+            nct_fail(ctx, NCT_ERR_CUDA, "upload of the k-NN weight table failed");
+            return nullptr;
+        }
+    }
+    return dev;
 }
 
 NctStageTimer::NctStageTimer(nct_ctx *c, int stage) : ctx(c)

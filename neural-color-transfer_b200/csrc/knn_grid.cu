@@ -115,7 +115,8 @@ __device__ __forceinline__ void scan_range(const uint32_t *__restrict__ s_lab, c
 __global__ void __launch_bounds__(128) knn_grid_kernel(const uint32_t *__restrict__ mask, const uint8_t *__restrict__ lab,
                                                        const int *__restrict__ start, const uint32_t *__restrict__ s_lab,
                                                        const int *__restrict__ s_id, int lw, int w, int n, int samples, int K,
-                                                       int *__restrict__ knn_id, double *__restrict__ knn_w)
+                                                       int *__restrict__ knn_id, double *__restrict__ knn_w,
+                                                       const double *__restrict__ wtab)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -174,9 +175,8 @@ __global__ void __launch_bounds__(128) knn_grid_kernel(const uint32_t *__restric
     for (int i = 0; i < 8; ++i) {
         const unsigned long long k = top.key[i];
         if (k != ~0ull) {
-            const double d = __ddiv_rn(__dsqrt_rn((double)(uint32_t)(k >> 32)), 255.0);
             knn_id[(size_t)p * 8 + i] = (int)(uint32_t)(k & 0xffffffffull);
-            knn_w[(size_t)p * 8 + i] = exp(__dsub_rn(1.0, __ddiv_rn(d, 3.0)));
+            knn_w[(size_t)p * 8 + i] = wtab[(uint32_t)(k >> 32)];  // exp(1 - sqrt(D2)/255/3), host-libm table
         } else {
             knn_id[(size_t)p * 8 + i] = -1;
             knn_w[(size_t)p * 8 + i] = 0.0;
@@ -196,6 +196,8 @@ int nct_find_knns(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int nlabe
     NCT_REQUIRE(ctx, nlabels >= 1 && nlabels <= MAXK && samples >= 1, "bad cluster count / samples");
     NCT_REQUIRE(ctx, (long long)lw * samples >= w && (long long)lh * samples >= h, "label grid %dx%d x %d does not cover the %dx%d image", lw, lh, samples, w, h);
     const int n = h * w, K = nlabels;
+    const double *wtab = nct_knn_weight_table(ctx);
+    if (!wtab) return NCT_ERR_NOMEM;
     const size_t T = (size_t)K * CELLS;
     const size_t max_pairs = (size_t)n * (K < 5 ? K : 5);
     uint32_t *mask = (uint32_t *)nct_scratch(ctx, "knn_mask", sizeof(uint32_t) * (size_t)lw * lh);
@@ -214,7 +216,7 @@ int nct_find_knns(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int nlabe
     NCT_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int) * (T + 1), ctx->stream));
     grid_fill_kernel<<<nct_div_up(n, 256), 256, 0, ctx->stream>>>(mask, lab_dev, lw, w, n, samples, K, start, count, s_lab, s_id);
     NCT_CHECK_LAUNCH(ctx);
-    knn_grid_kernel<<<nct_div_up(n, 128), 128, 0, ctx->stream>>>(mask, lab_dev, start, s_lab, s_id, lw, w, n, samples, K, knn_id_dev, knn_w_dev);
+    knn_grid_kernel<<<nct_div_up(n, 128), 128, 0, ctx->stream>>>(mask, lab_dev, start, s_lab, s_id, lw, w, n, samples, K, knn_id_dev, knn_w_dev, wtab);
     NCT_CHECK_LAUNCH(ctx);
     return NCT_OK;
 }

@@ -39,6 +39,12 @@ struct nct_ctx {
     double prof_ms[16] = {0};
     long long prof_calls[16] = {0};
 
+    // transcendental tables evaluated by the HOST C library (the same libm the oracle uses), so that the gradient and
+    // neighbour weights entering the un-converged CG are bit-identical to the oracle's (a 1-ulp
+    // difference there changes the final image by ~43 dB)
+    double pow_alpha = -1.0;
+    std::vector<double> pow_host, knnw_host;
+
     // opaque sub-module states (owned, freed in nct_destroy)
     struct VggState *vgg = nullptr;
     struct PipeState *pipe = nullptr;
@@ -47,6 +53,11 @@ struct nct_ctx {
 int nct_fail(nct_ctx *ctx, int code, const char *fmt, ...);
 // returns device pointer of at least `bytes` bytes, stable until a larger request under the same name
 void *nct_scratch(nct_ctx *ctx, const char *name, size_t bytes);
+
+// [256 * 256] pow(|l1 * (1/255) - l0 * (1/255)|, alpha) at index l0 * 256 + l1 (compute_gradientMat, CT/ColorTransfer.cpp:519-546)
+const double *nct_pow_table(nct_ctx *ctx, double alpha);
+// [3 * 255^2 + 1] exp(1 - sqrt(D2) / 255 / 3) indexed by the integer squared Lab distance (sortMergeComputeWeight, CT/ColorTransfer.cpp:60-110)
+const double *nct_knn_weight_table(nct_ctx *ctx);
 
 #define NCT_CUDA(ctx, call)                                                                          \
     do {                                                                                             \

@@ -100,7 +100,7 @@ struct NlSystem {
 };
 
 __global__ void nl_setup_kernel(const double *__restrict__ weight, const uint8_t *__restrict__ src, int h, int w, double lam,
-                                double alpha, double sqrt_dw, double *__restrict__ d2, double *__restrict__ wx2,
+                                const double *__restrict__ ptab, double sqrt_dw, double *__restrict__ d2, double *__restrict__ wx2,
                                 double *__restrict__ wy2)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,12 +111,12 @@ __global__ void nl_setup_kernel(const double *__restrict__ weight, const uint8_t
     const double L = __dmul_rn((double)src[(size_t)p * 3], 1.0 / 255.0);
     double vx = 0.0, vy = 0.0;
     if (x + 1 < w) {
-        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(pow(fabs(__dsub_rn(__dmul_rn((double)src[(size_t)(p + 1) * 3], 1.0 / 255.0), L)), alpha), 1e-4)));
+        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(ptab[(int)src[(size_t)p * 3] * 256 + (int)src[(size_t)(p + 1) * 3]], 1e-4)));
         const double gg = __dmul_rn(g, g);
         vx = __dadd_rn(gg, gg);
     }
     if (y + 1 < h) {
-        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(pow(fabs(__dsub_rn(__dmul_rn((double)src[(size_t)(p + w) * 3], 1.0 / 255.0), L)), alpha), 1e-4)));
+        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(ptab[(int)src[(size_t)p * 3] * 256 + (int)src[(size_t)(p + w) * 3]], 1e-4)));
         const double gg = __dmul_rn(g, g);
         vy = __dadd_rn(gg, gg);
     }
@@ -347,7 +347,7 @@ struct WlsScalars {
     int iters;
 };
 
-__global__ void wls_setup_kernel(const uint8_t *__restrict__ lab, int H, int W, double lam, double alpha,
+__global__ void wls_setup_kernel(const uint8_t *__restrict__ lab, int H, int W, double lam, const double *__restrict__ ptab,
                                  double *__restrict__ wx, double *__restrict__ wy)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -356,11 +356,11 @@ __global__ void wls_setup_kernel(const uint8_t *__restrict__ lab, int H, int W, 
     const double L = __dmul_rn((double)lab[(size_t)p * 3], 1.0 / 255.0);
     double vx = 0.0, vy = 0.0;
     if (x + 1 < W) {
-        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(pow(fabs(__dsub_rn(__dmul_rn((double)lab[(size_t)(p + 1) * 3], 1.0 / 255.0), L)), alpha), 1e-4)));
+        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(ptab[(int)lab[(size_t)p * 3] * 256 + (int)lab[(size_t)(p + 1) * 3]], 1e-4)));
         vx = __dmul_rn(g, g);
     }
     if (y + 1 < H) {
-        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(pow(fabs(__dsub_rn(__dmul_rn((double)lab[(size_t)(p + W) * 3], 1.0 / 255.0), L)), alpha), 1e-4)));
+        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(ptab[(int)lab[(size_t)p * 3] * 256 + (int)lab[(size_t)(p + W) * 3]], 1e-4)));
         vy = __dmul_rn(g, g);
     }
     wx[p] = vx;
@@ -590,7 +590,9 @@ int nct_solve_nonlocal(nct_ctx *ctx, double *a_dev, double *b_dev, const double 
 
     NCT_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned), ctx->stream));
     NCT_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int) * ((size_t)n + 1), ctx->stream));
-    nl_setup_kernel<<<blocks, TPB, 0, ctx->stream>>>(weight_dev, cnt_lab_dev, h, w, lam, alpha_f, sqrt_dw, d2, wx2, wy2);
+    const double *ptab = nct_pow_table(ctx, alpha_f);
+    if (!ptab) return NCT_ERR_NOMEM;
+    nl_setup_kernel<<<blocks, TPB, 0, ctx->stream>>>(weight_dev, cnt_lab_dev, h, w, lam, ptab, sqrt_dw, d2, wx2, wy2);
     NCT_CHECK_LAUNCH(ctx);
     nl_links_kernel<<<nct_div_up(n * 8, TPB), TPB, 0, ctx->stream>>>(knn_id_dev, knn_w_dev, n, 8, nlw, kw2, count);
     NCT_CHECK_LAUNCH(ctx);
@@ -654,7 +656,9 @@ int nct_solve_wls_jacobi(nct_ctx *ctx, double *a_dev, double *b_dev, const doubl
            *Ap = vec + (size_t)n * 30;
 
     NCT_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned), ctx->stream));
-    wls_setup_kernel<<<blocks, TPB, 0, ctx->stream>>>(cnt_lab_full_dev, H, W, lam, alpha, wx, wy);
+    const double *ptab = nct_pow_table(ctx, alpha);
+    if (!ptab) return NCT_ERR_NOMEM;
+    wls_setup_kernel<<<blocks, TPB, 0, ctx->stream>>>(cnt_lab_full_dev, H, W, lam, ptab, wx, wy);
     NCT_CHECK_LAUNCH(ctx);
     wls_pack_kernel<<<blocks, TPB, 0, ctx->stream>>>(a_dev, b_dev, n, x);
     NCT_CHECK_LAUNCH(ctx);

@@ -427,7 +427,7 @@ __global__ void mg_diag_kernel(MgLevel L)
 
 // fine-level edge weights in FP64 (the operator CG solves with) plus FP32 copies for the preconditioner
 __global__ void wls_weights_kernel(const uint8_t *__restrict__ lab, const double *__restrict__ rough, int H, int W, double lam,
-                                   double alpha, double *__restrict__ wx, double *__restrict__ wy, T *__restrict__ fr, T *__restrict__ fwx,
+                                   const double *__restrict__ ptab, double *__restrict__ wx, double *__restrict__ wy, T *__restrict__ fr, T *__restrict__ fwx,
                                    T *__restrict__ fwy)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -436,11 +436,11 @@ __global__ void wls_weights_kernel(const uint8_t *__restrict__ lab, const double
     const double L = __dmul_rn((double)lab[(size_t)p * 3], 1.0 / 255.0);
     double vx = 0.0, vy = 0.0;
     if (x + 1 < W) {
-        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(pow(fabs(__dsub_rn(__dmul_rn((double)lab[(size_t)(p + 1) * 3], 1.0 / 255.0), L)), alpha), 1e-4)));
+        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(ptab[(int)lab[(size_t)p * 3] * 256 + (int)lab[(size_t)(p + 1) * 3]], 1e-4)));
         vx = __dmul_rn(g, g);
     }
     if (y + 1 < H) {
-        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(pow(fabs(__dsub_rn(__dmul_rn((double)lab[(size_t)(p + W) * 3], 1.0 / 255.0), L)), alpha), 1e-4)));
+        const double g = __dsqrt_rn(__ddiv_rn(lam, __dadd_rn(ptab[(int)lab[(size_t)p * 3] * 256 + (int)lab[(size_t)(p + W) * 3]], 1e-4)));
         vy = __dmul_rn(g, g);
     }
     wx[p] = vx;
@@ -679,7 +679,9 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
 
     // ---- set-up: fine weights, coarse operators, diagonals
     NCT_CUDA(ctx, cudaMemsetAsync(counter, 0, sizeof(unsigned), ctx->stream));
-    wls_weights_kernel<<<blocks0, TPB, 0, ctx->stream>>>(cnt_lab_full_dev, rough_dev, H, W, lam, alpha, wx64, wy64, (T *)h.lv[0].rsum,
+    const double *ptab = nct_pow_table(ctx, alpha);
+    if (!ptab) return NCT_ERR_NOMEM;
+    wls_weights_kernel<<<blocks0, TPB, 0, ctx->stream>>>(cnt_lab_full_dev, rough_dev, H, W, lam, ptab, wx64, wy64, (T *)h.lv[0].rsum,
                                                          (T *)h.lv[0].wx, (T *)h.lv[0].wy);
     NCT_CHECK_LAUNCH(ctx);
     for (int k = 0; k < nl; ++k) {

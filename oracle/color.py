@@ -127,9 +127,21 @@ def gradient_weights(L, lam, alpha):
     h, w = L.shape
     gx = np.zeros((h, w))
     gy = np.zeros((h, w))
-    gx[:, :-1] = np.sqrt(lam / (np.abs(L[:, 1:] - L[:, :-1]) ** alpha + 1e-4))
-    gy[:-1, :] = np.sqrt(lam / (np.abs(L[1:, :] - L[:-1, :]) ** alpha + 1e-4))
+    gx[:, :-1] = np.sqrt(lam / (pow_libm(np.abs(L[:, 1:] - L[:, :-1]), alpha) + 1e-4))
+    gy[:-1, :] = np.sqrt(lam / (pow_libm(np.abs(L[1:, :] - L[:-1, :]), alpha) + 1e-4))
     return gx, gy
+
+
+def pow_libm(x, alpha):
+    """Element-wise pow through the C library (math.pow -> libm), not numpy's vector loops: numpy may dispatch
+    float64 pow to SIMD code whose last bit differs between CPUs, and the colour least squares amplifies a 1-ulp
+    difference in these weights to ~43 dB in the final image (tests/test_oracle_pipeline.py).  L is 8-bit / 255, so
+    there are at most 65536 distinct arguments."""
+    import math
+
+    u, inv = np.unique(np.asarray(x, np.float64), return_inverse=True)
+    pu = np.array([math.pow(float(v), float(alpha)) for v in u], np.float64)
+    return pu[inv].reshape(np.shape(x))
 
 
 # ------------------------------------------------------------------ non-local least squares

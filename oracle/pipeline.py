@@ -32,10 +32,13 @@ DEFAULT_CFG = dict(bds=2.0, eps=0.6, nl=2.0, l=0.125, w=0.024, clusters=10, knum
 
 
 def transfer_pair(cnt, stl, weights=None, cfg=None, features_fn=None, on_level=None, stop_after_level=4, timings=None,
-                  im2col=True, pm_mode="canonical", result_hook=None):
+                  im2col=True, pm_mode="canonical", result_hook=None, cg_mode="reference"):
     """cnt, stl: uint8 BGR (H, W, 3).  Returns the uint8 BGR result (content size).
     pm_mode: "canonical" = deterministic jump-flood oracle (the parity target); "reference" = reference-semantics
-    in-place serial PatchMatch in the reference's layout / summation order (CPU baseline only)."""
+    in-place serial PatchMatch in the reference's layout / summation order (CPU baseline only).
+    cg_mode: "reference" = explicit A, A^T A by scipy (the reference's structure; summation order unspecified);
+    "canonical" = the defined-order matrix-free CG of oracle/cg_oracle.c (decision N1) -- with canonical features
+    (vgg.features_canonical) this makes the whole oracle run a bit-level target for the product."""
     cfg = DEFAULT_CFG | (cfg or {})
     t_acc = timings if timings is not None else {}
 
@@ -106,8 +109,12 @@ def transfer_pair(cnt, stl, weights=None, cfg=None, features_fn=None, on_level=N
         weight = color.confidence_weights(err.reshape(ah, aw))
         norm_factor = float(cw * ch) / float(aw * ah)
         lam = cfg["w"] * norm_factor
-        a1, b1, its = color.solve_nonlocal(a0, b0, weight, cnt_lab * (1.0 / 255.0), stl_lab * (1.0 / 255.0), knn_id, knn_w, l,
-                                           cfg["l"], cfg["alpha"], cfg["nl"], cfg["knum"], norm_factor)
+        if cg_mode == "canonical":
+            d2, wx2, wy2, kw2 = canonical_cg_weights(weight, cnt_lab, knn_id, knn_w, cfg["l"], cfg["alpha"], cfg["nl"], cfg["knum"], norm_factor)
+            a1, b1, its = _pm.solve_nonlocal_canon(a0, b0, cnt_lab, stl_lab, d2, wx2, wy2, knn_id, kw2, 50 if l == 4 else 100)
+        else:
+            a1, b1, its = color.solve_nonlocal(a0, b0, weight, cnt_lab * (1.0 / 255.0), stl_lab * (1.0 / 255.0), knn_id, knn_w, l,
+                                               cfg["l"], cfg["alpha"], cfg["nl"], cfg["knum"], norm_factor)
         tick("nonlocal", t0)
         t0 = time.perf_counter()
         a2, b2, rough = color.upsample_coefficients(a1, b1, cnt_lab_full_d, cw, ch)
@@ -131,6 +138,24 @@ def transfer_pair(cnt, stl, weights=None, cfg=None, features_fn=None, on_level=N
                 featC[k] = new[k]
             tick("vgg", t0)
     return result
+
+
+def canonical_cg_weights(weight, cnt_lab_u8, knn_id, knn_w, local_weight, alpha, nonlocal_weight, knum, d_weight):
+    """The squared constraint weights of solve_nonlocal_downsample_gpu_gradient (CT/ColorTransfer.cpp:548-911) in the
+    form cg_oracle.c consumes: d2 = (sqrt(weight) * sqrt(dWeight))^2 per pixel; wx2 / wy2 = 2 g^2 for the edge to x+1 /
+    y+1 (each 4-neighbour edge is listed from both ends); kw2 = (sqrt(NN.w) * sqrt(nl / k))^2 per link.  Every
+    operation is a separately rounded IEEE double operation (float parameters as in the reference's signature)."""
+    h, w = weight.shape
+    lam = float(np.float32(local_weight))
+    gx, gy = color.gradient_weights(cnt_lab_u8[..., 0].astype(np.float64) * (1.0 / 255.0), lam, float(np.float32(alpha)))
+    gx2, gy2 = gx * gx, gy * gy
+    wx2 = (gx2 + gx2).ravel()
+    wy2 = (gy2 + gy2).ravel()
+    dw = np.sqrt(weight.ravel()) * float(np.sqrt(np.float32(d_weight)))
+    d2 = dw * dw
+    iw = np.sqrt(np.asarray(knn_w, np.float64)) * np.sqrt(nonlocal_weight / float(knum))
+    kw2 = np.where(np.asarray(knn_id) >= 0, iw * iw, 0.0)
+    return d2, wx2, wy2, np.ascontiguousarray(kw2)
 
 
 def psnr(a, b):

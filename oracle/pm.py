@@ -22,7 +22,7 @@ _lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 
 def build(force: bool = False):
     """Compile the C restatement (gcc). Building the checker is not using it."""
-    srcs = [os.path.join(_HERE, f) for f in ("pm_oracle.c", "bds_oracle.c", "cg_oracle.c", "cluster_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("pm_oracle.c", "bds_oracle.c", "cg_oracle.c", "cluster_oracle.c", "conv_oracle.c")]
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle_pm.so"], stdout=subprocess.DEVNULL)
     return _LIB
@@ -58,6 +58,9 @@ def lib():
         L.orc_kmeans_labels.restype = C.c_int
         for fn in (L.orc_find_knns, L.orc_find_knns_brute):
             fn.argtypes = [_ip, C.c_int, C.c_int, C.c_int, _bp, C.c_int, C.c_int, C.c_int, _ip, _dp]
+        L.orc_conv3x3_relu_canon.argtypes = [_fp, _fp, _fp, _fp] + [C.c_int] * 4
+        L.orc_maxpool2x2_ceil.argtypes = [_fp, _fp] + [C.c_int] * 3
+        L.orc_preprocess_bgr.argtypes = [_bp, _fp, C.c_int]
         _lib = L
     return _lib
 

@@ -11,7 +11,10 @@ Follows
   relu             caffe/layers/relu_layer.cpp:9-19
 
 FP32 throughout (torch CPU; its convolution's summation order is not Caffe's, so conv parity is a tolerance test
-like Caffe's own, caffe/test/test_convolution_layer.cpp:231-265, 1e-4)."""
+like Caffe's own, caffe/test/test_convolution_layer.cpp:231-265, 1e-4).
+
+`features_canonical` runs the same graph through oracle/conv_oracle.c, whose summation order is DEFINED (tap-major,
+channel-minor, one fmaf chain per output) -- the bit-exact target of the product's FP32 convolution engine."""
 from __future__ import annotations
 
 import numpy as np
@@ -49,4 +52,33 @@ def features(img_bgr_u8, weights, deepest_level=0, im2col=False):
                 out[lvl] = np.ascontiguousarray(x[0].permute(1, 2, 0).numpy())
                 if lvl == deepest_level:
                     break
+    return out
+
+
+def features_canonical(img_bgr_u8, weights, deepest_level=0):
+    """Same graph, canonical summation order (oracle/conv_oracle.c).  Returns [f0..f4] HWC float32 (None below
+    deepest_level)."""
+    from .pm import lib
+
+    L = lib()
+    img = np.ascontiguousarray(img_bgr_u8, dtype=np.uint8)
+    H, W, _ = img.shape
+    x = np.empty((H, W, 3), np.float32)
+    L.orc_preprocess_bgr(img, x, H * W)
+    out = [None] * 5
+    for name, cin, cout, pool_before in VGG19_TRUNK:
+        if pool_before:
+            Ho, Wo = (H - 2 + 1) // 2 + 1, (W - 2 + 1) // 2 + 1
+            y = np.empty((Ho, Wo, cin), np.float32)
+            L.orc_maxpool2x2_ceil(x, y, H, W, cin)
+            x, H, W = y, Ho, Wo
+        w, b = weights[name]
+        y = np.empty((H, W, cout), np.float32)
+        L.orc_conv3x3_relu_canon(x, np.ascontiguousarray(w, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32), y, H, W, cin, cout)
+        x = y
+        if name in LEVEL_OF:
+            lvl = LEVEL_OF[name]
+            out[lvl] = x
+            if lvl == deepest_level:
+                break
     return out

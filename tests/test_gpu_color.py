@@ -107,13 +107,12 @@ def test_solve_nonlocal(ctx, dev, h, w, layer, dwt):
                              to_dev(kw, dev), layer, d_weight=dwt, want_iters=True)
     d2, wx2, wy2 = (ctx.read_scratch(k, np.float64, n) for k in ("nl_d2", "nl_wx2", "nl_wy2"))
     kw2 = ctx.read_scratch("nl_kw2", np.float64, n * 8)
-    # the kernel's operator coefficients agree with the reference formulas (pow() may differ in the last ulps)
-    gx, gy = color.gradient_weights(cl[..., 0] / 255.0, float(np.float32(0.125)), float(np.float32(1.2)))
-    dw = np.sqrt(weight.ravel()) * float(np.sqrt(np.float32(dwt)))
-    assert np.allclose(wx2, 2 * (gx * gx).ravel(), rtol=1e-14) and np.allclose(wy2, 2 * (gy * gy).ravel(), rtol=1e-14)
-    assert np.array_equal(d2, dw * dw)
-    iw = np.sqrt(kw) * np.sqrt(2.0 / 8)
-    assert np.array_equal(kw2.reshape(n, 8), np.where(ids >= 0, iw * iw, 0.0))
+    # the kernel's operator coefficients equal the oracle's bit for bit (pow() comes from a host-libm table on both sides)
+    from oracle import pipeline
+    od2, owx2, owy2, okw2 = pipeline.canonical_cg_weights(weight, cl, ids, kw, 0.125, 1.2, 2.0, 8, dwt)
+    assert np.array_equal(wx2, owx2) and np.array_equal(wy2, owy2)
+    assert np.array_equal(d2, od2)
+    assert np.array_equal(kw2.reshape(n, 8), okw2)
     # bit-exact against the canonical-order oracle
     maxit = 50 if layer == 4 else 100
     ca, cb, cits = oracle.solve_nonlocal_canon(a0, b0, cl, sl, d2, wx2, wy2, ids, kw2, maxit)

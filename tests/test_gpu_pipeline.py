@@ -104,6 +104,26 @@ def test_pipeline_end_to_end_psnr_vs_independent_oracle(pctx, dev, weights):
     assert ps >= 35.0  # see DESIGN.md: FP32 conv summation order differs -> a few NNF entries flip -> bounded colour drift
 
 
+@pytest.mark.parametrize("seed,ch,cw,sh,sw", [(4, 128, 128, 128, 128), (8, 120, 152, 136, 104), (9, 256, 256, 256, 256)])
+def test_pipeline_end_to_end_against_independent_canonical_oracle(pctx, dev, weights, seed, ch, cw, sh, sw):
+    """The north star's end-to-end bar (final image PSNR >= 50 dB), on fully INDEPENDENT runs: the oracle computes its
+    own features (oracle/conv_oracle.c, canonical order), its own NNFs, votes, neighbours, weights (host libm), the
+    canonical-order CG and a direct WLS solve; nothing is shared with the GPU run but the inputs.  The FP32 convolution
+    engine is bit-exact against the canonical conv order, so every stage up to the CG is bit-identical and only the
+    iterative WLS (1e-8 residual vs. direct solve) can differ -- by rare single-LSB flips."""
+    from oracle import vgg
+
+    cnt, stl = synth.pair(seed, ch, cw, sh, sw)
+    pctx.set_vgg_engine(0)
+    out = pctx.transfer_pair(cnt, stl)
+    ref = pipeline.transfer_pair(cnt, stl, None, features_fn=lambda img, deepest: vgg.features_canonical(img, weights, deepest),
+                                 cg_mode="canonical")
+    ps = pipeline.psnr(out, ref)
+    ndiff = int((out != ref).sum())
+    print(f"end-to-end vs independent canonical oracle ({ch}x{cw} / {sh}x{sw}): PSNR {ps:.1f} dB, {ndiff} of {out.size} bytes differ")
+    assert ps >= 50.0
+
+
 def test_pipeline_host_and_device_entry_points_agree_and_are_deterministic(pctx, dev):
     cnt, stl = synth.pair(5, 96, 128, 128, 96)
     a = pctx.transfer_pair(cnt, stl)

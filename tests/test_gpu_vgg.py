@@ -42,6 +42,20 @@ def test_vgg19_features_match_oracle(vctx, dev, weights, h, w):
         assert (g >= 0).all()  # post-ReLU
 
 
+@pytest.mark.parametrize("h,w", [(64, 48), (97, 131), (160, 160)])
+def test_fp32_engine_is_bit_exact_against_the_canonical_order_oracle(vctx, dev, weights, h, w):
+    """Engine 0 (FP32 CUDA cores) sums tap-major / channel-minor with one fmaf chain per output -- the order
+    oracle/conv_oracle.c defines -- so all five feature maps are bit-identical, ragged sizes included."""
+    img, _ = synth.pair(11, h, w)
+    vctx.set_vgg_engine(0)
+    feats = vctx.predict(to_dev(img, dev), 0)
+    vctx.synchronize()
+    ref = vgg.features_canonical(img, weights, 0)
+    for l in range(5):
+        g = feats[l].cpu().numpy()
+        assert np.array_equal(g.view(np.uint32), ref[l].view(np.uint32)), f"level {l}: {(g != ref[l]).sum()} of {g.size} values differ"
+
+
 def test_vgg19_im2col_oracle_agrees_with_direct(weights):
     img, _ = synth.pair(1, 40, 36)
     a = vgg.features(img, weights, 0)
