@@ -3,6 +3,7 @@
 // cudaMemGetInfo) and the per-level cudaMalloc/cudaFree churn of NCT/main.cu:238-326.
 #include "nct_internal.h"
 #include <cmath>
+#include <cstring>
 
 int nct_fail(nct_ctx *ctx, int code, const char *fmt, ...)
 {
@@ -38,25 +39,31 @@ void *nct_scratch(nct_ctx *ctx, const char *name, size_t bytes)
     return p;
 }
 
+// Both tables are uploaded with stream-ordered copies on ctx->stream (a synchronous cudaMemcpy from pageable memory
+// may return before the DMA has landed, and ctx->stream does not synchronise with the legacy default stream).
 const double *nct_pow_table(nct_ctx *ctx, double alpha)
 {
-    double *dev = (double *)nct_scratch(ctx, "tab_pow", sizeof(double) * 65536);
+    // one table per exponent: the CG stage uses (double)(float)alpha, the WLS stage alpha itself
+    // (CT/ColorTransfer.cpp:548-550 takes floats, :951 doubles); tables are never rebuilt in steady state
+    char name[48];
+    unsigned long long bits;
+    memcpy(&bits, &alpha, sizeof(bits));
+    snprintf(name, sizeof(name), "tab_pow_%016llx", bits);
+    auto it = ctx->scratch.find(name);
+    if (it != ctx->scratch.end() && it->second.ptr) return (const double *)it->second.ptr;
+    double *dev = (double *)nct_scratch(ctx, name, sizeof(double) * 65536);
     if (!dev) return nullptr;
-    if (ctx->pow_alpha != alpha || ctx->pow_host.empty()) {
-        // queued kernels may still read the previous table / the host staging vector
-        cudaStreamSynchronize(ctx->stream);
-        ctx->pow_host.resize(65536);
-        for (int l0 = 0; l0 < 256; ++l0)
-            for (int l1 = 0; l1 < 256; ++l1) {
-                volatile double a = (double)l1 * (1.0 / 255.0), b = (double)l0 * (1.0 / 255.0);  // volatile: no contraction
-                volatile double d = a - b;
-                ctx->pow_host[l0 * 256 + l1] = pow(fabs(d), alpha);
-            }
-        if (cudaMemcpy(dev, ctx->pow_host.data(), sizeof(double) * 65536, cudaMemcpyHostToDevice) != cudaSuccess) {
-            nct_fail(ctx, NCT_ERR_CUDA, "upload of the pow table failed");
-            return nullptr;
+    std::vector<double> &host = ctx->pow_host[bits];
+    host.resize(65536);
+    for (int l0 = 0; l0 < 256; ++l0)
+        for (int l1 = 0; l1 < 256; ++l1) {
+            volatile double a = (double)l1 * (1.0 / 255.0), b = (double)l0 * (1.0 / 255.0);  // volatile: no contraction
+            volatile double d = a - b;
+            host[l0 * 256 + l1] = pow(fabs(d), alpha);
         }
-        ctx->pow_alpha = alpha;
+    if (cudaMemcpyAsync(dev, host.data(), sizeof(double) * 65536, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+        nct_fail(ctx, NCT_ERR_CUDA, "upload of the pow table failed");
+        return nullptr;
     }
     return dev;
 }
@@ -64,19 +71,19 @@ const double *nct_pow_table(nct_ctx *ctx, double alpha)
 const double *nct_knn_weight_table(nct_ctx *ctx)
 {
     const int n = 3 * 255 * 255 + 1;
+    auto it = ctx->scratch.find("tab_knnw");
+    if (it != ctx->scratch.end() && it->second.ptr) return (const double *)it->second.ptr;
     double *dev = (double *)nct_scratch(ctx, "tab_knnw", sizeof(double) * n);
     if (!dev) return nullptr;
-    if (ctx->knnw_host.empty()) {
-        ctx->knnw_host.resize(n);
-        for (int i = 0; i < n; ++i) {
-            volatile double d = sqrt((double)i) / 255.0;
-            volatile double q = d / 3.0;
-            ctx->knnw_host[i] = exp(1.0 - q);
-        }
-        if (cudaMemcpy(dev, ctx->knnw_host.data(), sizeof(double) * n, cudaMemcpyHostToDevice) != cudaSuccess) {
-            nct_fail(ctx, NCT_ERR_CUDA, "upload of the k-NN weight table failed");
-            return nullptr;
-        }
+    ctx->knnw_host.resize(n);
+    for (int i = 0; i < n; ++i) {
+        volatile double d = sqrt((double)i) / 255.0;
+        volatile double q = d / 3.0;
+        ctx->knnw_host[i] = exp(1.0 - q);
+    }
+    if (cudaMemcpyAsync(dev, ctx->knnw_host.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+        nct_fail(ctx, NCT_ERR_CUDA, "upload of the k-NN weight table failed");
+        return nullptr;
     }
     return dev;
 }

@@ -42,8 +42,8 @@ struct nct_ctx {
     // transcendental tables evaluated by the HOST C library (the same libm the oracle uses), so that the gradient and
     // neighbour weights entering the un-converged CG are bit-identical to the oracle's (a 1-ulp
     // difference there changes the final image by ~43 dB)
-    double pow_alpha = -1.0;
-    std::vector<double> pow_host, knnw_host;
+    std::map<unsigned long long, std::vector<double>> pow_host;  // keyed by the exponent's bit pattern
+    std::vector<double> knnw_host;
 
     // opaque sub-module states (owned, freed in nct_destroy)
     struct VggState *vgg = nullptr;

@@ -106,6 +106,8 @@ struct PMDir {
     const uint32_t *nnf_in;  // NNF at the end of the previous step
     uint32_t *nnf_out;
     float *nnd;              // own entry only: read + write in place
+    const int8_t *lc_in;     // step of the last change of every entry at the end of the previous step (-1 = never)
+    int8_t *lc_out;
     const float *rng;        // [aw][ndraws]
     int ah, aw, bh, bw;
     int rs_start, n_mag, ndraws;
@@ -117,6 +119,7 @@ struct PMStep {
     int nq_total;   // queries of both directions
     int jump;
     int iter;
+    int t;          // step index 4 * iter + jump index (D4 bookkeeping)
     int first;      // compute the initial distance instead of reading nnd
     int do_random;  // jump == 1: fused random search
     unsigned long long *counters;  // nullptr or 2 x u64 {evaluated, reference-semantics}
@@ -175,14 +178,14 @@ struct QueryPatch {
 // loads the query patch into registers (or records where to find it)
 template <int C>
 __device__ __forceinline__ void load_query(QueryPatch<C> &q, const float *__restrict__ a, int ax, int ay, int aw,
-                                           int ah, int lane)
+                                           int ah, int lane, bool fetch = true)
 {
     using T = PMTraits<C>;
     q.aw = aw;
     q.amask = patch_mask(ax, ay, aw, ah);
     const int j = (T::GROUPS == 1) ? lane : (lane % T::V);
     q.a_base = a + ((size_t)ay * aw + ax) * C + j * 4;
-    if (T::A_IN_REGS) {
+    if (T::A_IN_REGS && fetch) {
         const int g = (T::GROUPS == 1) ? 0 : lane / T::V;
 #pragma unroll
         for (int i = 0; i < T::PPL; ++i) {
@@ -273,20 +276,10 @@ __global__ void __launch_bounds__(PM_TPB, (C <= 128) ? PM_MINB_SMALL : 1) pm_ste
     const int aw = D.aw, ah = D.ah, bw = D.bw, bh = D.bh;
     const int ax = p % aw, ay = p / aw;
 
-    QueryPatch<C> q;
-    load_query<C>(q, D.a, ax, ay, aw, ah, lane);
-
     const uint32_t v0 = D.nnf_in[p];
     int xbest = int_to_x(v0), ybest = int_to_y(v0);
     float dbest;
     unsigned n_eval = 0, n_ref = 0;
-    if (s.first) {
-        dbest = eval_dist<C>(q, D.b, xbest, ybest, bw, bh, lane);
-        n_eval++;
-        n_ref++;
-    } else {
-        dbest = D.nnd[p];
-    }
 
     // ---- propagation: L, R, U, D candidates from the previous step's NNF
     const int jump = s.jump;
@@ -310,10 +303,24 @@ __global__ void __launch_bounds__(PM_TPB, (C <= 128) ? PM_MINB_SMALL : 1) pm_ste
                     bool dup = (cand[k] == v0);
 #pragma unroll
                     for (int t = 0; t < k; ++t) dup = dup || (use[t] && cand[t] == cand[k]);
-                    use[k] = !dup;
+                    // D4 (unchanged-source skip, oracle/pm_oracle.c): the neighbour's entry has not changed since this
+                    // slot last judged it, so the candidate would be rejected again
+                    const bool stale = s.t >= 4 && (int)D.lc_in[qy[k] * aw + qx[k]] <= s.t - 5;
+                    use[k] = !dup && !stale;
                 }
             }
         }
+    }
+    // with D4 most queries of a converged region have nothing to evaluate in the jump 8/4/2 steps: the query patch is
+    // only fetched when something will be compared against it
+    QueryPatch<C> q;
+    load_query<C>(q, D.a, ax, ay, aw, ah, lane, s.first || s.do_random || use[0] || use[1] || use[2] || use[3]);
+    if (s.first) {
+        dbest = eval_dist<C>(q, D.b, xbest, ybest, bw, bh, lane);
+        n_eval++;
+        n_ref++;
+    } else {
+        dbest = D.nnd[p];
     }
     // the distances do not depend on each other: issue the row loads of BATCH candidates before the first FMA
     // (memory-level parallelism; the kernel is latency-bound, profiles/r1_pm_step_ncu.md)
@@ -367,7 +374,9 @@ __global__ void __launch_bounds__(PM_TPB, (C <= 128) ? PM_MINB_SMALL : 1) pm_ste
     }
 
     if (lane == 0) {
-        D.nnf_out[p] = xy_to_int(xbest, ybest);
+        const uint32_t vnew = xy_to_int(xbest, ybest);
+        D.nnf_out[p] = vnew;
+        D.lc_out[p] = vnew != v0 ? (int8_t)s.t : D.lc_in[p];
         D.nnd[p] = dbest;
         if (s.counters) {
             atomicAdd(&s.counters[0], (unsigned long long)n_eval);
@@ -457,31 +466,10 @@ __global__ void __launch_bounds__(128, 4) pm_step_hw_kernel(const PMStep s)
     const int aw = D.aw, ah = D.ah, bw = D.bw, bh = D.bh;
     const int ax = p % aw, ay = p / aw;
 
-    HWQuery<C> q;
-    q.aw = aw;
-    q.amask = patch_mask(ax, ay, aw, ah);
-    q.a_base = D.a + ((size_t)ay * aw + ax) * C + j * 4;
-    if (HWTraits<C>::A_IN_REGS) {
-#pragma unroll
-        for (int pi = 0; pi < 9; ++pi) {
-            const int dy = pi / 3 - 1, dx = pi % 3 - 1;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if ((q.amask >> pi) & 1u) v = ldg4(q.a_base + ((ptrdiff_t)dy * aw + dx) * C);
-            q.a[pi] = v;
-        }
-    }
-
     const uint32_t v0 = D.nnf_in[p];
     int xbest = int_to_x(v0), ybest = int_to_y(v0);
     float dbest;
     unsigned n_eval = 0, n_ref = 0;
-    if (s.first) {
-        dbest = hw_eval<C>(q, D.b, xbest, ybest, bw, bh, j, hmask);
-        n_eval++;
-        n_ref++;
-    } else {
-        dbest = D.nnd[p];
-    }
 
     const int jump = s.jump;
     uint32_t cand[4];
@@ -504,10 +492,35 @@ __global__ void __launch_bounds__(128, 4) pm_step_hw_kernel(const PMStep s)
                     bool dup = (cand[k] == v0);
 #pragma unroll
                     for (int t = 0; t < k; ++t) dup = dup || (use[t] && cand[t] == cand[k]);
-                    use[k] = !dup;
+                    // D4 (unchanged-source skip, oracle/pm_oracle.c): the neighbour's entry has not changed since this
+                    // slot last judged it, so the candidate would be rejected again
+                    const bool stale = s.t >= 4 && (int)D.lc_in[qy[k] * aw + qx[k]] <= s.t - 5;
+                    use[k] = !dup && !stale;
                 }
             }
         }
+    }
+    // with D4 most queries of a converged region have nothing to evaluate in the jump 8/4/2 steps: the query patch is
+    // only fetched when something will be compared against it
+    HWQuery<C> q;
+    q.aw = aw;
+    q.amask = patch_mask(ax, ay, aw, ah);
+    q.a_base = D.a + ((size_t)ay * aw + ax) * C + j * 4;
+    if (HWTraits<C>::A_IN_REGS && (s.first || s.do_random || use[0] || use[1] || use[2] || use[3])) {
+#pragma unroll
+        for (int pi = 0; pi < 9; ++pi) {
+            const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((q.amask >> pi) & 1u) v = ldg4(q.a_base + ((ptrdiff_t)dy * aw + dx) * C);
+            q.a[pi] = v;
+        }
+    }
+    if (s.first) {
+        dbest = hw_eval<C>(q, D.b, xbest, ybest, bw, bh, j, hmask);
+        n_eval++;
+        n_ref++;
+    } else {
+        dbest = D.nnd[p];
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -542,7 +555,9 @@ __global__ void __launch_bounds__(128, 4) pm_step_hw_kernel(const PMStep s)
         }
     }
     if (j == 0) {
-        D.nnf_out[p] = xy_to_int(xbest, ybest);
+        const uint32_t vnew = xy_to_int(xbest, ybest);
+        D.nnf_out[p] = vnew;
+        D.lc_out[p] = vnew != v0 ? (int8_t)s.t : D.lc_in[p];
         D.nnd[p] = dbest;
         if (s.counters) {
             atomicAdd(&s.counters[0], (unsigned long long)n_eval);
@@ -596,7 +611,7 @@ __global__ void __launch_bounds__(PM_TPB) pm_init_dist_kernel(const PMStep s)
 }
 
 template <int C>
-int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1, int ndir)
+int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1, int ndir, int8_t *lc)
 {
     const int warps_per_block = PM_TPB / 32;
     const int blocks = nct_div_up(s.nq_total, warps_per_block);
@@ -608,11 +623,16 @@ int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1
     }
     uint32_t *user[2] = {s.d[0].nnf_out, ndir > 1 ? s.d[1].nnf_out : nullptr};
     uint32_t *tmp[2] = {tmp0, tmp1};
+    // last-change steps, double buffered like the field: [buffer][direction 0 | direction 1]
+    const size_t nq = (size_t)s.nq_total;
+    NCT_CUDA(ctx, cudaMemsetAsync(lc, 0xff, nq, ctx->stream));
+    int8_t *lcbuf[2][2] = {{lc, lc + s.nq0}, {lc + nq, lc + nq + s.nq0}};
     int step = 0;
     for (int iter = 0; iter < iters; ++iter)
         for (int jump = 8; jump > 0; jump /= 2, ++step) {
             s.iter = iter;
             s.jump = jump;
+            s.t = step;
             s.first = (step == 0);
             s.do_random = (jump == 1);
             for (int d = 0; d < ndir; ++d) {
@@ -620,6 +640,8 @@ int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1
                 // 4*iters steps is even, so the final NNF lands in the caller's buffer.
                 s.d[d].nnf_in = (step & 1) ? tmp[d] : user[d];
                 s.d[d].nnf_out = (step & 1) ? user[d] : tmp[d];
+                s.d[d].lc_in = lcbuf[step & 1][d];
+                s.d[d].lc_out = lcbuf[(step & 1) ^ 1][d];
             }
             StepLauncher<C>::go(s, ctx->stream);
             NCT_CHECK_LAUNCH(ctx);
@@ -664,7 +686,7 @@ int check_params(nct_ctx *ctx, const int *p)
                          p[4] <= 4096,
                 "image sides must be in [1, 4096] (12-bit NNF packing)");
     NCT_REQUIRE(ctx, p[5] == 3, "patch size %d unsupported (reference uses 3, CT/Config.h:70)", p[5]);
-    NCT_REQUIRE(ctx, p[6] >= 0 && p[6] <= 64, "iters %d out of range", p[6]);
+    NCT_REQUIRE(ctx, p[6] >= 0 && p[6] <= 31, "iters %d out of range [0, 31] (the reference uses 10, NCT/main.cu:65)", p[6]);
     NCT_REQUIRE(ctx, p[7] >= 1, "rs_max must be >= 1");
     NCT_REQUIRE(ctx, p[8] == 0, "flag_constraint must be 0 (the reference never enables it, NCT/main.cu:66)");
     return NCT_OK;
@@ -672,13 +694,15 @@ int check_params(nct_ctx *ctx, const int *p)
 
 int dispatch_pm(nct_ctx *ctx, int C, PMStep &s, int iters, uint32_t *t0, uint32_t *t1, int ndir)
 {
+    int8_t *lc = (int8_t *)nct_scratch(ctx, "pm_last_change", 2 * (size_t)s.nq_total);
+    if (!lc) return NCT_ERR_NOMEM;
     switch (C) {
-    case 16: return launch_pm<16>(ctx, s, iters, t0, t1, ndir);
-    case 32: return launch_pm<32>(ctx, s, iters, t0, t1, ndir);
-    case 64: return launch_pm<64>(ctx, s, iters, t0, t1, ndir);
-    case 128: return launch_pm<128>(ctx, s, iters, t0, t1, ndir);
-    case 256: return launch_pm<256>(ctx, s, iters, t0, t1, ndir);
-    case 512: return launch_pm<512>(ctx, s, iters, t0, t1, ndir);
+    case 16: return launch_pm<16>(ctx, s, iters, t0, t1, ndir, lc);
+    case 32: return launch_pm<32>(ctx, s, iters, t0, t1, ndir, lc);
+    case 64: return launch_pm<64>(ctx, s, iters, t0, t1, ndir, lc);
+    case 128: return launch_pm<128>(ctx, s, iters, t0, t1, ndir, lc);
+    case 256: return launch_pm<256>(ctx, s, iters, t0, t1, ndir, lc);
+    case 512: return launch_pm<512>(ctx, s, iters, t0, t1, ndir, lc);
     }
     return nct_fail(ctx, NCT_ERR_ARG, "unsupported channel count %d", C);
 }

@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(TPB) mg_smooth_rz_kernel(MgLevel L, PcgScalars
 }
 
 // the whole bottom of the V-cycle (levels h.bottom .. nlevels-1, each <= 1024 nodes) in one block
-__global__ void __launch_bounds__(512) mg_bottom_kernel(MgHierarchy h)
+__global__ void __launch_bounds__(1024) mg_bottom_kernel(MgHierarchy h)
 {
     const int last = h.nlevels - 1;
     for (int k = h.bottom; k < last; ++k) {
@@ -591,7 +591,7 @@ int vcycle(nct_ctx *ctx, const MgHierarchy &h, PcgScalars *sc, double *partials,
         mg_restrict_kernel<<<nct_div_up(Cc.n, TPB), TPB, 0, ctx->stream>>>(L, Cc);
         NCT_CHECK_LAUNCH(ctx);
     }
-    mg_bottom_kernel<<<1, 512, 0, ctx->stream>>>(h);
+    mg_bottom_kernel<<<1, h.lv[h.bottom].n > 1024 ? 1024 : 512, 0, ctx->stream>>>(h);
     NCT_CHECK_LAUNCH(ctx);
     for (int k = h.bottom - 1; k >= 0; --k) {
         const MgLevel &L = h.lv[k];
@@ -671,8 +671,9 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
         L.b = vp; vp += (size_t)L.n * 6;
         L.t = vp; vp += (size_t)L.n * 6;
     }
+    static const int bottom_n = getenv("NCT_MG_BOTTOM_N") ? atoi(getenv("NCT_MG_BOTTOM_N")) : 1024;
     for (int k = 0; k < nl; ++k)
-        if (h.lv[k].n <= 1024) { h.bottom = k; break; }
+        if (h.lv[k].n <= bottom_n) { h.bottom = k; break; }
     if (h.bottom == 0) h.bottom = 1;  // level 0 always uses the grid kernels (tiny images only)
     double *x = dvec, *r = dvec + (size_t)n0 * 6, *p0 = dvec + (size_t)n0 * 12, *p1 = dvec + (size_t)n0 * 18, *Ap = dvec + (size_t)n0 * 24;
     double *wx64 = dcoef, *wy64 = dcoef + n0;

@@ -45,6 +45,8 @@ def lib():
         L.orc_chw_to_hwc.argtypes = [_fp, _fp, C.c_int, C.c_int]
         L.orc_patchmatch.argtypes = [_fp, _fp, _up, _fp, _ip, _lp]
         L.orc_patchmatch.restype = C.c_int
+        L.orc_patchmatch_opts.argtypes = [_fp, _fp, _up, _fp, _ip, _lp, C.c_int]
+        L.orc_patchmatch_opts.restype = C.c_int
         L.orc_patchmatch_ref_serial.argtypes = [_fp, _fp, _up, _fp, _ip]
         L.orc_patchmatch_ref_serial.restype = C.c_int
         L.orc_num_threads.restype = C.c_int
@@ -121,17 +123,19 @@ def dist_ref_chw(a_chw, b_chw, ax, ay, bx, by, cutoff=float(2**31), use_fma=1):
     return float(lib().orc_dist_ref_chw(a_chw, b_chw, Cn, ah, aw, bh, bw, ax, ay, bx, by, 3, cutoff, use_fma))
 
 
-def patchmatch(a_hwc, b_hwc, ann, params):
-    """Deterministic PatchMatch (decisions D1-D3). Returns (ann, annd, (evals_ref, evals_dedup))."""
+def patchmatch(a_hwc, b_hwc, ann, params, d4=True):
+    """Deterministic PatchMatch (decisions D1-D4). Returns (ann, annd, (evals_ref, evals_gpu, evals_dedup)):
+    evals_ref = evaluations of the reference semantics, evals_gpu = left after D3 de-duplication + D4 unchanged-source
+    skip (what the GPU kernel computes), evals_dedup = left after D3 alone.  d4=False switches D4 off (same field)."""
     a = np.ascontiguousarray(a_hwc, np.float32)
     b = np.ascontiguousarray(b_hwc, np.float32)
     ann = np.array(ann, dtype=np.uint32, copy=True).ravel()
     annd = np.empty(ann.shape[0], np.float32)
-    stats = np.zeros(2, np.int64)
-    rc = lib().orc_patchmatch(a, b, ann, annd, np.ascontiguousarray(params, np.int32), stats)
+    stats = np.zeros(3, np.int64)
+    rc = lib().orc_patchmatch_opts(a, b, ann, annd, np.ascontiguousarray(params, np.int32), stats, 1 if d4 else 0)
     if rc != 0:
         raise ValueError(f"orc_patchmatch: unsupported parameters ({rc})")
-    return ann, annd, (int(stats[0]), int(stats[1]))
+    return ann, annd, (int(stats[0]), int(stats[2]), int(stats[1]))
 
 
 def patchmatch_ref_serial(a_chw, b_chw, ann, params):

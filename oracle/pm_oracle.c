@@ -286,17 +286,34 @@ void orc_chw_to_hwc(const float *src, float *dst, int C, int npix)
  *   (contract of NCT/main.cu:204-214).
  * stats[0] = evaluations the reference semantics perform (neighbour in A, candidate in B,
  *            plus the initial one and every random-search candidate);
- * stats[1] = evaluations left after D3 de-duplication (what the GPU kernel computes). ---- */
+ * stats[1] = evaluations left after D3 de-duplication;
+ * stats[2] = evaluations left after D3 + D4 (what the GPU kernel computes).
+ * D4 (unchanged-source skip): step t = 4 * iter + jump index reads the neighbour q's entry as of the end of step
+ *   t - 1; the same (query, jump, direction) slot read q's entry as of the end of step t - 5 one iteration earlier.
+ *   If q's entry did not change during steps t-4 .. t-1 the candidate is the one already judged then, its distance
+ *   was >= the query's best at that time >= the best now, and acceptance is strict (<): it would be rejected again,
+ *   so it is not evaluated.  The resulting field is identical with and without D4 (orc_patchmatch_opts(.., d4 = 0)
+ *   switches it off; tests/test_oracle_pm.py compares the two).  ---- */
+int orc_patchmatch_opts(const float *a, const float *b, uint32_t *ann, float *annd,
+                        const int *params, long long *stats, int d4);
+
 int orc_patchmatch(const float *a, const float *b, uint32_t *ann, float *annd,
                    const int *params, long long *stats)
+{
+    return orc_patchmatch_opts(a, b, ann, annd, params, stats, 1);
+}
+
+int orc_patchmatch_opts(const float *a, const float *b, uint32_t *ann, float *annd,
+                        const int *params, long long *stats, int d4)
 {
     const int C = params[0], ah = params[1], aw = params[2], bh = params[3], bw = params[4];
     const int patch_w = params[5], iters = params[6], rs_max = params[7];
     if (patch_w != 3 || params[8] != 0) return -1;
+    if (iters > 31) return -3; /* D4 step indices are kept in a signed char */
     if (C % 4 != 0) return -2;
     if (C >= 128 ? (C % 128 != 0) : (C != 64 && C != 32 && C != 16)) return -2;
     const int n = ah * aw;
-    long long ev_ref = 0, ev_dedup = 0;
+    long long ev_ref = 0, ev_dedup = 0, ev_d4 = 0;
 
     int rs_start = rs_max;
     if (rs_start > (bw > bh ? bw : bh)) rs_start = (bw > bh ? bw : bh);
@@ -307,29 +324,36 @@ int orc_patchmatch(const float *a, const float *b, uint32_t *ann, float *annd,
     orc_xorwow_uniform_table(aw, ndraws, rng);
 
     uint32_t *prev = (uint32_t *)malloc(sizeof(uint32_t) * n);
+    /* D4 bookkeeping: step of the last change of every entry (-1 = never), double buffered like the field */
+    signed char *lc = (signed char *)malloc((size_t)n), *lc_prev = (signed char *)malloc((size_t)n);
+    memset(lc, 0xff, (size_t)n);
 
     /* initial distance (:710-712) */
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : ev_ref, ev_dedup)
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : ev_ref, ev_dedup, ev_d4)
     for (int p = 0; p < n; ++p) {
         int ax = p % aw, ay = p / aw;
         uint32_t v = ann[p];
         annd[p] = dist_canon(a, b, C, ah, aw, bh, bw, ax, ay, int_to_x(v), int_to_y(v));
         ev_ref++;
         ev_dedup++;
+        ev_d4++;
     }
 
     for (int iter = 0; iter < iters; ++iter) {
         for (int jump = 8; jump > 0; jump /= 2) {
             memcpy(prev, ann, sizeof(uint32_t) * n);
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : ev_ref, ev_dedup)
+            memcpy(lc_prev, lc, (size_t)n);
+            const int t = 4 * iter + (jump == 8 ? 0 : jump == 4 ? 1 : jump == 2 ? 2 : 3);
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : ev_ref, ev_dedup, ev_d4)
             for (int p = 0; p < n; ++p) {
                 int ax = p % aw, ay = p / aw;
                 uint32_t v0 = prev[p];
                 int xbest = int_to_x(v0), ybest = int_to_y(v0);
                 float dbest = annd[p];
-                uint32_t seen[5];
-                int nseen = 0;
+                uint32_t seen[5], seen4[5];
+                int nseen = 0, nseen4 = 0;
                 seen[nseen++] = v0;
+                seen4[nseen4++] = v0;
                 /* L, R, U, D (:725-798) */
                 const int qx[4] = {ax - jump, ax + jump, ax, ax};
                 const int qy[4] = {ay, ay, ay - jump, ay + jump};
@@ -342,11 +366,16 @@ int orc_patchmatch(const float *a, const float *b, uint32_t *ann, float *annd,
                     if (!(yp >= 0 && yp < bh && xp >= 0 && xp < bw)) continue;
                     ev_ref++;
                     uint32_t cv = xy_to_int(xp, yp);
-                    int dup = 0;
-                    for (int t = 0; t < nseen; ++t) dup |= (seen[t] == cv);
-                    if (dup) continue;
-                    seen[nseen++] = cv;
-                    ev_dedup++;
+                    int dup = 0, dup4 = 0;
+                    for (int i = 0; i < nseen; ++i) dup |= (seen[i] == cv);
+                    for (int i = 0; i < nseen4; ++i) dup4 |= (seen4[i] == cv);
+                    if (!dup) { seen[nseen++] = cv; ev_dedup++; }
+                    if (d4) {   /* the GPU's rule: D3 against the candidates it evaluated, then D4 */
+                        if (dup4) continue;
+                        if (t >= 4 && lc_prev[qy[k] * aw + qx[k]] <= t - 5) continue;
+                        seen4[nseen4++] = cv;
+                    } else if (dup) continue;
+                    ev_d4++;
                     float d = dist_canon(a, b, C, ah, aw, bh, bw, ax, ay, xp, yp);
                     if (d < dbest) { xbest = xp; ybest = yp; dbest = d; }
                 }
@@ -364,18 +393,22 @@ int orc_patchmatch(const float *a, const float *b, uint32_t *ann, float *annd,
                         ev_ref++;
                         if (xp == xbest && yp == ybest) continue; /* D3: d == dbest, never accepted */
                         ev_dedup++;
+                        ev_d4++;
                         float d = dist_canon(a, b, C, ah, aw, bh, bw, ax, ay, xp, yp);
                         if (d + FLT_MIN < dbest) { xbest = xp; ybest = yp; dbest = d; }
                     }
                 }
                 ann[p] = xy_to_int(xbest, ybest);
                 annd[p] = dbest;
+                if (ann[p] != v0) lc[p] = (signed char)t;
             }
         }
     }
     free(prev);
+    free(lc);
+    free(lc_prev);
     free(rng);
-    if (stats) { stats[0] = ev_ref; stats[1] = ev_dedup; }
+    if (stats) { stats[0] = ev_ref; stats[1] = ev_dedup; stats[2] = ev_d4; }
     return 0;
 }
 

@@ -152,3 +152,23 @@ def test_golden_vectors():
         assert np.array_equal(annd.view(np.uint32), g[key + "_annd"].view(np.uint32)), key
     assert np.array_equal(oracle.xorwow_raw(0, 8), g["xorwow_seed0"])
     assert np.array_equal(oracle.xorwow_raw(699, 8), g["xorwow_seed699"])
+
+
+@pytest.mark.parametrize("Cn,ah,aw,bh,bw,rs", [(64, 40, 36, 37, 41, 9), (128, 31, 33, 33, 29, 6), (256, 24, 24, 24, 24, 4)])
+def test_d4_unchanged_source_skip_never_changes_the_field(Cn, ah, aw, bh, bw, rs):
+    """D4 only drops candidates that would be rejected again: NNF and distances are bit-identical with and without it,
+    at every iteration count, while the number of evaluated candidates drops."""
+    a = oracle.l2norm_hwc(synth.feature_volume(41, ah, aw, Cn, smooth=3))
+    b = oracle.l2norm_hwc(synth.feature_volume(42, bh, bw, Cn, smooth=3))
+    init = oracle.nnf_init(ah, aw, bh, bw)
+    for iters in (1, 2, 3, 10):
+        p = oracle.make_params(Cn, ah, aw, bh, bw, iters=iters, rs_max=rs)
+        ann1, annd1, st1 = oracle.patchmatch(a, b, init, p, d4=True)
+        ann0, annd0, st0 = oracle.patchmatch(a, b, init, p, d4=False)
+        assert np.array_equal(ann1, ann0) and np.array_equal(annd1.view(np.uint32), annd0.view(np.uint32))
+        assert st1[0] == st0[0] and st1[2] == st0[2] == st0[1]
+        assert st1[1] <= st0[1]
+        if iters == 1:
+            assert st1[1] == st0[1]  # nothing to remember in the first iteration
+        if iters == 10:
+            assert st1[1] < 0.8 * st0[1]
