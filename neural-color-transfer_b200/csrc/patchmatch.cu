@@ -359,8 +359,11 @@ __global__ void __launch_bounds__(PM_TPB, (C <= 128) ? PM_MINB_SMALL : 1) pm_ste
             const int xmin = max(xbest - mag, 0), xmax = min(xbest + mag + 1, bw);
             const int ymin = max(ybest - mag, 0), ymax = min(ybest + mag + 1, bh);
             const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
-            const int xp = xmin + (int)(__fmul_rn(u1, (float)(xmax - xmin))) % (xmax - xmin);
-            const int yp = ymin + (int)(__fmul_rn(u2, (float)(ymax - ymin))) % (ymax - ymin);
+            // (int)(u * w) % w with u in (0, 1]: the product is in [0, w], so the modulo only maps w to 0
+            const int wx = xmax - xmin, wy = ymax - ymin;
+            const int tx = (int)(__fmul_rn(u1, (float)wx)), ty = (int)(__fmul_rn(u2, (float)wy));
+            const int xp = xmin + (tx >= wx ? tx - wx : tx);
+            const int yp = ymin + (ty >= wy ? ty - wy : ty);
             n_ref++;
             if (xp == xbest && yp == ybest) continue;
             n_eval++;
@@ -414,6 +417,49 @@ __device__ __forceinline__ float hw_eval(const HWQuery<C> &q, const float *__res
     constexpr int NV = HWTraits<C>::NV;
     const unsigned valid = q.amask & patch_mask(bx, by, bw, bh);
     const float *b_base = b + ((size_t)by * bw + bx) * C + j * 4;
+    if (valid == 0x1FFu) {
+        // interior fast path (the common case): no per-pixel predicates, three row pointers and immediate offsets;
+        // exactly the same FMA sequence as the general path below
+        const float *rb[3] = {b_base - (ptrdiff_t)bw * C, b_base, b_base + (ptrdiff_t)bw * C};
+        float4 bv[9 * NV];
+#pragma unroll
+        for (int pi = 0; pi < 9; ++pi)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) bv[pi * NV + k] = ldg4(rb[pi / 3] + (pi % 3 - 1) * C + k * 64);
+        float acc0 = 0.f, acc1 = 0.f;
+        if (NV == 1) {
+            if (HWTraits<C>::A_IN_REGS) {
+#pragma unroll
+                for (int pi = 0; pi < 9; ++pi) {
+                    if (pi & 1) acc1 = fma4(q.a[pi], bv[pi], acc1);
+                    else acc0 = fma4(q.a[pi], bv[pi], acc0);
+                }
+            } else {
+                const float *ra[3] = {q.a_base - (ptrdiff_t)q.aw * C, q.a_base, q.a_base + (ptrdiff_t)q.aw * C};
+#pragma unroll
+                for (int pi = 0; pi < 9; ++pi) {
+                    const float4 av = ldg4(ra[pi / 3] + (pi % 3 - 1) * C);
+                    if (pi & 1) acc1 = fma4(av, bv[pi], acc1);
+                    else acc0 = fma4(av, bv[pi], acc0);
+                }
+            }
+        } else {
+            const float *ra[3] = {q.a_base - (ptrdiff_t)q.aw * C, q.a_base, q.a_base + (ptrdiff_t)q.aw * C};
+#pragma unroll
+            for (int pi = 0; pi < 9; ++pi) {
+                const float4 a0 = ldg4(ra[pi / 3] + (pi % 3 - 1) * C);
+                const float4 a1 = ldg4(ra[pi / 3] + (pi % 3 - 1) * C + 64);
+                acc0 = fma4(a0, bv[pi * NV], acc0);
+                acc1 = fma4(a1, bv[pi * NV + 1], acc1);
+            }
+        }
+        float acc = __fadd_rn(acc0, acc1);
+        acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 8));
+        acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 4));
+        acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 2));
+        acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 1));
+        return __fdiv_rn(-acc, 9.0f);
+    }
     float4 bv[9 * NV];
 #pragma unroll
     for (int pi = 0; pi < 9; ++pi) {
@@ -541,8 +587,11 @@ __global__ void __launch_bounds__(128, 4) pm_step_hw_kernel(const PMStep s)
             const int xmin = max(xbest - mag, 0), xmax = min(xbest + mag + 1, bw);
             const int ymin = max(ybest - mag, 0), ymax = min(ybest + mag + 1, bh);
             const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
-            const int xp = xmin + (int)(__fmul_rn(u1, (float)(xmax - xmin))) % (xmax - xmin);
-            const int yp = ymin + (int)(__fmul_rn(u2, (float)(ymax - ymin))) % (ymax - ymin);
+            // (int)(u * w) % w with u in (0, 1]: the product is in [0, w], so the modulo only maps w to 0
+            const int wx = xmax - xmin, wy = ymax - ymin;
+            const int tx = (int)(__fmul_rn(u1, (float)wx)), ty = (int)(__fmul_rn(u2, (float)wy));
+            const int xp = xmin + (tx >= wx ? tx - wx : tx);
+            const int yp = ymin + (ty >= wy ? ty - wy : ty);
             n_ref++;
             if (xp == xbest && yp == ybest) continue;
             n_eval++;
@@ -566,6 +615,428 @@ __global__ void __launch_bounds__(128, 4) pm_step_hw_kernel(const PMStep s)
     }
 }
 
+// ------------------------------------------------------------------ unified-loop step kernel (C = 64 ... 512)
+// One candidate loop per query: [initial entry (first step only)] + compacted propagation candidates + random-search
+// candidates, all through ONE inlined copy of the distance code.  Compared with the unrolled kernels above:
+//   * after D4 most queries have 0-2 propagation candidates per step, in different slots; unrolled code evaluates
+//     slot k of one half warp and slot k' of the other at different program counters (serialised), the compacted
+//     loop evaluates them together;
+//   * the kernel is ~4x smaller (one distance body instead of six);
+//   * interior patches (all nine pixels valid on both sides -- almost all of them) take a predicate-free path with
+//     three row pointers and immediate offsets.
+// The FMA / reduction sequence per distance is unchanged, so the result is bit-identical (oracle D2).
+// HALF = true : 16 lanes per query (C = 64: 1 float4 per lane and pixel, C = 128: 2)
+// HALF = false: 32 lanes per query (C = 256: 2 float4 per lane and pixel, C = 512: 4)
+template <int C, bool HALF>
+struct UTraits {
+    static constexpr int LANES = HALF ? 16 : 32;
+    static constexpr int NV = C / (4 * LANES);          // float4 per lane per pixel
+    static constexpr int STRIDE = 4 * LANES;            // floats between a lane's consecutive vectors
+    static constexpr bool A_IN_REGS = (C == 64) || (C == 256);
+};
+
+template <int C, bool HALF>
+struct UQuery {
+    using T = UTraits<C, HALF>;
+    float4 a[T::A_IN_REGS ? 9 * T::NV : 1];
+    const float *a_base;
+    int aw;
+    unsigned amask;
+};
+
+// canonical slot structure (oracle D2): 32 accumulator slots, slot = (vector index within the pixel row) mod 32 for
+// C >= 128, and (pixel parity) * 16 + vector index for C = 64; butterfly xor 16, 8, 4, 2, 1.
+//   HALF, C = 64 : a lane owns slots j (even pixels, acc0) and j + 16 (odd pixels, acc1)
+//   HALF, C = 128: a lane owns slots j (vector j, acc0) and j + 16 (vector j + 16, acc1)
+//   warp, C >= 256: a lane owns slot `lane` (vectors lane, lane + 32, ... in ascending order, one accumulator)
+template <int C, bool HALF>
+__device__ __forceinline__ void u_accumulate(float &acc0, float &acc1, int pi, const float4 *av, const float4 *bv)
+{
+    constexpr int NV = UTraits<C, HALF>::NV;
+    if (HALF) {
+        if (NV == 1) {
+            if (pi & 1) acc1 = fma4(av[0], bv[0], acc1);
+            else acc0 = fma4(av[0], bv[0], acc0);
+        } else {
+            acc0 = fma4(av[0], bv[0], acc0);
+            acc1 = fma4(av[1], bv[1], acc1);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc0 = fma4(av[k], bv[k], acc0);
+    }
+}
+
+template <int C, bool HALF>
+__device__ __forceinline__ float u_finish(float acc0, float acc1, unsigned mask, int n)
+{
+    float acc;
+    if (HALF) acc = __fadd_rn(acc0, acc1);  // == the xor-16 step of the 32-slot butterfly
+    else acc = __fadd_rn(acc0, __shfl_xor_sync(mask, acc0, 16));
+    acc = __fadd_rn(acc, __shfl_xor_sync(mask, acc, 8));
+    acc = __fadd_rn(acc, __shfl_xor_sync(mask, acc, 4));
+    acc = __fadd_rn(acc, __shfl_xor_sync(mask, acc, 2));
+    acc = __fadd_rn(acc, __shfl_xor_sync(mask, acc, 1));
+    return __fdiv_rn(-acc, (float)n);
+}
+
+template <int C, bool HALF>
+__device__ __forceinline__ float u_eval(const UQuery<C, HALF> &q, const float *__restrict__ b, int bx, int by, int bw, int bh, int j,
+                                        unsigned mask)
+{
+    using T = UTraits<C, HALF>;
+    constexpr int NV = T::NV, ST = T::STRIDE;
+    const unsigned valid = q.amask & patch_mask(bx, by, bw, bh);
+    const float *b_base = b + ((size_t)by * bw + bx) * C + j * 4;
+    float acc0 = 0.f, acc1 = 0.f;
+    if (valid == 0x1FFu) {
+        const float *rb[3] = {b_base - (ptrdiff_t)bw * C, b_base, b_base + (ptrdiff_t)bw * C};
+        const float *ra[3] = {q.a_base - (ptrdiff_t)q.aw * C, q.a_base, q.a_base + (ptrdiff_t)q.aw * C};
+        float4 bv[9 * NV];
+#pragma unroll
+        for (int pi = 0; pi < 9; ++pi)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) bv[pi * NV + k] = ldg4(rb[pi / 3] + (pi % 3 - 1) * C + k * ST);
+#pragma unroll
+        for (int pi = 0; pi < 9; ++pi) {
+            float4 av[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                if (T::A_IN_REGS) av[k] = q.a[pi * NV + k];
+                else av[k] = ldg4(ra[pi / 3] + (pi % 3 - 1) * C + k * ST);
+            }
+            u_accumulate<C, HALF>(acc0, acc1, pi, av, &bv[pi * NV]);
+        }
+        return u_finish<C, HALF>(acc0, acc1, mask, 9);
+    }
+    float4 bv[9 * NV];
+#pragma unroll
+    for (int pi = 0; pi < 9; ++pi) {
+        const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+        const bool ok = (valid >> pi) & 1u;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) v = ldg4(b_base + ((ptrdiff_t)dy * bw + dx) * C + k * ST);
+            bv[pi * NV + k] = v;
+        }
+    }
+#pragma unroll
+    for (int pi = 0; pi < 9; ++pi) {
+        const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+        if ((valid >> pi) & 1u) {
+            float4 av[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                if (T::A_IN_REGS) av[k] = q.a[pi * NV + k];
+                else av[k] = ldg4(q.a_base + ((ptrdiff_t)dy * q.aw + dx) * C + k * ST);
+            }
+            u_accumulate<C, HALF>(acc0, acc1, pi, av, &bv[pi * NV]);
+        }
+    }
+    return u_finish<C, HALF>(acc0, acc1, mask, __popc(valid));
+}
+
+template <int C, bool HALF>
+__global__ void __launch_bounds__(128, HALF ? 4 : 2) pm_step_u_kernel(const PMStep s)
+{
+    using T = UTraits<C, HALF>;
+    const int lane = threadIdx.x & 31;
+    const int j = HALF ? (lane & 15) : lane;
+    const unsigned mask = HALF ? ((lane >> 4) ? 0xffff0000u : 0x0000ffffu) : 0xffffffffu;
+    const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int qidx = HALF ? warp_global * 2 + (lane >> 4) : warp_global;
+    if (qidx >= s.nq_total) return;  // whole (half) warps leave together; the shuffles only name the own group
+    const int dsel = qidx >= s.nq0 ? 1 : 0;
+    const PMDir &D = s.d[dsel];
+    const int p = qidx - (dsel ? s.nq0 : 0);
+    const int aw = D.aw, ah = D.ah, bw = D.bw, bh = D.bh;
+    const int ax = p % aw, ay = p / aw;
+
+    const uint32_t v0 = D.nnf_in[p];
+    int xbest = int_to_x(v0), ybest = int_to_y(v0);
+    unsigned n_eval = 0, n_ref = 0;
+
+    // ---- propagation candidates L, R, U, D from the previous step's field: de-duplicated (D3), unchanged sources
+    //      skipped (D4), compacted into c[0 .. n)
+    const int jump = s.jump;
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    int n = 0;
+    {
+        const int qx[4] = {ax - jump, ax + jump, ax, ax};
+        const int qy[4] = {ay, ay, ay - jump, ay + jump};
+        const int sx[4] = {jump, -jump, 0, 0};
+        const int sy[4] = {0, 0, jump, -jump};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (qx[k] >= 0 && qx[k] < aw && qy[k] >= 0 && qy[k] < ah) {
+                const int qi = qy[k] * aw + qx[k];
+                const uint32_t vp = D.nnf_in[qi];
+                const int xp = int_to_x(vp) + sx[k], yp = int_to_y(vp) + sy[k];
+                if (yp >= 0 && yp < bh && xp >= 0 && xp < bw) {
+                    n_ref++;
+                    const uint32_t cv = xy_to_int(xp, yp);
+                    bool dup = (cv == v0) || (n > 0 && cv == c0) || (n > 1 && cv == c1) || (n > 2 && cv == c2);
+                    const bool stale = s.t >= 4 && (int)D.lc_in[qi] <= s.t - 5;
+                    if (!dup && !stale) {
+                        if (n == 0) c0 = cv;
+                        else if (n == 1) c1 = cv;
+                        else if (n == 2) c2 = cv;
+                        else c3 = cv;
+                        n++;
+                    }
+                }
+            }
+        }
+    }
+    const int n_first = s.first ? 1 : 0;
+    const int n_prop_end = n_first + n;
+    const int total = n_prop_end + (s.do_random ? D.n_mag : 0);
+
+    UQuery<C, HALF> q;
+    q.aw = aw;
+    q.amask = patch_mask(ax, ay, aw, ah);
+    q.a_base = D.a + ((size_t)ay * aw + ax) * C + j * 4;
+    if (T::A_IN_REGS && total > 0) {  // the query patch is only fetched when something will be compared against it
+#pragma unroll
+        for (int pi = 0; pi < 9; ++pi) {
+            const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+#pragma unroll
+            for (int k = 0; k < T::NV; ++k) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((q.amask >> pi) & 1u) v = ldg4(q.a_base + ((ptrdiff_t)dy * aw + dx) * C + k * T::STRIDE);
+                q.a[pi * T::NV + k] = v;
+            }
+        }
+    }
+    float dbest = s.first ? 0.f : D.nnd[p];
+    const float *u = D.rng + (size_t)ax * D.ndraws + (size_t)s.iter * 2 * D.n_mag;
+
+#pragma unroll 1
+    for (int i = 0; i < total; ++i) {
+        int cx, cy;
+        const bool is_rand = i >= n_prop_end;
+        if (!is_rand) {
+            const int k = i - n_first;
+            const uint32_t cv = (i < n_first) ? v0 : (k == 0 ? c0 : (k == 1 ? c1 : (k == 2 ? c2 : c3)));
+            cx = int_to_x(cv);
+            cy = int_to_y(cv);
+            if (i < n_first) n_ref++;
+        } else {
+            // random search around the current best (NCT/GeneralizedPatchMatch.cu:806-821); mag = rs_start / 2^m
+            const int m = i - n_prop_end;
+            const int mag = D.rs_start >> m;
+            const int xmin = max(xbest - mag, 0), xmax = min(xbest + mag + 1, bw);
+            const int ymin = max(ybest - mag, 0), ymax = min(ybest + mag + 1, bh);
+            const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
+            // (int)(u * w) % w with u in (0, 1]: the product is in [0, w], so the modulo only maps w to 0
+            const int wx = xmax - xmin, wy = ymax - ymin;
+            const int tx = (int)(__fmul_rn(u1, (float)wx)), ty = (int)(__fmul_rn(u2, (float)wy));
+            cx = xmin + (tx >= wx ? tx - wx : tx);
+            cy = ymin + (ty >= wy ? ty - wy : ty);
+            n_ref++;
+            if (cx == xbest && cy == ybest) continue;  // D3: d == dbest, never accepted
+        }
+        n_eval++;
+        const float d = u_eval<C, HALF>(q, D.b, cx, cy, bw, bh, j, mask);
+        const float dcmp = is_rand ? __fadd_rn(d, FLT_MIN) : d;
+        if (i < n_first || dcmp < dbest) {
+            dbest = d;
+            xbest = cx;
+            ybest = cy;
+        }
+    }
+
+    if (j == 0) {
+        const uint32_t vnew = xy_to_int(xbest, ybest);
+        D.nnf_out[p] = vnew;
+        D.lc_out[p] = vnew != v0 ? (int8_t)s.t : D.lc_in[p];
+        D.nnd[p] = dbest;
+        if (s.counters) {
+            atomicAdd(&s.counters[0], (unsigned long long)n_eval);
+            atomicAdd(&s.counters[1], (unsigned long long)n_ref);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ tiled step kernel (C = 64 ... 512)
+// After D4 the late steps are sparse (about one candidate per query), and pm_step_u_kernel becomes bound by the
+// LIFETIME of its short warps: field entry -> four neighbour entries -> patch rows is a chain of dependent global
+// loads (~2.5 us) paid by every (half) warp for one query (profiles/r1_pm_step_ncu.md).  Here a warp owns a TILE of
+// up to 32 consecutive queries:
+//   phase 1, lane = query: the field / last-change reads are coalesced, the candidate lists are built by 32 lanes at
+//            once, queries with nothing to evaluate are finished right there (coalesced stores);
+//   phase 2, 16 (or 32) lanes = one query: the queries that do have work are walked one after the other by the two
+//            half warps (even / odd ranked work items), so the dependent-load chain is paid once per tile.
+// The per-query arithmetic is pm_step_u_kernel's, bit for bit.
+struct TQueryState {
+    uint32_t v0, c0, c1, c2, c3;
+    int qidx;
+    int n;        // propagation candidates
+    float dbest;
+};
+
+template <int C, bool HALF>
+__global__ void __launch_bounds__(128, HALF ? 4 : 2) pm_step_t_kernel(const PMStep s, const int tile)
+{
+    using T = UTraits<C, HALF>;
+    __shared__ TQueryState st_all[4][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    TQueryState *st = st_all[wib];
+    const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int q_first = warp_global * tile;
+    if (q_first >= s.nq_total) return;  // whole warps leave together
+    const int jump = s.jump;
+    const int n_first = s.first ? 1 : 0;
+    unsigned n_eval = 0, n_ref = 0;
+
+    // ---- phase 1: one lane per query
+    bool has_work = false;
+    {
+        const int qidx = q_first + lane;
+        if (lane < tile && qidx < s.nq_total) {
+            const int dsel = qidx >= s.nq0 ? 1 : 0;
+            const PMDir &D = s.d[dsel];
+            const int p = qidx - (dsel ? s.nq0 : 0);
+            const int aw = D.aw, ah = D.ah, bw = D.bw, bh = D.bh;
+            const int ax = p % aw, ay = p / aw;
+            const uint32_t v0 = D.nnf_in[p];
+            uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            int n = 0;
+            const int qx[4] = {ax - jump, ax + jump, ax, ax};
+            const int qy[4] = {ay, ay, ay - jump, ay + jump};
+            const int sx[4] = {jump, -jump, 0, 0};
+            const int sy[4] = {0, 0, jump, -jump};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (qx[k] >= 0 && qx[k] < aw && qy[k] >= 0 && qy[k] < ah) {
+                    const int qi = qy[k] * aw + qx[k];
+                    const uint32_t vp = D.nnf_in[qi];
+                    const int xp = int_to_x(vp) + sx[k], yp = int_to_y(vp) + sy[k];
+                    if (yp >= 0 && yp < bh && xp >= 0 && xp < bw) {
+                        n_ref++;
+                        const uint32_t cv = xy_to_int(xp, yp);
+                        const bool dup = (cv == v0) || (n > 0 && cv == c0) || (n > 1 && cv == c1) || (n > 2 && cv == c2);
+                        const bool stale = s.t >= 4 && (int)D.lc_in[qi] <= s.t - 5;  // D4
+                        if (!dup && !stale) {
+                            if (n == 0) c0 = cv;
+                            else if (n == 1) c1 = cv;
+                            else if (n == 2) c2 = cv;
+                            else c3 = cv;
+                            n++;
+                        }
+                    }
+                }
+            }
+            const int total = n_first + n + (s.do_random ? D.n_mag : 0);
+            if (total == 0) {  // nothing to compare: the entry stays
+                D.nnf_out[p] = v0;
+                D.lc_out[p] = D.lc_in[p];
+            } else {
+                has_work = true;
+                st[lane].v0 = v0; st[lane].c0 = c0; st[lane].c1 = c1; st[lane].c2 = c2; st[lane].c3 = c3;
+                st[lane].qidx = qidx;
+                st[lane].n = n;
+                st[lane].dbest = s.first ? 0.f : D.nnd[p];
+            }
+        }
+    }
+    const unsigned work = __ballot_sync(0xffffffffu, has_work);
+    __syncwarp();
+
+    // ---- phase 2: one group of 16 / 32 lanes per query with work
+    const int grp = HALF ? (lane >> 4) : 0;
+    const int j = HALF ? (lane & 15) : lane;
+    const unsigned mask = HALF ? (grp ? 0xffff0000u : 0x0000ffffu) : 0xffffffffu;
+    // even-ranked work items -> lanes 0-15, odd-ranked -> lanes 16-31: both groups run the SAME loop (converged), each on
+    // its own item
+    const int nwork = __popc(work);
+#pragma unroll 1
+    for (int r = grp; r < nwork; r += (HALF ? 2 : 1)) {
+        const int src = (int)__fns(work, 0, r + 1);
+        const TQueryState q0 = st[src];
+        const int qidx = q0.qidx;
+        const int dsel = qidx >= s.nq0 ? 1 : 0;
+        const PMDir &D = s.d[dsel];
+        const int p = qidx - (dsel ? s.nq0 : 0);
+        const int aw = D.aw, ah = D.ah, bw = D.bw, bh = D.bh;
+        const int ax = p % aw, ay = p / aw;
+        const uint32_t v0 = q0.v0;
+        int xbest = int_to_x(v0), ybest = int_to_y(v0);
+        float dbest = q0.dbest;
+        const int n_prop_end = n_first + q0.n;
+        const int total = n_prop_end + (s.do_random ? D.n_mag : 0);
+
+        UQuery<C, HALF> q;
+        q.aw = aw;
+        q.amask = patch_mask(ax, ay, aw, ah);
+        q.a_base = D.a + ((size_t)ay * aw + ax) * C + j * 4;
+        if (T::A_IN_REGS) {
+#pragma unroll
+            for (int pi = 0; pi < 9; ++pi) {
+                const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+#pragma unroll
+                for (int k = 0; k < T::NV; ++k) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if ((q.amask >> pi) & 1u) v = ldg4(q.a_base + ((ptrdiff_t)dy * aw + dx) * C + k * T::STRIDE);
+                    q.a[pi * T::NV + k] = v;
+                }
+            }
+        }
+        const float *u = D.rng + (size_t)ax * D.ndraws + (size_t)s.iter * 2 * D.n_mag;
+#pragma unroll 1
+        for (int i = 0; i < total; ++i) {
+            int cx, cy;
+            const bool is_rand = i >= n_prop_end;
+            if (!is_rand) {
+                const int k = i - n_first;
+                const uint32_t cv = (i < n_first) ? v0 : (k == 0 ? q0.c0 : (k == 1 ? q0.c1 : (k == 2 ? q0.c2 : q0.c3)));
+                cx = int_to_x(cv);
+                cy = int_to_y(cv);
+                if (i < n_first) n_ref += (j == 0);
+            } else {
+                const int m = i - n_prop_end;
+                const int mag = D.rs_start >> m;
+                const int xmin = max(xbest - mag, 0), xmax = min(xbest + mag + 1, bw);
+                const int ymin = max(ybest - mag, 0), ymax = min(ybest + mag + 1, bh);
+                const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
+                const int wx = xmax - xmin, wy = ymax - ymin;
+                const int tx = (int)(__fmul_rn(u1, (float)wx)), ty = (int)(__fmul_rn(u2, (float)wy));
+                cx = xmin + (tx >= wx ? tx - wx : tx);
+                cy = ymin + (ty >= wy ? ty - wy : ty);
+                n_ref += (j == 0);
+                if (cx == xbest && cy == ybest) continue;  // D3
+            }
+            n_eval += (j == 0);
+            const float d = u_eval<C, HALF>(q, D.b, cx, cy, bw, bh, j, mask);
+            const float dcmp = is_rand ? __fadd_rn(d, FLT_MIN) : d;
+            if (i < n_first || dcmp < dbest) {
+                dbest = d;
+                xbest = cx;
+                ybest = cy;
+            }
+        }
+        if (j == 0) {
+            const uint32_t vnew = xy_to_int(xbest, ybest);
+            D.nnf_out[p] = vnew;
+            D.lc_out[p] = vnew != v0 ? (int8_t)s.t : D.lc_in[p];
+            D.nnd[p] = dbest;
+        }
+    }
+    if (s.counters && (n_eval | n_ref)) {
+        atomicAdd(&s.counters[0], (unsigned long long)n_eval);
+        atomicAdd(&s.counters[1], (unsigned long long)n_ref);
+    }
+}
+
+// queries per warp: 32 when that still leaves >= ~16 warps per SM, otherwise fewer (the coarse levels have few queries)
+static int pm_tile_size(int nq_total, int num_sms)
+{
+    int tile = 32;
+    while (tile > 2 && nq_total / tile < num_sms * 16) tile >>= 1;
+    return tile;
+}
+
 template <int C>
 struct UseHalfWarp { static constexpr bool value = (C == 64 || C == 128); };
 
@@ -573,6 +1044,18 @@ template <int C, bool HW = UseHalfWarp<C>::value>
 struct StepLauncher {
     static void go(const PMStep &s, cudaStream_t st)
     {
+        static const char *legacy = getenv("NCT_PM_LEGACY");  // A/B switch for profiling
+        if (C >= 256 && !legacy) {
+            const int tile = pm_tile_size(s.nq_total, 148);
+            const int blocks = nct_div_up(nct_div_up(s.nq_total, tile), 4);  // 4 warps per block, `tile` queries per warp
+            pm_step_t_kernel<(C >= 256 ? C : 256), false><<<blocks, 128, 0, st>>>(s, tile);
+            return;
+        }
+        if (C >= 256 && legacy[0] == 'u') {
+            const int blocks = nct_div_up(s.nq_total, 4);  // 128 threads = 4 warps = 4 queries
+            pm_step_u_kernel<(C >= 256 ? C : 256), false><<<blocks, 128, 0, st>>>(s);
+            return;
+        }
         const int blocks = nct_div_up(s.nq_total, PM_TPB / 32);
         pm_step_kernel<C><<<blocks, PM_TPB, 0, st>>>(s);
     }
@@ -581,13 +1064,20 @@ template <int C>
 struct StepLauncher<C, true> {
     static void go(const PMStep &s, cudaStream_t st)
     {
-        static const bool legacy = getenv("NCT_PM_LEGACY") != nullptr;  // A/B switch for profiling
-        if (legacy) {
+        static const char *legacy = getenv("NCT_PM_LEGACY");  // A/B switch for profiling: "1" warp kernel, "hw" unrolled half warp
+        if (legacy && legacy[0] == '1') {
             const int blocks = nct_div_up(s.nq_total, PM_TPB / 32);
             pm_step_kernel<C><<<blocks, PM_TPB, 0, st>>>(s);
-        } else {
+        } else if (legacy && legacy[0] == 'h') {
             const int blocks = nct_div_up(s.nq_total, 8);  // 128 threads = 4 warps = 8 queries
             pm_step_hw_kernel<C><<<blocks, 128, 0, st>>>(s);
+        } else if (legacy) {
+            const int blocks = nct_div_up(s.nq_total, 8);
+            pm_step_u_kernel<C, true><<<blocks, 128, 0, st>>>(s);
+        } else {
+            const int tile = pm_tile_size(s.nq_total, 148);
+            const int blocks = nct_div_up(nct_div_up(s.nq_total, tile), 4);
+            pm_step_t_kernel<C, true><<<blocks, 128, 0, st>>>(s, tile);
         }
     }
 };
