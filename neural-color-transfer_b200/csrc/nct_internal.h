@@ -45,6 +45,10 @@ struct nct_ctx {
     std::map<unsigned long long, std::vector<double>> pow_host;  // keyed by the exponent's bit pattern
     std::vector<double> knnw_host;
 
+    // WLS warm start (set by the pair orchestrator around its per-level solves; off for direct nct_solve_wls callers)
+    int wls_warm = 0;
+    int wls_prev_n = 0;
+
     // opaque sub-module states (owned, freed in nct_destroy)
     struct VggState *vgg = nullptr;
     struct PipeState *pipe = nullptr;

@@ -175,7 +175,12 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
         STEP(nct_upsample_coefficients(ctx, a_lvl, b_lvl, ah, aw, cntLabFull, ch, cw, a_full, b_full, rough));
         if (ah == ch && aw == cw) lam = lam * 4;
         { NctStageTimer t(ctx, ST_WLS);
-        STEP(nct_solve_wls(ctx, a_full, b_full, rough, cntLabFull, ch, cw, lam, cfg.wls_alpha, cfg.wls_rel_tol, 0, nullptr, nullptr)); }
+        static const bool warm = !(getenv("NCT_WLS_WARM") && atoi(getenv("NCT_WLS_WARM")) == 0);  // default on
+        ctx->wls_warm = warm ? 1 : 0;
+        if (l == 0) ctx->wls_prev_n = 0;  // never carry a solution from one pair into the next
+        rc = nct_solve_wls(ctx, a_full, b_full, rough, cntLabFull, ch, cw, lam, cfg.wls_alpha, cfg.wls_rel_tol, 0, nullptr, nullptr);
+        ctx->wls_warm = 0;
+        if (rc) return rc; }
         STEP(nct_apply_coefficients(ctx, cntLabFull, a_full, b_full, ch, cw, refine, nullptr));
         result = refine;
         if (l >= cfg.stop_after_level) break;

@@ -46,6 +46,8 @@ struct MgHierarchy {
     MgLevel lv[MAX_LEVELS];
     int nlevels;
     int bottom;  // first level handled by the single-block kernel
+    int mid;     // first level handled by the cluster kernel (== bottom: no such level)
+    int bottom_smem_bytes;  // > 0: the bottom levels run out of shared memory (mg_bottom_smem_kernel)
 };
 
 // the FP64 operator of the outer CG
@@ -54,31 +56,34 @@ struct FineOp {
     const double *rough, *wx, *wy;
 };
 
-__device__ __forceinline__ void ld6(const float *__restrict__ v, int i, float (&o)[6])
+// Vector layout: three PLANES of 2-component records, plane k holding components (2k, 2k+1) of all n nodes
+// (v[(k * n + i) * 2 + c]).  A warp's load of one plane is one contiguous 256 B (float2) / 512 B (double2) segment;
+// the [n][6] records of the first version made every load instruction touch three times as many cache lines.
+__device__ __forceinline__ void ld6(const float *__restrict__ v, int i, int n, float (&o)[6])
 {
-    const float2 *q = reinterpret_cast<const float2 *>(v + (size_t)i * 6);
-    const float2 t0 = q[0], t1 = q[1], t2 = q[2];
+    const float2 *q = reinterpret_cast<const float2 *>(v);
+    const float2 t0 = q[i], t1 = q[(size_t)n + i], t2 = q[2 * (size_t)n + i];
     o[0] = t0.x; o[1] = t0.y; o[2] = t1.x; o[3] = t1.y; o[4] = t2.x; o[5] = t2.y;
 }
-__device__ __forceinline__ void st6(float *__restrict__ v, int i, const float (&o)[6])
+__device__ __forceinline__ void st6(float *__restrict__ v, int i, int n, const float (&o)[6])
 {
-    float2 *q = reinterpret_cast<float2 *>(v + (size_t)i * 6);
-    q[0] = make_float2(o[0], o[1]);
-    q[1] = make_float2(o[2], o[3]);
-    q[2] = make_float2(o[4], o[5]);
+    float2 *q = reinterpret_cast<float2 *>(v);
+    q[i] = make_float2(o[0], o[1]);
+    q[(size_t)n + i] = make_float2(o[2], o[3]);
+    q[2 * (size_t)n + i] = make_float2(o[4], o[5]);
 }
-__device__ __forceinline__ void ld6(const double *__restrict__ v, int i, double (&o)[6])
+__device__ __forceinline__ void ld6(const double *__restrict__ v, int i, int n, double (&o)[6])
 {
-    const double2 *q = reinterpret_cast<const double2 *>(v + (size_t)i * 6);
-    const double2 t0 = q[0], t1 = q[1], t2 = q[2];
+    const double2 *q = reinterpret_cast<const double2 *>(v);
+    const double2 t0 = q[i], t1 = q[(size_t)n + i], t2 = q[2 * (size_t)n + i];
     o[0] = t0.x; o[1] = t0.y; o[2] = t1.x; o[3] = t1.y; o[4] = t2.x; o[5] = t2.y;
 }
-__device__ __forceinline__ void st6(double *__restrict__ v, int i, const double (&o)[6])
+__device__ __forceinline__ void st6(double *__restrict__ v, int i, int n, const double (&o)[6])
 {
-    double2 *q = reinterpret_cast<double2 *>(v + (size_t)i * 6);
-    q[0] = make_double2(o[0], o[1]);
-    q[1] = make_double2(o[2], o[3]);
-    q[2] = make_double2(o[4], o[5]);
+    double2 *q = reinterpret_cast<double2 *>(v);
+    q[i] = make_double2(o[0], o[1]);
+    q[(size_t)n + i] = make_double2(o[2], o[3]);
+    q[2 * (size_t)n + i] = make_double2(o[4], o[5]);
 }
 
 // sum_e w_e * X_j over the 4 neighbours, X given by a functor
@@ -127,9 +132,9 @@ __device__ __forceinline__ double nbr_sum64(const FineOp &F, int i, GetX getx, d
 __device__ __forceinline__ void op_presmooth2(const MgLevel &L, int i)
 {
     T bi[6], s[6], o[6];
-    ld6(L.b, i, bi);
+    ld6(L.b, i, L.n, bi);
     nbr_sum(L, i, [&](int j, T (&xj)[6]) {
-        ld6(L.b, j, xj);
+        ld6(L.b, j, L.n, xj);
         const T f = OMEGA * L.invd[j];
 #pragma unroll
         for (int k = 0; k < 6; ++k) xj[k] *= f;
@@ -137,20 +142,20 @@ __device__ __forceinline__ void op_presmooth2(const MgLevel &L, int i)
     const T f = OMEGA * L.invd[i];
 #pragma unroll
     for (int k = 0; k < 6; ++k) o[k] = f * bi[k] + f * ((T(1) - OMEGA) * bi[k] + s[k]);
-    st6(L.x, i, o);
+    st6(L.x, i, L.n, o);
 }
 
 // t = b - M x
 __device__ __forceinline__ void op_residual_to_t(const MgLevel &L, int i)
 {
     T bi[6], xi[6], s[6], r[6];
-    ld6(L.b, i, bi);
-    ld6(L.x, i, xi);
-    nbr_sum(L, i, [&](int j, T (&xj)[6]) { ld6(L.x, j, xj); }, s);
+    ld6(L.b, i, L.n, bi);
+    ld6(L.x, i, L.n, xi);
+    nbr_sum(L, i, [&](int j, T (&xj)[6]) { ld6(L.x, j, L.n, xj); }, s);
     const T d = T(1) / L.invd[i];
 #pragma unroll
     for (int k = 0; k < 6; ++k) r[k] = bi[k] - d * xi[k] + s[k];
-    st6(L.t, i, r);
+    st6(L.t, i, L.n, r);
 }
 
 // interpolation weight of fine index x towards coarse index J (cell-centred linear interpolation; at the border the
@@ -177,12 +182,12 @@ __device__ __forceinline__ void op_restrict(const MgLevel &F, const MgLevel &Cc,
             const T w = wy * pw(x, J, Cc.W);
             if (w == T(0)) continue;
             T r[6];
-            ld6(F.t, y * F.W + x, r);
+            ld6(F.t, y * F.W + x, F.n, r);
 #pragma unroll
             for (int k = 0; k < 6; ++k) acc[k] += w * r[k];
         }
     }
-    st6(Cc.b, c, acc);
+    st6(Cc.b, c, Cc.n, acc);
 }
 
 // (P xc) at fine node j
@@ -192,10 +197,10 @@ __device__ __forceinline__ void prolong_at(const MgLevel &F, const MgLevel &Cc, 
     const int Jp = x >> 1, Ip = y >> 1;
     const int Jn = min(max(Jp + ((x & 1) ? 1 : -1), 0), Cc.W - 1), In = min(max(Ip + ((y & 1) ? 1 : -1), 0), Cc.H - 1);
     T c00[6], c01[6], c10[6], c11[6];
-    ld6(Cc.x, Ip * Cc.W + Jp, c00);
-    ld6(Cc.x, Ip * Cc.W + Jn, c01);
-    ld6(Cc.x, In * Cc.W + Jp, c10);
-    ld6(Cc.x, In * Cc.W + Jn, c11);
+    ld6(Cc.x, Ip * Cc.W + Jp, Cc.n, c00);
+    ld6(Cc.x, Ip * Cc.W + Jn, Cc.n, c01);
+    ld6(Cc.x, In * Cc.W + Jp, Cc.n, c10);
+    ld6(Cc.x, In * Cc.W + Jn, Cc.n, c11);
 #pragma unroll
     for (int k = 0; k < 6; ++k) o[k] = T(0.5625) * c00[k] + T(0.1875) * c01[k] + T(0.1875) * c10[k] + T(0.0625) * c11[k];
 }
@@ -205,32 +210,32 @@ __device__ __forceinline__ void op_prolong_smooth(const MgLevel &F, const MgLeve
 {
     auto gety = [&](int j, T (&yj)[6]) {
         T pc[6];
-        ld6(F.x, j, yj);
+        ld6(F.x, j, F.n, yj);
         prolong_at(F, Cc, j, pc);
 #pragma unroll
         for (int k = 0; k < 6; ++k) yj[k] += pc[k];
     };
     T yi[6], bi[6], s[6], o[6];
     gety(i, yi);
-    ld6(F.b, i, bi);
+    ld6(F.b, i, F.n, bi);
     nbr_sum(F, i, gety, s);
     const T invd = F.invd[i], d = T(1) / invd;
 #pragma unroll
     for (int k = 0; k < 6; ++k) o[k] = yi[k] + OMEGA * invd * (bi[k] - d * yi[k] + s[k]);
-    st6(F.t, i, o);
+    st6(F.t, i, F.n, o);
 }
 
 // one damped-Jacobi sweep t -> x; leaves b_i and the new x_i in registers for the fused r.z
 __device__ __forceinline__ void op_smooth_t_to_x(const MgLevel &L, int i, T (&bi)[6], T (&o)[6])
 {
     T ti[6], s[6];
-    ld6(L.t, i, ti);
-    ld6(L.b, i, bi);
-    nbr_sum(L, i, [&](int j, T (&xj)[6]) { ld6(L.t, j, xj); }, s);
+    ld6(L.t, i, L.n, ti);
+    ld6(L.b, i, L.n, bi);
+    nbr_sum(L, i, [&](int j, T (&xj)[6]) { ld6(L.t, j, L.n, xj); }, s);
     const T invd = L.invd[i], d = T(1) / invd;
 #pragma unroll
     for (int k = 0; k < 6; ++k) o[k] = ti[k] + OMEGA * invd * (bi[k] - d * ti[k] + s[k]);
-    st6(L.x, i, o);
+    st6(L.x, i, L.n, o);
 }
 
 // ---- deterministic reductions (block tree + "last block done")
@@ -343,38 +348,38 @@ __global__ void __launch_bounds__(TPB) mg_smooth_rz_kernel(MgLevel L, PcgScalars
 }
 
 // the whole bottom of the V-cycle (levels h.bottom .. nlevels-1, each <= 1024 nodes) in one block
-__global__ void __launch_bounds__(1024) mg_bottom_kernel(MgHierarchy h)
+__device__ __forceinline__ void bottom_body(const MgLevel *lv, int bottom, int nlevels)
 {
-    const int last = h.nlevels - 1;
-    for (int k = h.bottom; k < last; ++k) {
-        const MgLevel &L = h.lv[k];
+    const int last = nlevels - 1;
+    for (int k = bottom; k < last; ++k) {
+        const MgLevel &L = lv[k];
         for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_presmooth2(L, i);
         __syncthreads();
         for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_residual_to_t(L, i);
         __syncthreads();
-        const MgLevel &Cc = h.lv[k + 1];
+        const MgLevel &Cc = lv[k + 1];
         for (int c = threadIdx.x; c < Cc.n; c += blockDim.x) op_restrict(L, Cc, c);
         __syncthreads();
     }
     {   // coarsest level: a single node (exact) or a handful (Jacobi sweeps)
-        const MgLevel &L = h.lv[last];
+        const MgLevel &L = lv[last];
         if (L.n == 1) {
             if (threadIdx.x == 0) {
                 T b[6], o[6];
-                ld6(L.b, 0, b);
+                ld6(L.b, 0, L.n, b);
                 const T invd = L.invd[0];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) o[k] = b[k] * invd;
-                st6(L.x, 0, o);
+                st6(L.x, 0, L.n, o);
             }
         } else {
             for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_presmooth2(L, i);
         }
         __syncthreads();
     }
-    for (int k = last - 1; k >= h.bottom; --k) {
-        const MgLevel &L = h.lv[k];
-        const MgLevel &Cc = h.lv[k + 1];
+    for (int k = last - 1; k >= bottom; --k) {
+        const MgLevel &L = lv[k];
+        const MgLevel &Cc = lv[k + 1];
         for (int i = threadIdx.x; i < L.n; i += blockDim.x) op_prolong_smooth(L, Cc, i);
         __syncthreads();
         for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
@@ -382,6 +387,116 @@ __global__ void __launch_bounds__(1024) mg_bottom_kernel(MgHierarchy h)
             op_smooth_t_to_x(L, i, b, o);
         }
         __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) mg_bottom_kernel(MgHierarchy h) { bottom_body(h.lv, h.bottom, h.nlevels); }
+
+// The same bottom of the V-cycle with every vector and coefficient of its levels staged in SHARED memory: a sweep
+// over <= 2k nodes is then ~0.1 us instead of the ~1.2 us an L2 round trip per sweep costs (profiles/r1_wls_ncu.md:
+// the global-memory version spends 36 us on ~30 dependent sweeps).  Layout per level: x, b [n][6 planar], invd, wx, wy
+// [n]; one scratch vector t sized for the largest level.  Only b of the first level comes in and x goes out.
+__global__ void __launch_bounds__(1024) mg_bottom_smem_kernel(MgHierarchy h)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ MgLevel lv[MAX_LEVELS];
+    T *sp = reinterpret_cast<T *>(smem_raw);
+    if (threadIdx.x == 0) {
+        T *tbuf = sp;
+        T *q = sp + (size_t)h.lv[h.bottom].n * 6;
+        for (int k = h.bottom; k < h.nlevels; ++k) {
+            MgLevel L = h.lv[k];
+            const int n2 = (L.n + 1) & ~1;  // keep every array 8-byte aligned
+            L.x = q; q += (size_t)n2 * 6;
+            L.b = q; q += (size_t)n2 * 6;
+            L.invd = q; q += n2;
+            L.wx = q; q += n2;
+            L.wy = q; q += n2;
+            L.t = tbuf;
+            L.rsum = nullptr;  // only the set-up kernels read it
+            lv[k] = L;
+        }
+    }
+    __syncthreads();
+    for (int k = h.bottom; k < h.nlevels; ++k) {
+        const MgLevel &G = h.lv[k];
+        const MgLevel &S = lv[k];
+        T *sinvd = S.invd, *swx = const_cast<T *>(S.wx), *swy = const_cast<T *>(S.wy);
+        for (int i = threadIdx.x; i < G.n; i += blockDim.x) {
+            sinvd[i] = G.invd[i];
+            swx[i] = G.wx[i];
+            swy[i] = G.wy[i];
+        }
+    }
+    {
+        const MgLevel &G = h.lv[h.bottom];
+        const MgLevel &S = lv[h.bottom];
+        for (int i = threadIdx.x; i < G.n; i += blockDim.x) {
+            T v[6];
+            ld6(G.b, i, G.n, v);
+            st6(S.b, i, S.n, v);
+        }
+    }
+    __syncthreads();
+    bottom_body(lv, h.bottom, h.nlevels);
+    {
+        const MgLevel &G = h.lv[h.bottom];
+        const MgLevel &S = lv[h.bottom];
+        for (int i = threadIdx.x; i < G.n; i += blockDim.x) {
+            T v[6];
+            ld6(S.x, i, S.n, v);
+            st6(G.x, i, G.n, v);
+        }
+    }
+}
+
+// dynamic shared memory mg_bottom_smem_kernel needs when its first level is `bottom`
+static size_t bottom_smem_bytes(const MgHierarchy &h, int bottom)
+{
+    size_t floats = (size_t)h.lv[bottom].n * 6;
+    for (int k = bottom; k < h.nlevels; ++k) {
+        const size_t n2 = ((size_t)h.lv[k].n + 1) & ~(size_t)1;
+        floats += n2 * 15;
+    }
+    return floats * sizeof(T);
+}
+
+// Levels h.mid .. nlevels-1 (each <= ~32k nodes) in ONE launch by a cluster of 8 thread blocks: the sweeps of these
+// levels are a few microseconds of work each, so as separate launches (5 per level and cycle) they cost more in launch
+// latency than in execution (profiles/r1_wls_ncu.md).  barrier.cluster (release / acquire at cluster scope, ~0.2 us)
+// orders the global-memory traffic between the sweeps; the <= 1024-node levels run in block 0 alone.
+constexpr int MID_CTAS = 8, MID_TPB = 1024;
+__global__ void __cluster_dims__(MID_CTAS, 1, 1) __launch_bounds__(MID_TPB) mg_mid_kernel(MgHierarchy h, int mid)
+{
+    unsigned rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int tid = (int)rank * MID_TPB + threadIdx.x, nthreads = MID_CTAS * MID_TPB;
+    auto cluster_sync = []() {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                     "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    };
+    for (int k = mid; k < h.bottom; ++k) {
+        const MgLevel &L = h.lv[k];
+        for (int i = tid; i < L.n; i += nthreads) op_presmooth2(L, i);
+        cluster_sync();
+        for (int i = tid; i < L.n; i += nthreads) op_residual_to_t(L, i);
+        cluster_sync();
+        const MgLevel &Cc = h.lv[k + 1];
+        for (int c = tid; c < Cc.n; c += nthreads) op_restrict(L, Cc, c);
+        cluster_sync();
+    }
+    if (rank == 0) bottom_body(h.lv, h.bottom, h.nlevels);
+    cluster_sync();
+    for (int k = h.bottom - 1; k >= mid; --k) {
+        const MgLevel &L = h.lv[k];
+        const MgLevel &Cc = h.lv[k + 1];
+        for (int i = tid; i < L.n; i += nthreads) op_prolong_smooth(L, Cc, i);
+        cluster_sync();
+        for (int i = tid; i < L.n; i += nthreads) {
+            T b[6], o[6];
+            op_smooth_t_to_x(L, i, b, o);
+        }
+        cluster_sync();
     }
 }
 
@@ -455,22 +570,24 @@ __global__ void pack6_kernel(const double *__restrict__ a, const double *__restr
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double o[6] = {a[(size_t)i * 3], a[(size_t)i * 3 + 1], a[(size_t)i * 3 + 2], b[(size_t)i * 3], b[(size_t)i * 3 + 1], b[(size_t)i * 3 + 2]};
-    st6(x, i, o);
+    st6(x, i, n, o);
 }
 __global__ void unpack6_kernel(const double *__restrict__ x, int n, double *__restrict__ a, double *__restrict__ b)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double o[6];
-    ld6(x, i, o);
+    ld6(x, i, n, o);
     a[(size_t)i * 3] = o[0]; a[(size_t)i * 3 + 1] = o[1]; a[(size_t)i * 3 + 2] = o[2];
     b[(size_t)i * 3] = o[3]; b[(size_t)i * 3 + 1] = o[4]; b[(size_t)i * 3 + 2] = o[5];
 }
 
 // ---- CG (FP64, 6 right-hand sides)
 // r = W x0 - M x0 ; r32 = (float) r -> level-0 right-hand side of the preconditioner ; rr, bb
-__global__ void __launch_bounds__(TPB) pcg_init_kernel(FineOp F, const double *__restrict__ x, double *__restrict__ r, T *__restrict__ r32,
-                                                       PcgScalars *sc, double *partials, unsigned *counter)
+// (xrhs = x0 supplies the right-hand side W x0; x is the initial guess -- x0 itself, or the previous level's solution)
+__global__ void __launch_bounds__(TPB) pcg_init_kernel(FineOp F, const double *__restrict__ x, const double *__restrict__ xrhs,
+                                                       double *__restrict__ r, T *__restrict__ r32, PcgScalars *sc, double *partials,
+                                                       unsigned *counter)
 {
     __shared__ double smem[12 * TPB / 32];
     const int i = blockIdx.x * TPB + threadIdx.x;
@@ -478,21 +595,22 @@ __global__ void __launch_bounds__(TPB) pcg_init_kernel(FineOp F, const double *_
 #pragma unroll
     for (int k = 0; k < 12; ++k) dots[k] = 0.0;
     if (i < F.n) {
-        double xi[6], s[6], ri[6];
+        double xi[6], x0i[6], s[6], ri[6];
         T rf[6];
-        ld6(x, i, xi);
-        const double d = nbr_sum64(F, i, [&](int j, double (&xj)[6]) { ld6(x, j, xj); }, s);
+        ld6(x, i, F.n, xi);
+        ld6(xrhs, i, F.n, x0i);
+        const double d = nbr_sum64(F, i, [&](int j, double (&xj)[6]) { ld6(x, j, F.n, xj); }, s);
         const double rg = F.rough[i];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            const double rhs = rg * xi[k];
+            const double rhs = rg * x0i[k];
             ri[k] = rhs - d * xi[k] + s[k];
             rf[k] = (T)ri[k];
             dots[k] = ri[k] * ri[k];
             dots[6 + k] = rhs * rhs;
         }
-        st6(r, i, ri);
-        st6(r32, i, rf);
+        st6(r, i, F.n, ri);
+        st6(r32, i, F.n, rf);
     }
     if (grid_reduce<12>(dots, partials, counter, smem)) {
         for (int k = 0; k < 6; ++k) {
@@ -521,22 +639,22 @@ __global__ void __launch_bounds__(TPB) pcg_spmv_kernel(FineOp F, const T *__rest
     auto getp = [&](int j, double (&o)[6]) {
         T zj[6];
         double pj[6];
-        ld6(z, j, zj);
-        ld6(pold, j, pj);
+        ld6(z, j, F.n, zj);
+        ld6(pold, j, F.n, pj);
 #pragma unroll
         for (int k = 0; k < 6; ++k) o[k] = (double)zj[k] + beta[k] * pj[k];
     };
     if (i < F.n) {
         double pi[6], s[6], api[6];
         getp(i, pi);
-        st6(pnew, i, pi);
+        st6(pnew, i, F.n, pi);
         const double d = nbr_sum64(F, i, getp, s);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             api[k] = d * pi[k] - s[k];
             dots[k] = pi[k] * api[k];
         }
-        st6(Ap, i, api);
+        st6(Ap, i, F.n, api);
     }
     if (grid_reduce<6>(dots, partials, counter, smem)) {
         for (int k = 0; k < 6; ++k) sc->alpha[k] = dots[k] > 0.0 ? sc->rz[k] / dots[k] : 0.0;
@@ -557,10 +675,10 @@ __global__ void __launch_bounds__(TPB) pcg_update_kernel(int n, double *__restri
     if (i < n) {
         double xi[6], ri[6], pi[6], api[6];
         T rf[6];
-        ld6(x, i, xi);
-        ld6(r, i, ri);
-        ld6(p, i, pi);
-        ld6(Ap, i, api);
+        ld6(x, i, n, xi);
+        ld6(r, i, n, ri);
+        ld6(p, i, n, pi);
+        ld6(Ap, i, n, api);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             xi[k] += alpha[k] * pi[k];
@@ -568,9 +686,9 @@ __global__ void __launch_bounds__(TPB) pcg_update_kernel(int n, double *__restri
             rf[k] = (T)ri[k];
             dots[k] = ri[k] * ri[k];
         }
-        st6(x, i, xi);
-        st6(r, i, ri);
-        st6(r32, i, rf);
+        st6(x, i, n, xi);
+        st6(r, i, n, ri);
+        st6(r32, i, n, rf);
     }
     if (grid_reduce<6>(dots, partials, counter, smem)) {
         for (int k = 0; k < 6; ++k) sc->rr[k] = dots[k];
@@ -578,29 +696,51 @@ __global__ void __launch_bounds__(TPB) pcg_update_kernel(int n, double *__restri
     }
 }
 
+// optional in-stream trace of one PCG iteration (NCT_WLS_TRACE=1): an event after every launch, printed per kernel
+struct TraceRec { const char *name; int n; cudaEvent_t e; };
+static std::vector<TraceRec> g_tr;
+static bool g_tr_on = false;
+#define TR(name, n)                                              \
+    do {                                                         \
+        if (g_tr_on) {                                           \
+            cudaEvent_t e__;                                     \
+            cudaEventCreate(&e__);                               \
+            cudaEventRecord(e__, ctx->stream);                   \
+            g_tr.push_back(TraceRec{name, (int)(n), e__});       \
+        }                                                        \
+    } while (0)
+
 // z (level-0 x) = B r32 (level-0 b); rz and beta come out of its last kernel
 int vcycle(nct_ctx *ctx, const MgHierarchy &h, PcgScalars *sc, double *partials, unsigned *counter)
 {
-    for (int k = 0; k < h.bottom; ++k) {
+    for (int k = 0; k < h.mid; ++k) {
         const MgLevel &L = h.lv[k];
         mg_presmooth2_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L);
         NCT_CHECK_LAUNCH(ctx);
+        TR("presmooth2", L.n);
         mg_residual_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L);
         NCT_CHECK_LAUNCH(ctx);
+        TR("residual", L.n);
         const MgLevel &Cc = h.lv[k + 1];
         mg_restrict_kernel<<<nct_div_up(Cc.n, TPB), TPB, 0, ctx->stream>>>(L, Cc);
         NCT_CHECK_LAUNCH(ctx);
+        TR("restrict", Cc.n);
     }
-    mg_bottom_kernel<<<1, h.lv[h.bottom].n > 1024 ? 1024 : 512, 0, ctx->stream>>>(h);
+    if (h.mid < h.bottom) mg_mid_kernel<<<MID_CTAS, MID_TPB, 0, ctx->stream>>>(h, h.mid);
+    else if (h.bottom_smem_bytes > 0) mg_bottom_smem_kernel<<<1, 1024, h.bottom_smem_bytes, ctx->stream>>>(h);
+    else mg_bottom_kernel<<<1, h.lv[h.bottom].n > 1024 ? 1024 : 512, 0, ctx->stream>>>(h);
     NCT_CHECK_LAUNCH(ctx);
-    for (int k = h.bottom - 1; k >= 0; --k) {
+    TR(h.mid < h.bottom ? "mid(cluster)" : "bottom", h.lv[h.mid].n);
+    for (int k = h.mid - 1; k >= 0; --k) {
         const MgLevel &L = h.lv[k];
         const MgLevel &Cc = h.lv[k + 1];
         mg_prolong_smooth_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L, Cc);
         NCT_CHECK_LAUNCH(ctx);
+        TR("prolong_smooth", L.n);
         if (k == 0) mg_smooth_rz_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L, sc, partials, counter);
         else mg_smooth_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L);
         NCT_CHECK_LAUNCH(ctx);
+        TR(k == 0 ? "smooth_rz" : "smooth", L.n);
     }
     return NCT_OK;
 }
@@ -671,10 +811,25 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
         L.b = vp; vp += (size_t)L.n * 6;
         L.t = vp; vp += (size_t)L.n * 6;
     }
-    static const int bottom_n = getenv("NCT_MG_BOTTOM_N") ? atoi(getenv("NCT_MG_BOTTOM_N")) : 1024;
-    for (int k = 0; k < nl; ++k)
-        if (h.lv[k].n <= bottom_n) { h.bottom = k; break; }
-    if (h.bottom == 0) h.bottom = 1;  // level 0 always uses the grid kernels (tiny images only)
+    // bottom = the first level whose whole sub-hierarchy fits the shared memory of one block (<= 200 KB; 1936 nodes
+    // for a 700 x 700 image); NCT_MG_BOTTOM_N > 0 selects the global-memory single-block kernel with that node limit
+    static const int bottom_n = getenv("NCT_MG_BOTTOM_N") ? atoi(getenv("NCT_MG_BOTTOM_N")) : 0;
+    h.bottom_smem_bytes = 0;
+    if (bottom_n > 0) {
+        for (int k = 0; k < nl; ++k)
+            if (h.lv[k].n <= bottom_n) { h.bottom = k; break; }
+        if (h.bottom == 0) h.bottom = 1;  // level 0 always uses the grid kernels (tiny images only)
+    } else {
+        constexpr int kSmemCap = 220 * 1024;  // of the 227 KB a block may use on sm_100
+        NCT_CUDA(ctx, cudaFuncSetAttribute(mg_bottom_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap));  // per device, cheap
+        for (int k = 1; k < nl; ++k)
+            if (bottom_smem_bytes(h, k) <= (size_t)kSmemCap) { h.bottom = k; break; }
+        h.bottom_smem_bytes = (int)bottom_smem_bytes(h, h.bottom);
+    }
+    static const int mid_n = getenv("NCT_MG_MID_N") ? atoi(getenv("NCT_MG_MID_N")) : 0;
+    h.mid = h.bottom;
+    for (int k = 1; k < h.bottom; ++k)
+        if (h.lv[k].n <= mid_n) { h.mid = k; break; }
     double *x = dvec, *r = dvec + (size_t)n0 * 6, *p0 = dvec + (size_t)n0 * 12, *p1 = dvec + (size_t)n0 * 18, *Ap = dvec + (size_t)n0 * 24;
     double *wx64 = dcoef, *wy64 = dcoef + n0;
 
@@ -699,7 +854,20 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
     NCT_CUDA(ctx, cudaMemsetAsync(p0, 0, sizeof(double) * 6 * (size_t)n0, ctx->stream));
     const MgLevel &L0 = h.lv[0];
     const FineOp F{H, W, n0, rough_dev, wx64, wy64};
-    pcg_init_kernel<<<blocks0, TPB, 0, ctx->stream>>>(F, x, r, L0.b, sc, partials, counter);
+    // warm start (pipeline levels >= 1): the previous level's solution of the same-size system is a better initial guess
+    // than x0; the converged result is the same to the tolerance
+    double *prev = nullptr;
+    if (ctx->wls_warm) {
+        prev = (double *)nct_scratch(ctx, "wls_prev_x", sizeof(double) * 6 * (size_t)n0);
+        if (!prev) return NCT_ERR_NOMEM;
+    }
+    const double *xrhs = x;
+    if (prev && ctx->wls_prev_n == n0) {
+        NCT_CUDA(ctx, cudaMemcpyAsync(Ap, x, sizeof(double) * 6 * (size_t)n0, cudaMemcpyDeviceToDevice, ctx->stream));
+        NCT_CUDA(ctx, cudaMemcpyAsync(x, prev, sizeof(double) * 6 * (size_t)n0, cudaMemcpyDeviceToDevice, ctx->stream));
+        xrhs = Ap;  // free until the first spmv
+    }
+    pcg_init_kernel<<<blocks0, TPB, 0, ctx->stream>>>(F, x, xrhs, r, L0.b, sc, partials, counter);
     NCT_CHECK_LAUNCH(ctx);
 
     double *pold = p0, *pnew = p1;
@@ -716,17 +884,39 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
         }
         if (worst <= rel_tol || hs.iters >= max_iters) break;
         for (int it = 0; it < check_every; ++it) {
+            static const bool trace_env = getenv("NCT_WLS_TRACE") != nullptr;
+            static int trace_count = 0;
+            g_tr_on = trace_env && (++trace_count == 70);  // one iteration in the middle of the second solve
+            TR("start", 0);
             int rc = vcycle(ctx, h, sc, partials, counter);
             if (rc) return rc;
             pcg_spmv_kernel<<<blocks0, TPB, 0, ctx->stream>>>(F, L0.x, pold, pnew, Ap, sc, partials, counter);
             NCT_CHECK_LAUNCH(ctx);
+            TR("pcg_spmv", n0);
             pcg_update_kernel<<<blocks0, TPB, 0, ctx->stream>>>(n0, x, r, L0.b, pnew, Ap, sc, partials, counter);
             NCT_CHECK_LAUNCH(ctx);
+            TR("pcg_update", n0);
+            if (g_tr_on) {
+                g_tr_on = false;
+                cudaStreamSynchronize(ctx->stream);
+                float tot = 0.f;
+                for (size_t q = 1; q < g_tr.size(); ++q) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, g_tr[q - 1].e, g_tr[q].e);
+                    tot += ms;
+                    fprintf(stderr, "[wls-trace] %-16s n=%7d %8.2f us\n", g_tr[q].name, g_tr[q].n, ms * 1e3f);
+                }
+                fprintf(stderr, "[wls-trace] iteration total %8.2f us (with %zu event records)\n", tot * 1e3f, g_tr.size());
+            }
             double *t = pold; pold = pnew; pnew = t;
         }
     }
     unpack6_kernel<<<blocks0, TPB, 0, ctx->stream>>>(x, n0, a_dev, b_dev);
     NCT_CHECK_LAUNCH(ctx);
+    if (prev) {
+        NCT_CUDA(ctx, cudaMemcpyAsync(prev, x, sizeof(double) * 6 * (size_t)n0, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->wls_prev_n = n0;
+    }
     if (iters_out) *iters_out = hs.iters;
     if (rel_res_out) *rel_res_out = worst;
     if (getenv("NCT_WLS_VERBOSE")) fprintf(stderr, "[nct] WLS %dx%d lam=%.3f: %d MG-PCG iterations, rel.res %.2e\n", H, W, lam, hs.iters, worst);
