@@ -14,17 +14,20 @@
 // cost by the brute force.  The result does not depend on the visiting order (keys are (d^2, id)), so the scatter
 // order inside a cell does not matter: deterministic output.
 #include "device_utils.cuh"
+#include <cstdlib>
 
 namespace {
 
-constexpr int CS = 1;                       // log2 of the cell size
-constexpr int CD = 256 >> CS;               // cells per axis (128)
-constexpr int CELLS = CD * CD * CD;         // cells per cluster (2M)
+// The cell size is chosen per call from the number of pixels (template parameter CS = log2 of the cell edge): the
+// finest level (490k pixels) uses 2-unit cells, the coarse levels -- whose few thousand points would leave a fine grid
+// almost empty and send every query through many empty shells -- use 4, 8 or 16-unit cells.
 constexpr int MAXK = 16;
 constexpr int FALLBACK_R = 6;               // shell radius after which the whole cluster is scanned instead
 
+template <int CS>
 __device__ __forceinline__ int cell_of(uint32_t lab)
 {
+    constexpr int CD = 256 >> CS;
     const int L = lab & 255, a = (lab >> 8) & 255, b = (lab >> 16) & 255;
     return ((L >> CS) * CD + (a >> CS)) * CD + (b >> CS);
 }
@@ -47,17 +50,20 @@ __global__ void cell_masks_kernel(const int *__restrict__ labels, int lw, int lh
     mask[id] = m;
 }
 
+template <int CS>
 __global__ void grid_count_kernel(const uint32_t *__restrict__ mask, const uint8_t *__restrict__ lab, int lw, int w, int n,
                                   int samples, int K, int *__restrict__ table)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t m = mask[((p / w) / samples) * lw + (p % w) / samples];
-    const int c = cell_of(pack_lab(lab, p));
+    constexpr int CELLS = (256 >> CS) * (256 >> CS) * (256 >> CS);
+    const int c = cell_of<CS>(pack_lab(lab, p));
     for (int l = 0; l < K; ++l)
         if ((m >> l) & 1u) atomicAdd(&table[(size_t)l * CELLS + c], 1);
 }
 
+template <int CS>
 __global__ void grid_fill_kernel(const uint32_t *__restrict__ mask, const uint8_t *__restrict__ lab, int lw, int w, int n,
                                  int samples, int K, const int *__restrict__ start, int *__restrict__ cursor,
                                  uint32_t *__restrict__ s_lab, int *__restrict__ s_id)
@@ -65,8 +71,9 @@ __global__ void grid_fill_kernel(const uint32_t *__restrict__ mask, const uint8_
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t m = mask[((p / w) / samples) * lw + (p % w) / samples];
+    constexpr int CELLS = (256 >> CS) * (256 >> CS) * (256 >> CS);
     const uint32_t v = pack_lab(lab, p);
-    const int c = cell_of(v);
+    const int c = cell_of<CS>(v);
     for (int l = 0; l < K; ++l)
         if ((m >> l) & 1u) {
             const size_t key = (size_t)l * CELLS + c;
@@ -112,12 +119,14 @@ __device__ __forceinline__ void scan_range(const uint32_t *__restrict__ s_lab, c
     }
 }
 
+template <int CS>
 __global__ void __launch_bounds__(128) knn_grid_kernel(const uint32_t *__restrict__ mask, const uint8_t *__restrict__ lab,
                                                        const int *__restrict__ start, const uint32_t *__restrict__ s_lab,
                                                        const int *__restrict__ s_id, int lw, int w, int n, int samples, int K,
                                                        int *__restrict__ knn_id, double *__restrict__ knn_w,
                                                        const double *__restrict__ wtab)
 {
+    constexpr int CD = 256 >> CS, CELLS = CD * CD * CD;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t m = mask[((p / w) / samples) * lw + (p % w) / samples];
@@ -130,7 +139,7 @@ __global__ void __launch_bounds__(128) knn_grid_kernel(const uint32_t *__restric
         if (!((m >> l) & 1u)) continue;
         const int *st = start + (size_t)l * CELLS;
         const int cl_begin = st[0], cl_end = st[CELLS];
-        if (cl_end - cl_begin <= 64) {  // tiny cluster: scan it
+        if (cl_end - cl_begin <= 512) {  // small cluster: scan it
             scan_range(s_lab, s_id, cl_begin, cl_end, q, p, top);
             continue;
         }
@@ -184,20 +193,12 @@ __global__ void __launch_bounds__(128) knn_grid_kernel(const uint32_t *__restric
     }
 }
 
-}  // namespace
-
-extern "C" {
-
-int nct_find_knns(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int nlabels, const uint8_t *lab_dev, int h, int w,
-                  int samples, int *knn_id_dev, double *knn_w_dev)
+template <int CS>
+int run_find_knns(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int K, const uint8_t *lab_dev, int h, int w, int samples,
+                  int *knn_id_dev, double *knn_w_dev, const double *wtab)
 {
-    if (!ctx) return NCT_ERR_ARG;
-    NCT_REQUIRE(ctx, labels_dev && lab_dev && knn_id_dev && knn_w_dev, "null pointer");
-    NCT_REQUIRE(ctx, nlabels >= 1 && nlabels <= MAXK && samples >= 1, "bad cluster count / samples");
-    NCT_REQUIRE(ctx, (long long)lw * samples >= w && (long long)lh * samples >= h, "label grid %dx%d x %d does not cover the %dx%d image", lw, lh, samples, w, h);
-    const int n = h * w, K = nlabels;
-    const double *wtab = nct_knn_weight_table(ctx);
-    if (!wtab) return NCT_ERR_NOMEM;
+    constexpr int CELLS = (256 >> CS) * (256 >> CS) * (256 >> CS);
+    const int n = h * w;
     const size_t T = (size_t)K * CELLS;
     const size_t max_pairs = (size_t)n * (K < 5 ? K : 5);
     uint32_t *mask = (uint32_t *)nct_scratch(ctx, "knn_mask", sizeof(uint32_t) * (size_t)lw * lh);
@@ -209,16 +210,41 @@ int nct_find_knns(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int nlabe
     cell_masks_kernel<<<nct_div_up(lw * lh, 256), 256, 0, ctx->stream>>>(labels_dev, lw, lh, mask);
     NCT_CHECK_LAUNCH(ctx);
     NCT_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int) * (T + 1), ctx->stream));
-    grid_count_kernel<<<nct_div_up(n, 256), 256, 0, ctx->stream>>>(mask, lab_dev, lw, w, n, samples, K, count);
+    grid_count_kernel<CS><<<nct_div_up(n, 256), 256, 0, ctx->stream>>>(mask, lab_dev, lw, w, n, samples, K, count);
     NCT_CHECK_LAUNCH(ctx);
     int rc = nct_exclusive_scan_i32(ctx, count, start, (int)T);
     if (rc) return rc;
     NCT_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(int) * (T + 1), ctx->stream));
-    grid_fill_kernel<<<nct_div_up(n, 256), 256, 0, ctx->stream>>>(mask, lab_dev, lw, w, n, samples, K, start, count, s_lab, s_id);
+    grid_fill_kernel<CS><<<nct_div_up(n, 256), 256, 0, ctx->stream>>>(mask, lab_dev, lw, w, n, samples, K, start, count, s_lab, s_id);
     NCT_CHECK_LAUNCH(ctx);
-    knn_grid_kernel<<<nct_div_up(n, 128), 128, 0, ctx->stream>>>(mask, lab_dev, start, s_lab, s_id, lw, w, n, samples, K, knn_id_dev, knn_w_dev, wtab);
+    knn_grid_kernel<CS><<<nct_div_up(n, 128), 128, 0, ctx->stream>>>(mask, lab_dev, start, s_lab, s_id, lw, w, n, samples, K, knn_id_dev, knn_w_dev, wtab);
     NCT_CHECK_LAUNCH(ctx);
     return NCT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nct_find_knns(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int nlabels, const uint8_t *lab_dev, int h, int w,
+                  int samples, int *knn_id_dev, double *knn_w_dev)
+{
+    if (!ctx) return NCT_ERR_ARG;
+    NCT_REQUIRE(ctx, labels_dev && lab_dev && knn_id_dev && knn_w_dev, "null pointer");
+    NCT_REQUIRE(ctx, nlabels >= 1 && nlabels <= MAXK && samples >= 1, "bad cluster count / samples");
+    NCT_REQUIRE(ctx, (long long)lw * samples >= w && (long long)lh * samples >= h, "label grid %dx%d x %d does not cover the %dx%d image", lw, lh, samples, w, h);
+    const double *wtab = nct_knn_weight_table(ctx);
+    if (!wtab) return NCT_ERR_NOMEM;
+    const int n = h * w;
+    // cell edge 2, 4, 8, 16 colour units (the result does not depend on it, only the search cost)
+    static const int force_cs = getenv("NCT_KNN_CS") ? atoi(getenv("NCT_KNN_CS")) : 0;
+    const int cs = force_cs ? force_cs : (n >= 300000 ? 1 : (n >= 60000 ? 2 : (n >= 10000 ? 3 : 4)));
+    switch (cs) {
+    case 1: return run_find_knns<1>(ctx, labels_dev, lw, lh, nlabels, lab_dev, h, w, samples, knn_id_dev, knn_w_dev, wtab);
+    case 2: return run_find_knns<2>(ctx, labels_dev, lw, lh, nlabels, lab_dev, h, w, samples, knn_id_dev, knn_w_dev, wtab);
+    case 3: return run_find_knns<3>(ctx, labels_dev, lw, lh, nlabels, lab_dev, h, w, samples, knn_id_dev, knn_w_dev, wtab);
+    default: return run_find_knns<4>(ctx, labels_dev, lw, lh, nlabels, lab_dev, h, w, samples, knn_id_dev, knn_w_dev, wtab);
+    }
 }
 
 }  // extern "C"
