@@ -198,18 +198,52 @@ __device__ __forceinline__ void nl_apply(const NlSystem &S, int i, const double 
 #pragma unroll
         for (int k = 0; k < 6; ++k) out[k] = __dadd_rn(out[k], __dmul_rn(w2, __dsub_rn(xi[k], xj[k])));
     };
-    if (x + 1 < w) link(i + 1, S.wx2[i]);
-    if (x > 0) link(i - 1, S.wx2[i - 1]);
-    if (y + 1 < h) link(i + w, S.wy2[i]);
-    if (y > 0) link(i - w, S.wy2[i - w]);
+    // Non-local links, four at a time: ids and weights first, then the four neighbour records, then the accumulation in
+    // the canonical order (k ascending, then ascending reverse-list position).  The arithmetic is that of one link()
+    // per neighbour; only the loads are issued together -- one link at a time is a chain of two dependent gathers per
+    // link (id -> record), 16-20 round trips per pixel, which was all of this kernel's time at the coarse levels.
+    auto link4 = [&](const int (&j)[4], const double (&w2)[4], const bool (&ok)[4]) {
+        double xj[4][6];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (ok[u]) getx(j[u], xj[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (ok[u]) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) out[k] = __dadd_rn(out[k], __dmul_rn(w2[u], __dsub_rn(xi[k], xj[u][k])));
+            }
+    };
+    {   // the 4-neighbour links x+1, x-1, y+1, y-1 (in this order)
+        const bool ok[4] = {x + 1 < w, x > 0, y + 1 < h, y > 0};
+        const int j[4] = {i + 1, i - 1, i + w, i - w};
+        const double w2[4] = {ok[0] ? S.wx2[i] : 0.0, ok[1] ? S.wx2[i - 1] : 0.0, ok[2] ? S.wy2[i] : 0.0, ok[3] ? S.wy2[i - w] : 0.0};
+        link4(j, w2, ok);
+    }
 #pragma unroll 1
-    for (int k = 0; k < 8; ++k) {
-        const int j = S.knn_id[(size_t)i * 8 + k];
-        if (j >= 0 && j < n) link(j, S.knn_w2[(size_t)i * 8 + k]);
+    for (int k0 = 0; k0 < 8; k0 += 4) {
+        const int4 jv = *reinterpret_cast<const int4 *>(S.knn_id + (size_t)i * 8 + k0);
+        const double2 wa = *reinterpret_cast<const double2 *>(S.knn_w2 + (size_t)i * 8 + k0);
+        const double2 wb = *reinterpret_cast<const double2 *>(S.knn_w2 + (size_t)i * 8 + k0 + 2);
+        const int j[4] = {jv.x, jv.y, jv.z, jv.w};
+        const double w2[4] = {wa.x, wa.y, wb.x, wb.y};
+        const bool ok[4] = {j[0] >= 0 && j[0] < n, j[1] >= 0 && j[1] < n, j[2] >= 0 && j[2] < n, j[3] >= 0 && j[3] < n};
+        link4(j, w2, ok);
     }
     const int e = S.rev_start[i + 1];
 #pragma unroll 1
-    for (int t = S.rev_start[i]; t < e; ++t) link(S.rev_src[t], S.rev_w2[t]);
+    for (int t = S.rev_start[i]; t < e; t += 4) {
+        int j[4];
+        double w2[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ok[u] = t + u < e;
+            j[u] = ok[u] ? S.rev_src[t + u] : 0;
+            w2[u] = ok[u] ? S.rev_w2[t + u] : 0.0;
+        }
+        link4(j, w2, ok);
+    }
 }
 
 // r = A^T b - A^T A x0 ; r1 = r.r per channel ; p_old = 0
