@@ -144,7 +144,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     pkg = g.load_package()
-    side, P, K = args.side, args.pairs_in_flight, args.steps
+    # pairs in flight per GPU: each needs a host thread that issues ~8k launches per pair, so never more than the
+    # host cores this rank can count on
+    cores = len(os.sched_getaffinity(0))
+    P = max(1, min(args.pairs_in_flight, cores // max(world, 1)))
+    side, K = args.side, args.steps
     weights = synth.vgg19_weights(19)
     # P pairs in flight per GPU: one libnct context + stream + host thread each (pairs are independent; the coarse
     # pyramid levels and the solvers' small kernels do not fill 148 SMs on their own)
@@ -307,10 +311,12 @@ def run_ours(args):
             "e2e": {"value": round(e2e, 4), "unit": "MP/s", "h2d_bytes_per_step": P * 2 * side * side * 3, "d2h_bytes_per_step": P * side * side * 3,
                     "ms_per_step": round(e2e_ms / K, 2)},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "pm_step_kernel (PatchMatch propagate + random search)", "bound": "hbm",
+            "roofline": {"kernel": "pm_step_t_kernel (PatchMatch propagate + random search, tiled step kernel)", "bound": "hbm",
                          "achieved": round(ach, 1) if ach else None, "peak": peak, "unit": "GB/s",
-                         "frac": round(ach / peak, 3) if ach else None, "traffic": 614.5e6, "traffic_note":
-                         "dram__bytes_read+write per finest-level launch from profiles/r1_pm_step_ncu.md (10.7 GB algorithmic per launch)",
+                         "frac": round(ach / peak, 3) if ach else None, "traffic": 946.8e6, "traffic_note":
+                         "dram__bytes_read+write of one finest-level random-search launch (ncu --set full, profiles/r1_pm_step_ncu.md; "
+                         "~15.9 GB algorithmic in that launch: candidate rows are re-used out of L2/L1, so DRAM traffic is far BELOW the "
+                         "algorithmic bytes and achieved can exceed the HBM peak)",
                          "peak_source": peak_src, "launches": int(nl), "avg_launch_ms": round(pm_ms / max(nl, 1), 4),
                          "algorithmic_GB_per_pair": round(evals_bytes[0] / 1e9, 1),
                          "measured_in": f"timed region, context 0 of {P} co-running streams",
@@ -343,7 +349,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-side", type=int, default=256, help="side of the bounded CPU sample pair")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pairs-in-flight", type=int, default=4, help="independent pairs processed concurrently per GPU (one step = this many pairs per rank)")
+    ap.add_argument("--pairs-in-flight", type=int, default=6, help="independent pairs processed concurrently per GPU (one step = this many pairs per rank)")
     ap.add_argument("--vgg-engine", type=int, default=2, choices=[0, 1, 2],
                     help="convolution engine: 0 fp32 CUDA cores, 1 tcgen05 tf32, 2 tcgen05 3xTF32 (default)")
     args = ap.parse_args()

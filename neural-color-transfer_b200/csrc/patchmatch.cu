@@ -635,10 +635,13 @@ struct UTraits {
     static constexpr bool A_IN_REGS = (C == 64) || (C == 256);
 };
 
-template <int C, bool HALF>
+// AS = true: the query patch lives in shared memory (a_s[vector][lane of the group]) instead of registers / L1:
+// 36 fewer registers per thread at C = 64, i.e. more resident warps for a latency-bound kernel
+template <int C, bool HALF, bool AS = false>
 struct UQuery {
     using T = UTraits<C, HALF>;
-    float4 a[T::A_IN_REGS ? 9 * T::NV : 1];
+    float4 a[(T::A_IN_REGS && !AS) ? 9 * T::NV : 1];
+    const float4 *a_s;
     const float *a_base;
     int aw;
     unsigned amask;
@@ -680,10 +683,11 @@ __device__ __forceinline__ float u_finish(float acc0, float acc1, unsigned mask,
     return __fdiv_rn(-acc, (float)n);
 }
 
-template <int C, bool HALF>
-__device__ __forceinline__ float u_eval(const UQuery<C, HALF> &q, const float *__restrict__ b, int bx, int by, int bw, int bh, int j,
+template <int C, bool HALF, bool AS = false>
+__device__ __forceinline__ float u_eval(const UQuery<C, HALF, AS> &q, const float *__restrict__ b, int bx, int by, int bw, int bh, int j,
                                         unsigned mask)
 {
+    constexpr int GL = UTraits<C, HALF>::LANES;
     using T = UTraits<C, HALF>;
     constexpr int NV = T::NV, ST = T::STRIDE;
     const unsigned valid = q.amask & patch_mask(bx, by, bw, bh);
@@ -702,7 +706,8 @@ __device__ __forceinline__ float u_eval(const UQuery<C, HALF> &q, const float *_
             float4 av[NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
-                if (T::A_IN_REGS) av[k] = q.a[pi * NV + k];
+                if (AS) av[k] = q.a_s[(pi * NV + k) * GL];
+                else if (T::A_IN_REGS) av[k] = q.a[pi * NV + k];
                 else av[k] = ldg4(ra[pi / 3] + (pi % 3 - 1) * C + k * ST);
             }
             u_accumulate<C, HALF>(acc0, acc1, pi, av, &bv[pi * NV]);
@@ -728,7 +733,8 @@ __device__ __forceinline__ float u_eval(const UQuery<C, HALF> &q, const float *_
             float4 av[NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
-                if (T::A_IN_REGS) av[k] = q.a[pi * NV + k];
+                if (AS) av[k] = q.a_s[(pi * NV + k) * GL];
+                else if (T::A_IN_REGS) av[k] = q.a[pi * NV + k];
                 else av[k] = ldg4(q.a_base + ((ptrdiff_t)dy * q.aw + dx) * C + k * ST);
             }
             u_accumulate<C, HALF>(acc0, acc1, pi, av, &bv[pi * NV]);
@@ -876,11 +882,12 @@ struct TQueryState {
     float dbest;
 };
 
-template <int C, bool HALF>
-__global__ void __launch_bounds__(128, HALF ? 4 : 2) pm_step_t_kernel(const PMStep s, const int tile)
+template <int C, bool HALF, bool AS = false>
+__global__ void __launch_bounds__(128, HALF ? (AS ? (C == 64 ? 6 : 5) : 4) : 2) pm_step_t_kernel(const PMStep s, const int tile)
 {
     using T = UTraits<C, HALF>;
     __shared__ TQueryState st_all[4][32];
+    __shared__ float4 a_sm[AS ? 128 * 9 * T::NV : 1];  // [group of the block][vector][lane of the group]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     TQueryState *st = st_all[wib];
     const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -967,11 +974,27 @@ __global__ void __launch_bounds__(128, HALF ? 4 : 2) pm_step_t_kernel(const PMSt
         const int n_prop_end = n_first + q0.n;
         const int total = n_prop_end + (s.do_random ? D.n_mag : 0);
 
-        UQuery<C, HALF> q;
+        UQuery<C, HALF, AS> q;
         q.aw = aw;
         q.amask = patch_mask(ax, ay, aw, ah);
         q.a_base = D.a + ((size_t)ay * aw + ax) * C + j * 4;
-        if (T::A_IN_REGS) {
+        q.a_s = nullptr;
+        if (AS) {
+            // this group's slice: groups are (warp, half); each vector slot holds LANES consecutive float4
+            float4 *slot = a_sm + (size_t)((wib * (HALF ? 2 : 1) + grp) * 9 * T::NV) * T::LANES + j;
+            __syncwarp(mask);  // the previous query's readers are done
+#pragma unroll
+            for (int pi = 0; pi < 9; ++pi) {
+                const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+#pragma unroll
+                for (int k = 0; k < T::NV; ++k) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if ((q.amask >> pi) & 1u) v = ldg4(q.a_base + ((ptrdiff_t)dy * aw + dx) * C + k * T::STRIDE);
+                    slot[(pi * T::NV + k) * T::LANES] = v;
+                }
+            }
+            q.a_s = slot;  // every lane reads back only what it wrote itself: no barrier needed
+        } else if (T::A_IN_REGS) {
 #pragma unroll
             for (int pi = 0; pi < 9; ++pi) {
                 const int dy = pi / 3 - 1, dx = pi % 3 - 1;
@@ -1008,7 +1031,7 @@ __global__ void __launch_bounds__(128, HALF ? 4 : 2) pm_step_t_kernel(const PMSt
                 if (cx == xbest && cy == ybest) continue;  // D3
             }
             n_eval += (j == 0);
-            const float d = u_eval<C, HALF>(q, D.b, cx, cy, bw, bh, j, mask);
+            const float d = u_eval<C, HALF, AS>(q, D.b, cx, cy, bw, bh, j, mask);
             const float dcmp = is_rand ? __fadd_rn(d, FLT_MIN) : d;
             if (i < n_first || dcmp < dbest) {
                 dbest = d;
@@ -1075,9 +1098,11 @@ struct StepLauncher<C, true> {
             const int blocks = nct_div_up(s.nq_total, 8);
             pm_step_u_kernel<C, true><<<blocks, 128, 0, st>>>(s);
         } else {
+            static const bool a_smem = getenv("NCT_PM_ASMEM") != nullptr;  // A/B: query patch in shared memory
             const int tile = pm_tile_size(s.nq_total, 148);
             const int blocks = nct_div_up(nct_div_up(s.nq_total, tile), 4);
-            pm_step_t_kernel<C, true><<<blocks, 128, 0, st>>>(s, tile);
+            if (a_smem) pm_step_t_kernel<C, true, true><<<blocks, 128, 0, st>>>(s, tile);
+            else pm_step_t_kernel<C, true><<<blocks, 128, 0, st>>>(s, tile);
         }
     }
 };
