@@ -27,9 +27,11 @@ constexpr int TPB = 256;
 constexpr int MAX_LEVELS = 14;
 // tunable through NCT_MG_OMEGA / NCT_MG_EDGE_SCALE for experiments; the defaults are the measured optimum on the
 // 700x700 workload (profiles/r1_wls_tuning.md)
-__constant__ float c_omega = 0.8f;
+__constant__ float c_omega = 0.55f;
 __constant__ float c_edge_scale = 0.5f;
+__constant__ float c_omega2 = 1.7f;  // damping of the second sweep of each pair: (0.55, 1.7) is a two-step Chebyshev-like pair, |p(lambda)| <= 0.36 on (0, 2)
 #define OMEGA c_omega
+#define OMEGA2 c_omega2
 
 typedef float T;  // precision of the preconditioner
 
@@ -139,9 +141,10 @@ __device__ __forceinline__ void op_presmooth2(const MgLevel &L, int i)
 #pragma unroll
         for (int k = 0; k < 6; ++k) xj[k] *= f;
     }, s);
-    const T f = OMEGA * L.invd[i];
+    // x1 = w1 D^-1 b ; x2 = x1 + w2 D^-1 (b - M x1)
+    const T f = OMEGA * L.invd[i], f2 = OMEGA2 * L.invd[i];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) o[k] = f * bi[k] + f * ((T(1) - OMEGA) * bi[k] + s[k]);
+    for (int k = 0; k < 6; ++k) o[k] = f * bi[k] + f2 * ((T(1) - OMEGA) * bi[k] + s[k]);
     st6(L.x, i, L.n, o);
 }
 
@@ -234,7 +237,7 @@ __device__ __forceinline__ void op_smooth_t_to_x(const MgLevel &L, int i, T (&bi
     nbr_sum(L, i, [&](int j, T (&xj)[6]) { ld6(L.t, j, L.n, xj); }, s);
     const T invd = L.invd[i], d = T(1) / invd;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) o[k] = ti[k] + OMEGA * invd * (bi[k] - d * ti[k] + s[k]);
+    for (int k = 0; k < 6; ++k) o[k] = ti[k] + OMEGA2 * invd * (bi[k] - d * ti[k] + s[k]);
     st6(L.x, i, L.n, o);
 }
 
@@ -761,7 +764,8 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
         static bool tuned = false;
         if (!tuned) {
             tuned = true;
-            const char *eo = getenv("NCT_MG_OMEGA"), *es = getenv("NCT_MG_EDGE_SCALE");
+            const char *eo = getenv("NCT_MG_OMEGA"), *es = getenv("NCT_MG_EDGE_SCALE"), *eo2 = getenv("NCT_MG_OMEGA2");
+            if (eo2) { float v = (float)atof(eo2); cudaMemcpyToSymbol(c_omega2, &v, sizeof(v)); }
             if (eo) { float v = (float)atof(eo); cudaMemcpyToSymbol(c_omega, &v, sizeof(v)); }
             if (es) { float v = (float)atof(es); cudaMemcpyToSymbol(c_edge_scale, &v, sizeof(v)); }
         }
