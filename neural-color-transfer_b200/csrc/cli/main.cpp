@@ -4,7 +4,12 @@
 // "Unrecognized parameter" + the list and exits with -1.  Reads <model_dir>/vgg19/VGG_ILSVRC_19_layers.caffemodel and
 // <input_root>/pairs.txt, writes <out_dir>/<content>_<style>_<bds>.png.
 // Extension: -ngpu N processes the pair list on GPUs g .. g+N-1, one worker (own context) per GPU, pair i on worker
-// i mod N; the reference is single-GPU (NCT/main.cu:563-565).
+// i mod N; the reference is single-GPU (NCT/main.cu:563-565).  -inflight P keeps P pairs in flight per GPU (P contexts,
+// streams and host threads per GPU; pair i on worker i mod (N * P)): the coarse pyramid levels and the solvers' small
+// kernels do not fill a B200 on their own, so P = 4..6 raises the throughput of a long pair list by ~1.5x.  With P > 1
+// the progress lines of different pairs interleave on stdout.  -engine selects the convolution engine (the reference has
+// whatever algorithm cuDNN picks): 2 = tensor cores, FP32-accurate 3xTF32 (default); 0 = FP32 CUDA cores in the canonical
+// summation order, the engine whose whole-pipeline output is bit-identical to the oracle's.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,6 +19,7 @@
 #include "../../../include/nct.h"
 
 extern "C" int nct_vgg19_load_caffemodel(nct_ctx *ctx, const char *path);
+extern "C" int nct_vgg19_set_engine(nct_ctx *ctx, int engine);
 extern "C" int nct_run_pairs(nct_ctx *ctx, const char *input_dir, const char *output_dir, const nct_config *cfg, int rank, int world, int *pairs_done);
 
 struct Param { const char *arg; const char *desc; int kind; void *dst; };  // kind 0 string, 1 int, 2 double
@@ -31,7 +37,7 @@ int main(int argc, char **argv)
     nct_config cfg;
     nct_config_default(&cfg);
     std::string model_dir, input_dir, output_dir;
-    int gpu_id = 0, ngpu = 1;
+    int gpu_id = 0, ngpu = 1, inflight = 1, engine = 2;
     std::vector<Param> params = {
         {"m", "Directory of network models.", 0, &model_dir},
         {"i", "Input directory of content and style images and pairs.txt.", 0, &input_dir},
@@ -43,6 +49,8 @@ int main(int argc, char **argv)
         {"l", "Weight of local constraint (default: 0.125).", 2, &cfg.local_weight},
         {"w", "Initial value of WLS weight (default: 0.024).", 2, &cfg.wls_lambda_init},
         {"ngpu", "Number of GPUs to spread the pair list over, starting at -g (default: 1).", 1, &ngpu},
+        {"inflight", "Pairs processed concurrently per GPU (default: 1).", 1, &inflight},
+        {"engine", "Convolution engine: 0 FP32 CUDA cores (bit-exact parity engine), 1 tcgen05 TF32, 2 tcgen05 3xTF32 (default: 2).", 1, &engine},
     };
     int i = 1;
     while (i < argc) {
@@ -69,26 +77,29 @@ int main(int argc, char **argv)
         }
     }
     if (ngpu < 1) ngpu = 1;
+    if (inflight < 1) inflight = 1;
+    const int nworkers = ngpu * inflight;
     const std::string weights = model_dir + "/vgg19/VGG_ILSVRC_19_layers.caffemodel";
-    std::vector<nct_ctx *> ctxs((size_t)ngpu, nullptr);
-    for (int r = 0; r < ngpu; ++r) {
-        if (nct_create(gpu_id + r, &ctxs[r]) != NCT_OK) {
-            fprintf(stderr, "Error: cannot create a context on GPU %d (libnct needs an sm_100 device; there is no CPU path).\n", gpu_id + r);
+    std::vector<nct_ctx *> ctxs((size_t)nworkers, nullptr);
+    for (int r = 0; r < nworkers; ++r) {
+        const int dev = gpu_id + r % ngpu;  // worker r -> GPU r mod N, so consecutive pairs go to different GPUs
+        if (nct_create(dev, &ctxs[r]) != NCT_OK) {
+            fprintf(stderr, "Error: cannot create a context on GPU %d (libnct needs an sm_100 device; there is no CPU path).\n", dev);
             return 1;
         }
         if (r == 0) printf("The number of device is: %d, set device %d.\n", ngpu, gpu_id);
-        if (nct_vgg19_load_caffemodel(ctxs[r], weights.c_str()) != NCT_OK) {
+        if (nct_vgg19_load_caffemodel(ctxs[r], weights.c_str()) != NCT_OK || nct_vgg19_set_engine(ctxs[r], engine) != NCT_OK) {
             fprintf(stderr, "Error: %s\n", nct_last_error(ctxs[r]));
             return 1;
         }
     }
     std::vector<std::thread> workers;
-    std::vector<int> done((size_t)ngpu, 0), rcs((size_t)ngpu, 0);
-    for (int r = 0; r < ngpu; ++r)
-        workers.emplace_back([&, r]() { rcs[r] = nct_run_pairs(ctxs[r], input_dir.c_str(), output_dir.c_str(), &cfg, r, ngpu, &done[r]); });
+    std::vector<int> done((size_t)nworkers, 0), rcs((size_t)nworkers, 0);
+    for (int r = 0; r < nworkers; ++r)
+        workers.emplace_back([&, r]() { rcs[r] = nct_run_pairs(ctxs[r], input_dir.c_str(), output_dir.c_str(), &cfg, r, nworkers, &done[r]); });
     for (auto &t : workers) t.join();
     int rc = 0;
-    for (int r = 0; r < ngpu; ++r) {
+    for (int r = 0; r < nworkers; ++r) {
         if (rcs[r]) { fprintf(stderr, "Error: %s\n", nct_last_error(ctxs[r])); rc = 1; }
         nct_destroy(ctxs[r]);
     }

@@ -165,13 +165,45 @@ def test_cli_drop_in_pairs_txt_end_to_end(pkg, pctx, weights, tmp_path):
         pairs.append((c, s))
     (inp / "pairs.txt").write_text("in/in0.png in/tar0.png 2.0\nin/in1.png in/tar1.png 0.5\nin/missing.png in/tar1.png 2.0\n")
     out = tmp_path / "res"
-    r = subprocess.run([cli, "-m", str(tmp_path / "model"), "-i", str(inp), "-o", str(out), "-g", "0"], capture_output=True, text=True)
+    r = subprocess.run([cli, "-m", str(tmp_path / "model"), "-i", str(inp), "-o", str(out), "-g", "0", "-engine", "0"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "Fail reading content image" in r.stdout and r.stdout.count("Final output file") == 2
+    pctx.set_vgg_engine(0)
     for i, bds in enumerate([2.0, 0.5]):
         got = pkg.png_read(str(out / f"in{i}_tar{i}_{bds:2.2f}.png"))
         ref = pctx.transfer_pair(pairs[i][0], pairs[i][1], pctx.default_config(bds_weight=bds))
         assert np.array_equal(got, ref)
+
+
+def test_cli_pairs_in_flight_gives_the_same_files(pkg, pctx, weights, tmp_path):
+    """-inflight P (P contexts / streams / host threads per GPU) only changes the schedule: every output PNG equals the
+    library result of its pair."""
+    import subprocess, os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "neural-color-transfer_b200", "neural_color_transfer")
+    model = tmp_path / "model" / "vgg19"
+    model.mkdir(parents=True)
+    pkg.write_caffemodel(str(model / "VGG_ILSVRC_19_layers.caffemodel"), weights, v1=True)
+    inp = tmp_path / "example"
+    (inp / "in").mkdir(parents=True)
+    pairs, lines = [], []
+    for i, (h, w) in enumerate([(96, 96), (80, 112), (104, 88)]):
+        c, s = synth.pair(20 + i, h, w)
+        pkg.png_write(str(inp / "in" / f"c{i}.png"), c)
+        pkg.png_write(str(inp / "in" / f"s{i}.png"), s)
+        pairs.append((c, s))
+        lines.append(f"in/c{i}.png in/s{i}.png 2.0")
+    (inp / "pairs.txt").write_text("\n".join(lines) + "\n")
+    out = tmp_path / "res"
+    r = subprocess.run([cli, "-m", str(tmp_path / "model"), "-i", str(inp), "-o", str(out), "-g", "0", "-inflight", "3", "-engine", "0"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("Final output file") == 3
+    pctx.set_vgg_engine(0)
+    for i in range(3):
+        got = pkg.png_read(str(out / f"c{i}_s{i}_2.00.png"))
+        assert np.array_equal(got, pctx.transfer_pair(pairs[i][0], pairs[i][1], pctx.default_config(bds_weight=2.0)))
 
 
 def test_caffemodel_v2_records_load_too(pkg, dev, weights, tmp_path):
