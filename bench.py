@@ -174,9 +174,20 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     def run_threads(fn):
-        ts = [threading.Thread(target=fn, args=(j,)) for j in range(P)]
+        errors = []
+
+        def guarded(j):
+            try:
+                torch.cuda.set_device(dev)  # the current device is per host thread
+                fn(j)
+            except BaseException as e:  # a worker that dies silently would make the timing meaningless
+                errors.append(e)
+
+        ts = [threading.Thread(target=guarded, args=(j,)) for j in range(P)]
         [t.start() for t in ts]
         [t.join() for t in ts]
+        if errors:
+            raise errors[0]
 
     def dev_steps(n, record=None):
         def work(j):

@@ -62,6 +62,7 @@ int nct_run_pairs(nct_ctx *ctx, const char *input_dir, const char *output_dir, c
                   int *pairs_done)
 {
     if (!ctx || !input_dir || !output_dir) return NCT_ERR_ARG;
+    cudaSetDevice(ctx->device);  // the calling thread may be a fresh worker thread (CLI -ngpu / -inflight)
     NCT_REQUIRE(ctx, world >= 1 && rank >= 0 && rank < world, "bad rank/world %d/%d", rank, world);
     nct_config cfg;
     if (cfg_in) cfg = *cfg_in;

@@ -360,7 +360,7 @@ extern "C" {
 int nct_reconstruct_bds(nct_ctx *ctx, const uint8_t *a_bgr, const uint8_t *b_bgr, const uint32_t *ann, const uint32_t *bnn,
                         int ah, int aw, int bh, int bw, double w_cohen, double w_complete, uint8_t *out_bgr)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     (void)a_bgr;  // the reference only uses a's size (Mat::zeros(a.size(), ...))
     NCT_REQUIRE(ctx, b_bgr && ann && bnn && out_bgr && ah > 0 && aw > 0 && bh > 0 && bw > 0, "bad arguments");
     const int *start, *list;
@@ -377,7 +377,7 @@ int nct_bds_feature_error(nct_ctx *ctx, const float *c_norm_hwc, const float *s_
                           const uint32_t *bnn, int C, int ah, int aw, int bh, int bw, float w_cohen, float w_complete,
                           float *err_dev, float *vote_out_dev)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, c_norm_hwc && s_raw_hwc && ann && bnn && err_dev, "null device pointer");
     NCT_REQUIRE(ctx, C == 16 || C == 32 || C == 64 || C == 128 || C == 256 || C == 384 || C == 512,
                 "unsupported channel count %d", C);

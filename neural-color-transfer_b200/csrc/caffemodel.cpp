@@ -146,6 +146,7 @@ extern "C" {
 int nct_vgg19_load_caffemodel(nct_ctx *ctx, const char *path)
 {
     if (!ctx || !path) return NCT_ERR_ARG;
+    cudaSetDevice(ctx->device);
     FILE *fp = fopen(path, "rb");
     if (!fp) return nct_fail(ctx, NCT_ERR_IO, "cannot open caffemodel '%s'", path);
     fseek(fp, 0, SEEK_END);

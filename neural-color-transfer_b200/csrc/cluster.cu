@@ -351,7 +351,7 @@ extern "C" {
 
 int nct_cluster_features(nct_ctx *ctx, const float *feat_norm_hwc_dev, int h, int w, int C, int k, int iterations, int *labels_dev)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, feat_norm_hwc_dev && labels_dev && h > 0 && w > 0 && C > 0, "bad arguments");
     NCT_REQUIRE(ctx, k >= 2 && k <= MAXK, "cluster count %d out of range [2, %d]", k, MAXK);
     const int n = h * w;
@@ -400,7 +400,7 @@ int nct_cluster_features(nct_ctx *ctx, const float *feat_norm_hwc_dev, int h, in
 int nct_find_knns_brute(nct_ctx *ctx, const int *labels_dev, int lw, int lh, int nlabels, const uint8_t *lab_dev, int h, int w,
                   int samples, int *knn_id_dev, double *knn_w_dev)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, labels_dev && lab_dev && knn_id_dev && knn_w_dev, "null pointer");
     NCT_REQUIRE(ctx, nlabels >= 1 && nlabels <= MAXK && samples >= 1, "bad cluster count / samples");
     NCT_REQUIRE(ctx, (long long)lw * samples >= w && (long long)lh * samples >= h, "label grid %dx%d x %d does not cover the %dx%d image", lw, lh, samples, w, h);

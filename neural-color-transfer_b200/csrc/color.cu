@@ -387,7 +387,7 @@ extern "C" {
 
 int nct_bgr2lab_u8(nct_ctx *ctx, const uint8_t *bgr_dev, uint8_t *lab_dev, int npix)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, bgr_dev && lab_dev && npix > 0, "bad arguments");
     const LabTables *t = lab_tables(ctx);
     if (!t) return nct_fail(ctx, NCT_ERR_CUDA, "Lab tables upload failed");
@@ -398,7 +398,7 @@ int nct_bgr2lab_u8(nct_ctx *ctx, const uint8_t *bgr_dev, uint8_t *lab_dev, int n
 
 int nct_lab2bgr_u8(nct_ctx *ctx, const uint8_t *lab_dev, uint8_t *bgr_dev, int npix)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, bgr_dev && lab_dev && npix > 0, "bad arguments");
     const LabTables *t = lab_tables(ctx);
     if (!t) return nct_fail(ctx, NCT_ERR_CUDA, "Lab tables upload failed");
@@ -409,7 +409,7 @@ int nct_lab2bgr_u8(nct_ctx *ctx, const uint8_t *lab_dev, uint8_t *bgr_dev, int n
 
 int nct_resize_linear_u8c3(nct_ctx *ctx, const uint8_t *src_dev, int sh, int sw, uint8_t *dst_dev, int dh, int dw)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, src_dev && dst_dev && sh > 0 && sw > 0 && dh > 0 && dw > 0, "bad arguments");
     dim3 block(32, 8), grid(nct_div_up(dw, 32), nct_div_up(dh, 8));
     const double inv_x = (double)dw / sw, inv_y = (double)dh / sh;
@@ -420,7 +420,7 @@ int nct_resize_linear_u8c3(nct_ctx *ctx, const uint8_t *src_dev, int sh, int sw,
 
 int nct_resize_linear_f64c3(nct_ctx *ctx, const double *src_dev, int sh, int sw, double *dst_dev, int dh, int dw)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, src_dev && dst_dev && src_dev != dst_dev && sh > 0 && sw > 0 && dh > 0 && dw > 0, "bad arguments");
     dim3 block(32, 8), grid(nct_div_up(dw, 32), nct_div_up(dh, 8));
     const double inv_x = (double)dw / sw, inv_y = (double)dh / sh;
@@ -432,7 +432,7 @@ int nct_resize_linear_f64c3(nct_ctx *ctx, const double *src_dev, int sh, int sw,
 int nct_local_fit(nct_ctx *ctx, const uint8_t *cnt_lab_dev, const uint8_t *stl_lab_dev, int h, int w, double eps, double *a_dev,
                   double *b_dev)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, cnt_lab_dev && stl_lab_dev && a_dev && b_dev && h > 0 && w > 0, "bad arguments");
     dim3 block(32, 8), grid(nct_div_up(w, 32), nct_div_up(h, 8));
     local_fit_kernel<<<grid, block, 0, ctx->stream>>>(cnt_lab_dev, stl_lab_dev, h, w, eps, a_dev, b_dev);
@@ -442,7 +442,7 @@ int nct_local_fit(nct_ctx *ctx, const uint8_t *cnt_lab_dev, const uint8_t *stl_l
 
 int nct_confidence_weights(nct_ctx *ctx, const float *err_dev, int n, double *weight_dev)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, err_dev && weight_dev && n > 0, "bad arguments");
     int blocks = nct_div_up(n, 256);
     if (blocks > 1024) blocks = 1024;
@@ -462,7 +462,7 @@ int nct_upsample_coefficients(nct_ctx *ctx, const double *a_lvl_dev, const doubl
                               const uint8_t *cnt_lab_full_dev, int H, int W, double *a_full_dev, double *b_full_dev,
                               double *rough_dev)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, a_lvl_dev && b_lvl_dev && cnt_lab_full_dev && a_full_dev && b_full_dev && rough_dev, "null pointer");
     if (W > w || H > h) {
         int rc = nct_resize_linear_f64c3(ctx, a_lvl_dev, h, w, a_full_dev, H, W);
@@ -483,7 +483,7 @@ int nct_upsample_coefficients(nct_ctx *ctx, const double *a_lvl_dev, const doubl
 int nct_apply_coefficients(nct_ctx *ctx, const uint8_t *cnt_lab_full_dev, const double *a_dev, const double *b_dev, int H, int W,
                            uint8_t *out_bgr_dev, uint8_t *out_lab_dev)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, cnt_lab_full_dev && a_dev && b_dev && out_bgr_dev && H > 0 && W > 0, "bad arguments");
     const LabTables *t = lab_tables(ctx);
     if (!t) return nct_fail(ctx, NCT_ERR_CUDA, "Lab tables upload failed");

@@ -115,14 +115,14 @@ extern "C" {
 
 int nct_profile_enable(nct_ctx *ctx, int enable)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     ctx->profile = enable ? 1 : 0;
     return NCT_OK;
 }
 
 int nct_profile_reset(nct_ctx *ctx)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     cudaStreamSynchronize(ctx->stream);
     for (auto &sp : ctx->prof_spans) { ctx->prof_pool.push_back(sp.e0); ctx->prof_pool.push_back(sp.e1); }
     ctx->prof_spans.clear();
@@ -215,7 +215,7 @@ const char *nct_last_error(const nct_ctx *ctx) { return ctx ? ctx->last_error.c_
 
 int nct_set_stream(nct_ctx *ctx, void *cuda_stream)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return NCT_OK;
 }
@@ -224,7 +224,7 @@ void *nct_get_stream(const nct_ctx *ctx) { return ctx ? (void *)ctx->stream : nu
 
 int nct_synchronize(nct_ctx *ctx)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NCT_OK;
 }
@@ -232,6 +232,7 @@ int nct_synchronize(nct_ctx *ctx)
 int nct_debug_read_scratch(nct_ctx *ctx, const char *name, void *host_dst, size_t bytes)
 {
     if (!ctx || !name || !host_dst) return NCT_ERR_ARG;
+    cudaSetDevice(ctx->device);
     auto it = ctx->scratch.find(name);
     if (it == ctx->scratch.end() || !it->second.ptr) return nct_fail(ctx, NCT_ERR_ARG, "no scratch buffer named '%s'", name);
     if (it->second.bytes < bytes) return nct_fail(ctx, NCT_ERR_ARG, "scratch '%s' holds %zu bytes < %zu", name, it->second.bytes, bytes);

@@ -92,7 +92,7 @@ extern "C" {
 
 int nct_l2norm(nct_ctx *ctx, const float *src, float *dst, int C, int H, int W)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, src && dst, "null device pointer");
     NCT_REQUIRE(ctx, C > 0 && C % 4 == 0 && C <= 512, "channel count %d must be a multiple of 4, <= 512", C);
     NCT_REQUIRE(ctx, H > 0 && W > 0, "bad size");
@@ -107,7 +107,7 @@ int nct_l2norm(nct_ctx *ctx, const float *src, float *dst, int C, int H, int W)
 
 int nct_chw_to_hwc(nct_ctx *ctx, const float *src, float *dst, int C, int H, int W)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, src && dst && src != dst && C > 0 && H > 0 && W > 0, "bad arguments");
     const int rows = C, cols = H * W;  // [C][HW] -> [HW][C]
     dim3 block(32, 8), grid(nct_div_up(cols, 32), nct_div_up(rows, 32));
@@ -118,7 +118,7 @@ int nct_chw_to_hwc(nct_ctx *ctx, const float *src, float *dst, int C, int H, int
 
 int nct_hwc_to_chw(nct_ctx *ctx, const float *src, float *dst, int C, int H, int W)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, src && dst && src != dst && C > 0 && H > 0 && W > 0, "bad arguments");
     const int rows = H * W, cols = C;  // [HW][C] -> [C][HW]
     dim3 block(32, 8), grid(nct_div_up(rows, 32), nct_div_up(cols, 32));

@@ -63,6 +63,14 @@ const double *nct_pow_table(nct_ctx *ctx, double alpha);
 // [3 * 255^2 + 1] exp(1 - sqrt(D2) / 255 / 3) indexed by the integer squared Lab distance (sortMergeComputeWeight, CT/ColorTransfer.cpp:60-110)
 const double *nct_knn_weight_table(nct_ctx *ctx);
 
+// Every public entry point starts with this: null check, and the context's device made current for the CALLING thread
+// (the current device is per host thread: a worker thread that did not create the context starts on device 0).
+#define NCT_ENTER(ctx)                                                                               \
+    do {                                                                                             \
+        if (!(ctx)) return NCT_ERR_ARG;                                                              \
+        cudaSetDevice((ctx)->device);                                                                \
+    } while (0)
+
 #define NCT_CUDA(ctx, call)                                                                          \
     do {                                                                                             \
         cudaError_t e__ = (call);                                                                    \

@@ -1228,7 +1228,7 @@ extern "C" {
 
 int nct_nnf_init(nct_ctx *ctx, uint32_t *ann_dev, int ah, int aw, int bh, int bw)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, ann_dev && ah > 0 && aw > 0 && bh > 0 && bw > 0, "bad arguments");
     dim3 block(32, 8), grid(nct_div_up(aw, 32), nct_div_up(ah, 8));
     nnf_init_kernel<<<grid, block, 0, ctx->stream>>>(ann_dev, ah, aw, bh, bw);
@@ -1239,7 +1239,7 @@ int nct_nnf_init(nct_ctx *ctx, uint32_t *ann_dev, int ah, int aw, int bh, int bw
 int nct_nnf_upsample(nct_ctx *ctx, const uint32_t *ann_half_dev, int ah_half, int aw_half, uint32_t *ann_dev, int ah,
                      int aw, int bh, int bw)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, ann_half_dev && ann_dev && ann_half_dev != ann_dev, "bad / aliased NNF buffers");
     NCT_REQUIRE(ctx, ah_half > 0 && aw_half > 0 && ah > 0 && aw > 0 && bh > 0 && bw > 0, "bad sizes");
     dim3 block(32, 8), grid(nct_div_up(aw, 32), nct_div_up(ah, 8));
@@ -1250,7 +1250,7 @@ int nct_nnf_upsample(nct_ctx *ctx, const uint32_t *ann_half_dev, int ah_half, in
 
 int nct_xorwow_table(nct_ctx *ctx, float *out_dev, int ncols, int ndraws)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, out_dev && ncols > 0 && ndraws > 0, "bad arguments");
     xorwow_table_kernel<<<nct_div_up(ncols, 128), 128, 0, ctx->stream>>>(out_dev, ncols, ndraws);
     NCT_CHECK_LAUNCH(ctx);
@@ -1259,7 +1259,7 @@ int nct_xorwow_table(nct_ctx *ctx, float *out_dev, int ncols, int ndraws)
 
 int nct_patchmatch(nct_ctx *ctx, const float *a, const float *b, uint32_t *ann, float *annd, const int params[11])
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     int rc = check_params(ctx, params);
     if (rc) return rc;
     NCT_REQUIRE(ctx, a && b && ann && annd, "null device pointer");
@@ -1280,7 +1280,7 @@ int nct_patchmatch(nct_ctx *ctx, const float *a, const float *b, uint32_t *ann, 
 int nct_patchmatch_bidir(nct_ctx *ctx, const float *a, const float *b, uint32_t *ann, float *annd, uint32_t *bnn,
                          float *bnnd, const int params[11])
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     int rc = check_params(ctx, params);
     if (rc) return rc;
     NCT_REQUIRE(ctx, a && b && ann && annd && bnn && bnnd, "null device pointer");
@@ -1302,7 +1302,7 @@ int nct_patchmatch_bidir(nct_ctx *ctx, const float *a, const float *b, uint32_t 
 
 int nct_patchmatch_count_evals(nct_ctx *ctx, int enable)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     ctx->pm_count_evals = enable ? 1 : 0;
     return NCT_OK;
 }
@@ -1310,6 +1310,7 @@ int nct_patchmatch_count_evals(nct_ctx *ctx, int enable)
 int nct_patchmatch_stats(nct_ctx *ctx, long long stats[2])
 {
     if (!ctx || !stats) return NCT_ERR_ARG;
+    cudaSetDevice(ctx->device);
     unsigned long long h[2];
     NCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     NCT_CUDA(ctx, cudaMemcpy(h, ctx->pm_counters, sizeof(h), cudaMemcpyDeviceToHost));

@@ -45,7 +45,7 @@ void nct_config_default(nct_config *cfg)
 int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int cw, const uint8_t *stl_bgr_dev, int sh, int sw,
                           const nct_config *cfg_in, uint8_t *out_bgr_dev)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, cnt_bgr_dev && stl_bgr_dev && out_bgr_dev, "null device pointer");
     NCT_REQUIRE(ctx, ch >= 32 && cw >= 32 && sh >= 32 && sw >= 32, "images must be at least 32 x 32");
     NCT_REQUIRE(ctx, ch <= 4095 && cw <= 4095 && sh <= 4095 && sw <= 4095, "image sides above 4095 do not fit the 12-bit NNF packing");
@@ -195,7 +195,7 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
 int nct_transfer_pair(nct_ctx *ctx, const uint8_t *cnt_bgr_host, int ch, int cw, const uint8_t *stl_bgr_host, int sh, int sw,
                       const nct_config *cfg, uint8_t *out_bgr_host)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, cnt_bgr_host && stl_bgr_host && out_bgr_host && ch > 0 && cw > 0 && sh > 0 && sw > 0, "bad arguments");
     const size_t nC = (size_t)ch * cw * 3, nS = (size_t)sh * sw * 3;
     uint8_t *dC = (uint8_t *)nct_scratch(ctx, "pipe_in_cnt", nC);

@@ -594,7 +594,7 @@ int nct_solve_nonlocal(nct_ctx *ctx, double *a_dev, double *b_dev, const double 
                        const uint8_t *stl_lab_dev, const int *knn_id_dev, const double *knn_w_dev, int h, int w, int layer,
                        double local_weight, double alpha, double nonlocal_weight, int knum, double d_weight, int iters_out[3])
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, a_dev && b_dev && weight_dev && cnt_lab_dev && stl_lab_dev && knn_id_dev && knn_w_dev, "null pointer");
     NCT_REQUIRE(ctx, h > 0 && w > 0 && knum == 8, "bad size / only k = 8 neighbours supported (CT/Config.h:69)");
     const int n = h * w, n3 = 3 * n;
@@ -671,7 +671,7 @@ int nct_solve_nonlocal(nct_ctx *ctx, double *a_dev, double *b_dev, const double 
 int nct_solve_wls_jacobi(nct_ctx *ctx, double *a_dev, double *b_dev, const double *rough_dev, const uint8_t *cnt_lab_full_dev, int H,
                   int W, double lam, double alpha, double rel_tol, int max_iters, int *iters_out, double *rel_res_out)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, a_dev && b_dev && rough_dev && cnt_lab_full_dev && H > 0 && W > 0, "bad arguments");
     if (rel_tol <= 0) rel_tol = 1e-10;
     if (max_iters <= 0) max_iters = 50000;

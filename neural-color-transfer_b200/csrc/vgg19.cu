@@ -243,7 +243,7 @@ int nct_vgg19_layer_shape(int layer, int *cin, int *cout)
 
 int nct_vgg19_set_weights(nct_ctx *ctx, int layer, const float *w_oihw_host, const float *bias_host)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, layer >= 0 && layer < 13 && w_oihw_host && bias_host, "bad arguments");
     if (!ctx->vgg) ctx->vgg = new VggState();
     const int cin = kTrunk[layer].cin, cout = kTrunk[layer].cout;
@@ -276,7 +276,7 @@ int nct_vgg19_set_weights(nct_ctx *ctx, int layer, const float *w_oihw_host, con
 
 int nct_vgg19_set_engine(nct_ctx *ctx, int engine)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, engine >= 0 && engine <= 2, "engine must be 0 (FP32 CUDA cores), 1 (tcgen05 TF32) or 2 (tcgen05 3xTF32)");
     if (!ctx->vgg) ctx->vgg = new VggState();
     ctx->vgg->engine = engine;
@@ -300,7 +300,7 @@ int nct_vgg19_level_dims(int h, int w, int dims[5][3])
 
 int nct_vgg19_features(nct_ctx *ctx, const uint8_t *bgr_dev, int h, int w, int deepest_level, float *feat_dev[5])
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, bgr_dev && feat_dev && h >= 16 && w >= 16, "bad arguments (image must be at least 16 x 16)");
     NCT_REQUIRE(ctx, deepest_level >= 0 && deepest_level <= 4, "deepest_level must be in [0, 4] (0 = conv5_1)");
     VggState *v = ctx->vgg;

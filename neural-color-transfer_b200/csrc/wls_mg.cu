@@ -755,7 +755,7 @@ extern "C" {
 int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *rough_dev, const uint8_t *cnt_lab_full_dev, int H,
                   int W, double lam, double alpha, double rel_tol, int max_iters, int *iters_out, double *rel_res_out)
 {
-    if (!ctx) return NCT_ERR_ARG;
+    NCT_ENTER(ctx);
     NCT_REQUIRE(ctx, a_dev && b_dev && rough_dev && cnt_lab_full_dev && H > 0 && W > 0, "bad arguments");
     if (rel_tol <= 0) rel_tol = 1e-10;
     if (max_iters <= 0) max_iters = 2000;

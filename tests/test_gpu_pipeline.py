@@ -124,6 +124,27 @@ def test_pipeline_end_to_end_against_independent_canonical_oracle(pctx, dev, wei
     assert ps >= 50.0
 
 
+@pytest.mark.parametrize("side", [700, 1000])
+def test_full_size_pairs_are_deterministic_across_runs_and_contexts(pkg, pctx, dev, weights, side):
+    """BASELINE configs[1] / configs[3] sizes (the oracle is too slow there): size-independent properties -- the result is
+    bit-identical run to run and context to context (no atomics / races anywhere in the path), has the content's shape,
+    and moves the content's colour statistics towards the style's."""
+    cnt, stl = synth.pair(1, side, side)
+    pctx.set_vgg_engine(2)
+    a = pctx.transfer_pair(cnt, stl)
+    b = pctx.transfer_pair(cnt, stl)
+    other = pkg.Context(0)
+    other.load_vgg19_weights(weights)
+    other.set_vgg_engine(2)
+    c = other.transfer_pair(cnt, stl)
+    other.close()
+    pctx.set_vgg_engine(0)
+    assert a.shape == cnt.shape and a.dtype == np.uint8
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    m = lambda x: x.reshape(-1, 3).astype(np.float64).mean(0)  # noqa: E731
+    assert np.abs(m(a) - m(stl)).sum() < np.abs(m(cnt) - m(stl)).sum()
+
+
 def test_pipeline_host_and_device_entry_points_agree_and_are_deterministic(pctx, dev):
     cnt, stl = synth.pair(5, 96, 128, 128, 96)
     a = pctx.transfer_pair(cnt, stl)
