@@ -46,7 +46,7 @@ int clamp_size(nct_ctx *ctx, uint8_t *&img, int &h, int &w)
     uint8_t *out = (uint8_t *)malloc((size_t)chh * cw * 3);
     if (!out) return NCT_ERR_NOMEM;
     NCT_CUDA(ctx, cudaMemcpyAsync(out, d_dst, (size_t)chh * cw * 3, cudaMemcpyDeviceToHost, ctx->stream));
-    NCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NCT_CUDA(ctx, nct_stream_wait(ctx));
     nct_png_free(img);
     img = out;
     h = chh;

@@ -17,6 +17,17 @@ int nct_fail(nct_ctx *ctx, int code, const char *fmt, ...)
     return code;
 }
 
+cudaError_t nct_stream_wait(nct_ctx *ctx)
+{
+    if (!ctx->wait_event) {
+        cudaError_t e = cudaEventCreateWithFlags(&ctx->wait_event, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(ctx->wait_event, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->wait_event);
+}
+
 void *nct_scratch(nct_ctx *ctx, const char *name, size_t bytes)
 {
     NctBuffer &b = ctx->scratch[name];
@@ -203,6 +214,7 @@ int nct_destroy(nct_ctx *ctx)
     nct_vgg_free(ctx);
     for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     for (auto &e : ctx->prof_pool) cudaEventDestroy(e);
+    if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);
     for (auto &kv : ctx->scratch)
         if (kv.second.ptr) cudaFree(kv.second.ptr);
     if (ctx->pm_counters) cudaFree(ctx->pm_counters);

@@ -21,6 +21,7 @@ struct nct_ctx {
     cudaStream_t stream = nullptr;
     std::string last_error;
     long long launches = 0;
+    cudaEvent_t wait_event = nullptr;  // cudaEventBlockingSync, see nct_stream_wait
 
     // named, grow-only device scratch buffers ("workspace arena"): no per-level
     // cudaMalloc/cudaFree on the hot path (the reference does ~12 per level,
@@ -55,6 +56,9 @@ struct nct_ctx {
 };
 
 int nct_fail(nct_ctx *ctx, int code, const char *fmt, ...);
+// Host wait for everything queued on ctx->stream WITHOUT spinning: a blocking-sync event, so that the many host
+// threads of a multi-pair / multi-GPU run (one per context) sleep instead of burning a core each while they wait.
+cudaError_t nct_stream_wait(nct_ctx *ctx);
 // returns device pointer of at least `bytes` bytes, stable until a larger request under the same name
 void *nct_scratch(nct_ctx *ctx, const char *name, size_t bytes);
 

@@ -207,7 +207,7 @@ int nct_transfer_pair(nct_ctx *ctx, const uint8_t *cnt_bgr_host, int ch, int cw,
     int rc = nct_transfer_pair_dev(ctx, dC, ch, cw, dS, sh, sw, cfg, dO);
     if (rc) return rc;
     NCT_CUDA(ctx, cudaMemcpyAsync(out_bgr_host, dO, nC, cudaMemcpyDeviceToHost, ctx->stream));
-    NCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NCT_CUDA(ctx, nct_stream_wait(ctx));
     return NCT_OK;
 }
 

@@ -662,7 +662,7 @@ int nct_solve_nonlocal(nct_ctx *ctx, double *a_dev, double *b_dev, const double 
     if (iters_out) {
         NlScalars hs;
         NCT_CUDA(ctx, cudaMemcpyAsync(&hs, sc, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
-        NCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        NCT_CUDA(ctx, nct_stream_wait(ctx));
         for (int c = 0; c < 3; ++c) iters_out[c] = hs.iters[c];
     }
     return NCT_OK;
@@ -706,7 +706,7 @@ int nct_solve_wls_jacobi(nct_ctx *ctx, double *a_dev, double *b_dev, const doubl
     double worst = 0.0;
     while (!done) {
         NCT_CUDA(ctx, cudaMemcpyAsync(&hs, sc, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
-        NCT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        NCT_CUDA(ctx, nct_stream_wait(ctx));
         worst = 0.0;
         for (int k = 0; k < 6; ++k) {
             const double rel = hs.bb[k] > 0.0 ? sqrt(hs.rr[k] / hs.bb[k]) : (hs.rr[k] > 0.0 ? 1.0 : 0.0);
