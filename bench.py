@@ -165,6 +165,7 @@ def run_ours(args):
     pairs = [[synth.pair((rank * P + j) * npairs + q, side, side) for q in range(npairs)] for j in range(P)]
     dev_pairs = [[(torch.from_numpy(c).to(dev), torch.from_numpy(s).to(dev)) for c, s in pj] for pj in pairs]
     pin_pairs = [[(torch.from_numpy(c).pin_memory(), torch.from_numpy(s).pin_memory()) for c, s in pj] for pj in pairs]
+    torch.cuda.synchronize(dev)  # inputs resident before any context stream touches them
     out_dev = torch.empty((K, P, side, side, 3), dtype=torch.uint8, device=dev)
     out_pin = [torch.empty((side, side, 3), dtype=torch.uint8).pin_memory() for _ in range(P)]
     gather_list = [torch.empty_like(out_dev) for _ in range(world)] if (world > 1 and rank == 0) else None

@@ -11,7 +11,9 @@ pytestmark = pytest.mark.gpu
 def to_dev(x, dev):
     import torch
 
-    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    torch.cuda.synchronize()  # libnct contexts run on their own non-blocking stream: the copy must have landed
+    return t
 
 
 @pytest.mark.parametrize("h,w,Cn,seed", [(44, 44, 512, 1), (63, 63, 512, 2), (16, 16, 512, 3), (33, 22, 512, 4), (20, 20, 64, 5)])

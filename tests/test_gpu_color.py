@@ -13,7 +13,9 @@ REL_TOL = 1e-4
 def to_dev(x, dev):
     import torch
 
-    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    torch.cuda.synchronize()  # libnct contexts run on their own non-blocking stream: the copy must have landed
+    return t
 
 
 def relerr(x, ref):

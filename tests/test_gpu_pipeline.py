@@ -11,7 +11,9 @@ pytestmark = pytest.mark.gpu
 def to_dev(x, dev):
     import torch
 
-    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    torch.cuda.synchronize()  # libnct contexts run on their own non-blocking stream: the copy must have landed
+    return t
 
 
 @pytest.fixture(scope="module")
@@ -234,11 +236,11 @@ def test_caffemodel_v2_records_load_too(pkg, dev, weights, tmp_path):
     c.load_caffemodel(p)
     img, _ = synth.pair(0, 64, 64)
     import torch
-    a = c.predict(torch.from_numpy(img).to(dev), 0)
+    a = c.predict(to_dev(img, dev), 0)
     c.synchronize()
     c2 = pkg.Context(0)
     c2.load_vgg19_weights(weights)
-    b = c2.predict(torch.from_numpy(img).to(dev), 0)
+    b = c2.predict(to_dev(img, dev), 0)
     c2.synchronize()
     assert all(np.array_equal(x.cpu().numpy(), y.cpu().numpy()) for x, y in zip(a, b))
     with pytest.raises(pkg.NctError):

@@ -16,7 +16,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def to_dev(x, dev):
     import torch
 
-    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    torch.cuda.synchronize()  # libnct contexts run on their own non-blocking stream: the copy must have landed
+    return t
 
 
 def u32(t):
@@ -30,6 +32,7 @@ def run_gpu_pm(pkg, ctx, dev, na, nb, ah, aw, bh, bw, Cn, iters, rs, bidir=True,
     bnn = torch.empty(bh * bw, dtype=torch.int32, device=dev)
     annd = torch.zeros(ah * aw, dtype=torch.float32, device=dev)
     bnnd = torch.zeros(bh * bw, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()  # the fills run on torch's stream, PatchMatch on the context's
     if init is None:
         ctx.init_ann(ann, ah, aw, bh, bw)
         ctx.init_ann(bnn, bh, bw, ah, aw)
@@ -236,6 +239,7 @@ def test_bad_arguments_are_rejected(pkg, ctx, dev):
     t = torch.zeros(16 * 16 * 48, dtype=torch.float32, device=dev)
     ann = torch.zeros(256, dtype=torch.int32, device=dev)
     annd = torch.zeros(256, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
     with pytest.raises(pkg.NctError):  # C = 48 unsupported
         ctx.patchmatch_single(t, t, ann, annd, pkg.make_params(48, 16, 16, 16, 16))
     with pytest.raises(pkg.NctError):  # patch 5 unsupported (reference fixes 3, CT/Config.h:70)

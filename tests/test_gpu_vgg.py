@@ -10,7 +10,9 @@ pytestmark = pytest.mark.gpu
 def to_dev(x, dev):
     import torch
 
-    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    torch.cuda.synchronize()  # libnct contexts run on their own non-blocking stream: the copy must have landed
+    return t
 
 
 @pytest.fixture(scope="module")
@@ -89,7 +91,7 @@ def test_missing_weights_fail_loudly(pkg, dev):
 
     c = pkg.Context(0)
     with pytest.raises(pkg.NctError):
-        c.predict(torch.zeros((32, 32, 3), dtype=torch.uint8, device=dev))
+        c.predict(to_dev(np.zeros((32, 32, 3), np.uint8), dev))
     c.close()
 
 
