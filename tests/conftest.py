@@ -13,6 +13,24 @@ def pytest_configure(config):
 
 
 def _has_gpu():
+    """True on a GPU box.  A fresh box occasionally fails the very first CUDA initialisation of a process (seen once:
+    "CUDA driver initialization failed" in pytest, while the next process on the same box ran fine), and a failed
+    initialisation is cached by torch for the life of the process -- so when nvidia-smi is present, probe in short-lived
+    subprocesses first and only then initialise CUDA here."""
+    import shutil
+    import subprocess
+    import time
+
+    if shutil.which("nvidia-smi") is not None:
+        for _ in range(6):
+            try:
+                r = subprocess.run([sys.executable, "-c", "import torch,sys; sys.exit(0 if torch.cuda.is_available() and torch.zeros(1, device='cuda').item() == 0 else 1)"],
+                                   capture_output=True, timeout=180)
+                if r.returncode == 0:
+                    break
+            except Exception:
+                pass
+            time.sleep(5)
     try:
         import torch
 
