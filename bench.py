@@ -128,11 +128,14 @@ def run_reference(args):
 
 
 def run_ours(args):
+    import __graft_entry__ as g
+
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        g.wait_for_cuda()  # (a transient first-initialisation failure was seen once on a fresh box)
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    import __graft_entry__ as g
     from oracle import synth  # synthetic inputs only (numpy); no oracle compute on this path
 
     rank = int(os.environ.get("RANK", "0"))
