@@ -170,6 +170,14 @@ int nct_solve_nonlocal(nct_ctx *ctx, double *a_dev, double *b_dev, const double 
                        const double *knn_w_dev, int h, int w, int layer, double local_weight, double alpha,
                        double nonlocal_weight, int knum, double d_weight, int iters_out[3]);
 
+/* solve_ls_cg_gpu with its own argument list (CT/SparseSolver_GPU.cuh:12, CT/SparseSolver_GPU.cu:3-198), for callers
+ * that keep the reference's host assembly (CT/ColorTransfer.cpp:548-949): A is constraints x size in CSR with ONE-based
+ * rowindex / columns, every array on the HOST; x holds the start vector and receives the result; plain CG on
+ * A^T A x = A^T b, `while (r1 > tolerance^2 && k <= maxitrs)`.  A^T A is applied as A^T (A p), never formed.
+ * Synchronous (x is a host result).  iters_out (may be NULL) receives the number of iterations done. */
+int nct_solve_ls_cg(nct_ctx *ctx, int size, int constraints, const double *A, const int *columns, const int *rowindex,
+                    double *x, const double *b, int nonzeros, double tolerance, int maxitrs, int *iters_out);
+
 /* upsample_color_coefficients_bilinear (CT/ColorTransfer.cpp:457-490): level -> full size + roughness map */
 int nct_upsample_coefficients(nct_ctx *ctx, const double *a_lvl_dev, const double *b_lvl_dev, int h, int w,
                               const uint8_t *cnt_lab_full_dev, int H, int W, double *a_full_dev, double *b_full_dev,

@@ -65,6 +65,7 @@ ABI = {
     "nct_local_fit": (_i, [c_ctx_p, _p, _p, _i, _i, _d, _p, _p]),
     "nct_confidence_weights": (_i, [c_ctx_p, _p, _i, _p]),
     "nct_solve_nonlocal": (_i, [c_ctx_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _d, _d, _d, _i, _d, C.POINTER(_i)]),
+    "nct_solve_ls_cg": (_i, [c_ctx_p, _i, _i, _p, _p, _p, _p, _p, _i, _d, _i, C.POINTER(_i)]),
     "nct_upsample_coefficients": (_i, [c_ctx_p, _p, _p, _i, _i, _p, _i, _i, _p, _p, _p]),
     "nct_solve_wls": (_i, [c_ctx_p, _p, _p, _p, _p, _i, _i, _d, _d, _d, _i, C.POINTER(_i), C.POINTER(_d)]),
     "nct_solve_wls_jacobi": (_i, [c_ctx_p, _p, _p, _p, _p, _i, _i, _d, _d, _d, _i, C.POINTER(_i), C.POINTER(_d)]),
@@ -396,6 +397,21 @@ class Context:
                                                 _ptr(knn_id), _ptr(knn_w), h, w, layer, local_weight, alpha,
                                                 nonlocal_weight, knum, d_weight, its if want_iters else None))
         return list(its) if want_iters else None
+
+    def solve_ls_cg(self, size, constraints, A, columns, rowindex, x, b, tolerance=1e-6, maxitrs=100):
+        """solve_ls_cg_gpu (CT/SparseSolver_GPU.cu:3-198) with its own argument list: HOST numpy arrays, one-based CSR
+        (A float64[nnz], columns / rowindex int32), x float64[size] updated in place.  Returns the iteration count."""
+        import numpy as np
+
+        A = np.ascontiguousarray(A, np.float64)
+        columns = np.ascontiguousarray(columns, np.int32)
+        rowindex = np.ascontiguousarray(rowindex, np.int32)
+        b = np.ascontiguousarray(b, np.float64)
+        assert x.dtype == np.float64 and x.flags["C_CONTIGUOUS"] and x.shape == (size,)
+        its = _i(0)
+        self._check(self.lib.nct_solve_ls_cg(self.h, size, constraints, A.ctypes.data, columns.ctypes.data, rowindex.ctypes.data,
+                                             x.ctypes.data, b.ctypes.data, int(A.shape[0]), tolerance, maxitrs, C.byref(its)))
+        return int(its.value)
 
     def upsample_coefficients(self, a_lvl, b_lvl, cnt_lab_full):
         import torch

@@ -128,6 +128,50 @@ def test_solve_nonlocal(ctx, dev, h, w, layer, dwt):
     assert worst < 5e-3
 
 
+def test_solve_ls_cg_with_the_reference_argument_list(pkg, ctx):
+    """nct_solve_ls_cg = solve_ls_cg_gpu's own signature (CT/SparseSolver_GPU.cuh:12): host arrays, one-based CSR of
+    the explicit constraint matrix the reference assembles (here: oracle assemble_nonlocal), x0 in / x out.  Against the
+    scipy restatement of the same loop: same iteration count; a few iterations agree to rounding, the full 100 to the
+    band the un-converged iterate is defined to."""
+    rng = np.random.default_rng(7)
+    h, w = 24, 20
+    n = h * w
+    cnt, stl = synth.pair(2, h, w)
+    cl, sl = color.bgr2lab_u8(cnt), color.bgr2lab_u8(stl)
+    ids, kw = rand_knn(rng, n)
+    weight = np.maximum(rng.random((h, w)), 1e-6)
+    a0, b0 = color.local_fit(cl, sl, 0.6)
+    A, B = color.assemble_nonlocal(weight, cl * (1.0 / 255.0), sl * (1.0 / 255.0), ids, kw, d_weight=16.0)
+    for c in range(3):
+        M = A[c].tocsr()
+        M.sort_indices()
+        rows, size = M.shape
+        x0 = np.concatenate([a0[..., c].ravel(), b0[..., c].ravel()])
+        for maxit, tol in ((5, 1e-9), (100, 5e-3)):
+            x = x0.copy()
+            its = ctx.solve_ls_cg(size, rows, M.data, M.indices + 1, M.indptr + 1, x, B[c], 1e-6, maxit)
+            ox, oits = color.cg_normal_equations(M, B[c], x0, 1e-6, maxit)
+            assert its == oits == maxit
+            assert relerr(x, ox) < tol, f"channel {c}, {maxit} iterations: {relerr(x, ox):.2e}"
+    # a small well-conditioned system: stops on the tolerance, at the least-squares solution
+    import scipy.sparse as sp
+
+    M = sp.vstack([sp.identity(30), sp.random(90, 30, density=0.1, random_state=3)]).tocsr()
+    M.sort_indices()
+    bb = rng.standard_normal(120)
+    x = np.zeros(30)
+    its = ctx.solve_ls_cg(30, 120, M.data, M.indices + 1, M.indptr + 1, x, bb, 1e-8, 100)
+    ox, oits = color.cg_normal_equations(M, bb, np.zeros(30), 1e-8, 100)
+    assert 0 < its < 100 and abs(its - oits) <= 1
+    assert relerr(x, np.linalg.lstsq(M.toarray(), bb, rcond=None)[0]) < 1e-7
+    # zero iterations when the start vector already satisfies the tolerance
+    x2 = x.copy()
+    assert ctx.solve_ls_cg(30, 120, M.data, M.indices + 1, M.indptr + 1, x2, bb, 1e-3, 100) == 0 and np.array_equal(x2, x)
+    # zero-based indices are rejected (the reference's arrays are one-based, CUSPARSE_INDEX_BASE_ONE)
+    with pytest.raises(pkg.NctError):
+        ctx.solve_ls_cg(30, 120, M.data, M.indices, M.indptr, x, bb, 1e-8, 10)
+
+
 @pytest.mark.parametrize("h,w,H,W", [(44, 44, 700, 700), (30, 25, 120, 100), (64, 64, 64, 64)])
 def test_upsample_roughness_apply_bit_exact(ctx, dev, h, w, H, W):
     rng = np.random.default_rng(H)
