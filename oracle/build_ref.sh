@@ -59,4 +59,33 @@ extern "C" int ref_dist_device(float *a1, float *b1, int channels, int a_rows, i
 EOT
 } > "$TMP/ref_dist_dev.cu"
 nvcc -O3 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -shared -o "$HERE/_ref/libref_dist_dev.so" "$TMP/ref_dist_dev.cu" -lcudart_static -lpthread -ldl -lrt
-echo "built $HERE/_ref/libref_dist.so libref_dist_dev.so from $SRC"
+# the reference's PatchMatch kernel itself (patchmatch_single, :677-831, with its helpers :9-66, :355-405, :461-488,
+# :505-515), verbatim, launched with the reference's geometry (24 x 24 blocks, NCT/main.cu:196-201, CT/Config.h:4) on
+# planar CHW volumes.  It is racy by construction (both __syncthreads are commented out), so it is used for
+# STATISTICAL agreement with the deterministic restatement (tests/test_oracle_ref.py), not for bit-level parity.
+{
+  echo '#include <climits>'
+  echo '#include <cfloat>'
+  echo '#include <cuda_runtime.h>'
+  echo '#include <curand_kernel.h>'
+  sed -n '9,66p' "$SRC"
+  sed -n '355,405p' "$SRC"
+  sed -n '461,488p' "$SRC"
+  sed -n '505,515p' "$SRC"
+  sed -n '677,831p' "$SRC"
+  cat <<'EOT'
+extern "C" int ref_patchmatch_device(float *a1_chw_dev, float *b1_chw_dev, unsigned int *ann_dev, float *annd_dev, const int *params_host)
+{
+    int *dparams = 0;
+    if (cudaMalloc(&dparams, 11 * sizeof(int)) != cudaSuccess) return -1;
+    cudaMemcpy(dparams, params_host, 11 * sizeof(int), cudaMemcpyHostToDevice);
+    dim3 block(24, 24), grid(params_host[2] / 24 + 1, params_host[1] / 24 + 1);
+    patchmatch_single<<<grid, block>>>(a1_chw_dev, b1_chw_dev, (float *)0, ann_dev, annd_dev, dparams);
+    int rc = (int)cudaDeviceSynchronize();
+    cudaFree(dparams);
+    return rc;
+}
+EOT
+} > "$TMP/ref_pm_dev.cu"
+nvcc -O3 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -shared -o "$HERE/_ref/libref_pm_dev.so" "$TMP/ref_pm_dev.cu" -lcudart_static -lpthread -ldl -lrt
+echo "built $HERE/_ref/libref_dist.so libref_dist_dev.so libref_pm_dev.so from $SRC"

@@ -87,3 +87,55 @@ def test_restated_distance_equals_reference_device_code(dev):
     got = out.cpu().numpy()
     mine = np.array([oracle.dist_ref_chw(a, b, *map(int, q[i]), use_fma=1) for i in range(nq)], np.float32)
     assert np.array_equal(got.view(np.uint32), mine.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_deterministic_patchmatch_agrees_statistically_with_the_verbatim_reference_kernel(pkg, ctx, dev):
+    """The reference's own patchmatch_single (compiled verbatim, racy by construction: both __syncthreads are commented
+    out, NCT/GeneralizedPatchMatch.cu:801,828) on the same B200 and the same inputs as the deterministic restatement
+    (BASELINE config 5 geometry: 256 x 128 x 128, B = A shifted by (+7, -3) + noise, 10 iterations).  Bit-level equality
+    is not defined against a racy kernel; what is: both find the same field where the answer is
+    unambiguous, and the restatement's matching energy is as good as the reference's."""
+    import torch
+
+    p = os.path.join(REF, "libref_pm_dev.so")
+    if not os.path.exists(p):
+        pytest.skip("oracle/_ref/libref_pm_dev.so not built")
+    L = C.CDLL(p)
+    Cn, H, W = 256, 128, 128
+    a, b = synth.pm_sweep_volumes(Cn, H, W)
+    na, nb = oracle.l2norm_hwc(a), oracle.l2norm_hwc(b)
+    params = oracle.make_params(Cn, H, W, H, W, iters=10, rs_max=8)
+    # the reference kernel: planar CHW volumes, its own launch geometry
+    a_chw = torch.from_numpy(np.ascontiguousarray(na.transpose(2, 0, 1))).to(dev)
+    b_chw = torch.from_numpy(np.ascontiguousarray(nb.transpose(2, 0, 1))).to(dev)
+    r_ann = torch.from_numpy(oracle.nnf_init(H, W, H, W).view(np.int32)).to(dev)
+    r_annd = torch.zeros(H * W, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    hp = np.ascontiguousarray(params, np.int32)
+    assert L.ref_patchmatch_device(C.c_void_p(a_chw.data_ptr()), C.c_void_p(b_chw.data_ptr()), C.c_void_p(r_ann.data_ptr()),
+                                   C.c_void_p(r_annd.data_ptr()), hp.ctypes.data_as(C.c_void_p)) == 0
+    ref_ann = r_ann.cpu().numpy().view(np.uint32)
+    ref_annd = r_annd.cpu().numpy()
+    # the product: pixel-major volumes through the C ABI
+    ta, tb = torch.from_numpy(na).to(dev), torch.from_numpy(nb).to(dev)
+    g_ann = torch.from_numpy(oracle.nnf_init(H, W, H, W).view(np.int32)).to(dev)
+    g_annd = torch.zeros(H * W, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    ctx.patchmatch_single(ta, tb, g_ann, g_annd, pkg.make_params(Cn, H, W, H, W, iters=10, rs_max=8))
+    ctx.synchronize()
+    our_ann = g_ann.cpu().numpy().view(np.uint32)
+    our_annd = g_annd.cpu().numpy()
+    same = float((our_ann == ref_ann).mean())
+    ratio = float(our_annd.mean() / ref_annd.mean())  # both negative: > 1 means the restatement's energy is lower (better)
+    gx, gy = np.meshgrid(np.arange(W), np.arange(H))
+    inner = ((gx.ravel() + 7 < W) & (gy.ravel() - 3 >= 0))
+    truth = (((gy.ravel() - 3) << 12) | (gx.ravel() + 7)).astype(np.uint32)
+    ref_ok = float((ref_ann == truth)[inner].mean())
+    our_ok = float((our_ann == truth)[inner].mean())
+    print(f"verbatim reference kernel vs deterministic restatement: identical entries {100 * same:.2f} %, "
+          f"mean(annd) ours / reference {ratio:.5f}, ground-truth shift recovered: reference {100 * ref_ok:.2f} %, ours {100 * our_ok:.2f} %")
+    assert np.isfinite(ref_annd).all() and np.isfinite(our_annd).all()
+    assert our_ok > 0.99 and ref_ok > 0.95
+    assert same > 0.85
+    assert ratio > 0.98  # within 2 % of (or better than) the reference's mean matching energy
