@@ -126,6 +126,23 @@ def test_pipeline_end_to_end_against_independent_canonical_oracle(pctx, dev, wei
     assert ps >= 50.0
 
 
+def test_pipeline_reproduces_the_committed_end_to_end_golden_images(pctx):
+    """tests/golden/e2e_golden.npz holds the canonical oracle's final images for two small pairs (generated on the CPU by
+    tests/golden/make_e2e_golden.py and checked there by tests/test_oracle_pipeline.py): the GPU pipeline with the FP32
+    convolution engine reproduces them byte for byte, without the oracle in the loop."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "e2e_golden.npz"))
+    pctx.set_vgg_engine(0)
+    for i, (seed, ch, cw, sh, sw) in enumerate(g["cases"]):
+        cnt, stl = synth.pair(int(seed), int(ch), int(cw), int(sh), int(sw))
+        out = pctx.transfer_pair(cnt, stl)
+        ref = g[f"case{i}_out"]
+        ps = pipeline.psnr(out, ref)
+        print(f"golden case {i}: PSNR {ps:.1f} dB, {int((out != ref).sum())} of {out.size} bytes differ")
+        assert ps >= 50.0
+
+
 @pytest.mark.parametrize("side", [700, 1000])
 def test_full_size_pairs_are_deterministic_across_runs_and_contexts(pkg, pctx, dev, weights, side):
     """BASELINE configs[1] / configs[3] sizes (the oracle is too slow there): size-independent properties -- the result is

@@ -73,3 +73,25 @@ def test_final_image_is_only_defined_to_about_40_dB_by_the_reference_arithmetic(
     assert 30.0 < p_ulp < 50.0 and 30.0 < p_can < 50.0
     # and the canonical run is reproducible
     assert np.array_equal(r_can, pipeline.transfer_pair(cnt, stl, None, features_fn=ff, cg_mode="canonical"))
+
+
+def test_end_to_end_golden_fixture_is_reproduced_by_the_canonical_oracle():
+    """tests/golden/e2e_golden.npz (tests/golden/make_e2e_golden.py): final image, per-level checksums of the NNFs, the
+    BDS reconstruction, the neighbour lists and the intermediate images, and the CG iteration counts of two small pairs."""
+    import importlib.util
+    import os
+    import zlib
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_e2e_golden", os.path.join(here, "make_e2e_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = np.load(os.path.join(here, "e2e_golden.npz"))
+    w = synth.vgg19_weights(19)
+    assert [tuple(int(v) for v in c) for c in g["cases"]] == gen.CASES
+    i = 0  # one case keeps the CPU suite short; the GPU suite checks both
+    out, levels = gen.run(*gen.CASES[i], w)
+    crc = np.array([[levels[l][k] for k in ("ann", "bnn", "sml", "knn", "img")] for l in range(5)], np.uint32)
+    assert np.array_equal(crc, g[f"case{i}_crc"]), "an oracle stage changed its result"
+    assert np.array_equal(np.array([levels[l]["cg_iters"] for l in range(5)], np.int32), g[f"case{i}_cg_iters"])
+    assert np.array_equal(out, g[f"case{i}_out"]) and zlib.crc32(out.tobytes()) == zlib.crc32(g[f"case{i}_out"].tobytes())
