@@ -96,8 +96,9 @@ int nct_nnf_upsample(nct_ctx *ctx, const uint32_t *ann_half_dev, int ah_half, in
 /* Replaces patchmatch_single<<<>>>(a1, b1, NULL, ann, annd, params),
  * NCT/GeneralizedPatchMatch.cu:677-831.  `params` is the reference's 11-int HOST array
  * {C, ah, aw, bh, bw, patch_w(=3), iters, rs_max, flag_constraint(=0), constraint, energy}
- * (NCT/main.cu:204-214).  a/b are L2-normalised HWC volumes.  ann in/out, annd out.
- * Deterministic jump-flood schedule: bit-exact vs oracle/pm_oracle.c. */
+ * (NCT/main.cu:204-214).  a/b are L2-normalised HWC volumes.  ann in/out, annd out.  iters in [0, 31] (the
+ * reference uses 10), C in {16, 32, 64, 128, 256, 512}, sides <= 4096 (12-bit packing).
+ * Deterministic jump-flood schedule (decisions D1-D4): bit-exact vs oracle/pm_oracle.c. */
 int nct_patchmatch(nct_ctx *ctx, const float *a_hwc_dev, const float *b_hwc_dev,
                    uint32_t *ann_dev, float *annd_dev, const int params[11]);
 
@@ -213,9 +214,11 @@ int nct_vgg19_layer_shape(int layer, int *cin, int *cout);
 /* Caffe blob layout: weights O x I x 3 x 3, bias O (host pointers). Replaces Net::CopyTrainedLayersFrom
  * (caffe/net.cpp:798) for one layer. */
 int nct_vgg19_set_weights(nct_ctx *ctx, int layer, const float *w_oihw_host, const float *bias_host);
-/* Convolution engine: 0 = FP32 on CUDA cores (exact FP32 products, fixed summation order; default),
- * 1 = tcgen05 tensor cores, kind::tf32 operands from TMA-staged shared memory, FP32 accumulation in TMEM
- * (layers with Cin >= 64; conv1_1 always runs on CUDA cores). */
+/* Convolution engine: 0 = FP32 on CUDA cores (exact FP32 products, fixed summation order: bit-exact vs
+ * oracle/conv_oracle.c; the default of a new context), 1 = tcgen05 tensor cores, kind::tf32 operands from TMA-staged
+ * shared memory, FP32 accumulation in TMEM (~1e-2 of the feature range after 13 layers), 2 = the same with the
+ * 3xTF32 hi/lo operand split (FP32-accurate, ~2e-4 of the feature range; the CLI's and bench.py's default).
+ * Tensor-core engines cover the layers with Cin >= 64; conv1_1 always runs on CUDA cores. */
 int nct_vgg19_set_engine(nct_ctx *ctx, int engine);
 /* Feature-map sizes {C, H, W} per level for an h x w image under Caffe's ceil-mode pooling
  * (caffe/layers/pooling_layer.cpp:90-93); replaces the Dim outputs of Classifier::Predict (NCT/Classifier.h:30-43). */
