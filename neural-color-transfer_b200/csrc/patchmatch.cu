@@ -882,9 +882,15 @@ struct TQueryState {
     float dbest;
 };
 
-template <int C, bool HALF, bool AS = false>
-__global__ void __launch_bounds__(128, HALF ? (AS ? (C == 64 ? 6 : 5) : 4) : 2) pm_step_t_kernel(const PMStep s, const int tile)
+// SPEC = true (experimental, NCT_PM_SPEC=1, C = 64 only; not yet measured): while candidate i is being reduced, the rows
+// of candidate i + 1 are already in flight -- the next propagation candidate is known, the next random-search candidate
+// is computed from the CURRENT best, i.e. assuming candidate i is rejected (the common case).  The position is
+// recomputed after the acceptance test as usual and the prefetched rows are only used if it still matches, so the
+// result is unchanged; a wrong guess costs one wasted set of loads.
+template <int C, bool HALF, bool AS = false, bool SPEC = false>
+__global__ void __launch_bounds__(128, SPEC ? 3 : (HALF ? (AS ? (C == 64 ? 6 : 5) : 4) : 2)) pm_step_t_kernel(const PMStep s, const int tile)
 {
+    static_assert(!SPEC || (HALF && C == 64 && !AS), "the speculative variant exists for C = 64 only");
     using T = UTraits<C, HALF>;
     __shared__ TQueryState st_all[4][32];
     __shared__ float4 a_sm[AS ? 128 * 9 * T::NV : 1];  // [group of the block][vector][lane of the group]
@@ -1007,36 +1013,118 @@ __global__ void __launch_bounds__(128, HALF ? (AS ? (C == 64 ? 6 : 5) : 4) : 2) 
             }
         }
         const float *u = D.rng + (size_t)ax * D.ndraws + (size_t)s.iter * 2 * D.n_mag;
-#pragma unroll 1
-        for (int i = 0; i < total; ++i) {
-            int cx, cy;
-            const bool is_rand = i >= n_prop_end;
-            if (!is_rand) {
-                const int k = i - n_first;
-                const uint32_t cv = (i < n_first) ? v0 : (k == 0 ? q0.c0 : (k == 1 ? q0.c1 : (k == 2 ? q0.c2 : q0.c3)));
-                cx = int_to_x(cv);
-                cy = int_to_y(cv);
-                if (i < n_first) n_ref += (j == 0);
-            } else {
-                const int m = i - n_prop_end;
-                const int mag = D.rs_start >> m;
-                const int xmin = max(xbest - mag, 0), xmax = min(xbest + mag + 1, bw);
-                const int ymin = max(ybest - mag, 0), ymax = min(ybest + mag + 1, bh);
-                const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
-                const int wx = xmax - xmin, wy = ymax - ymin;
-                const int tx = (int)(__fmul_rn(u1, (float)wx)), ty = (int)(__fmul_rn(u2, (float)wy));
-                cx = xmin + (tx >= wx ? tx - wx : tx);
-                cy = ymin + (ty >= wy ? ty - wy : ty);
-                n_ref += (j == 0);
-                if (cx == xbest && cy == ybest) continue;  // D3
+        if (SPEC) {
+            // candidate i of this query: propagation list entry, or the random-search draw around (xb, yb)
+            auto candidate = [&](int i, int xb, int yb, int &cx, int &cy) {
+                if (i < n_prop_end) {
+                    const int k = i - n_first;
+                    const uint32_t cv = (i < n_first) ? v0 : (k == 0 ? q0.c0 : (k == 1 ? q0.c1 : (k == 2 ? q0.c2 : q0.c3)));
+                    cx = int_to_x(cv);
+                    cy = int_to_y(cv);
+                } else {
+                    const int m = i - n_prop_end;
+                    const int mag = D.rs_start >> m;
+                    const int xmin = max(xb - mag, 0), xmax = min(xb + mag + 1, bw);
+                    const int ymin = max(yb - mag, 0), ymax = min(yb + mag + 1, bh);
+                    const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
+                    // (int)(u * w) % w with u in (0, 1]: the product is in [0, w], so the modulo only maps w to 0
+                    const int wx = xmax - xmin, wy = ymax - ymin;
+                    const int tx = (int)(__fmul_rn(u1, (float)wx)), ty = (int)(__fmul_rn(u2, (float)wy));
+                    cx = xmin + (tx >= wx ? tx - wx : tx);
+                    cy = ymin + (ty >= wy ? ty - wy : ty);
+                }
+            };
+            float4 pref[SPEC ? 9 : 1];  // rows of the speculatively fetched next candidate
+            bool have_pref = false;
+            int pcx = -1, pcy = -1;
+    #pragma unroll 1
+            for (int i = 0; i < total; ++i) {
+                int cx, cy;
+                const bool is_rand = i >= n_prop_end;
+                candidate(i, xbest, ybest, cx, cy);
+                if (!is_rand) {
+                    if (i < n_first) n_ref += (j == 0);
+                } else {
+                    n_ref += (j == 0);
+                    if (cx == xbest && cy == ybest) continue;  // D3
+                }
+                n_eval += (j == 0);
+                float d;
+                if (SPEC && (q.amask & patch_mask(cx, cy, bw, bh)) == 0x1FFu) {
+                    float4 bv[9];
+                    if (have_pref && pcx == cx && pcy == cy) {
+    #pragma unroll
+                        for (int pi = 0; pi < 9; ++pi) bv[pi] = pref[SPEC ? pi : 0];
+                    } else {
+                        const float *b_base = D.b + ((size_t)cy * bw + cx) * C + j * 4;
+                        const float *rb[3] = {b_base - (ptrdiff_t)bw * C, b_base, b_base + (ptrdiff_t)bw * C};
+    #pragma unroll
+                        for (int pi = 0; pi < 9; ++pi) bv[pi] = ldg4(rb[pi / 3] + (pi % 3 - 1) * C);
+                    }
+                    have_pref = false;
+                    if (i + 1 < total) {  // guess the next candidate assuming this one is rejected, and start its loads
+                        int ncx, ncy;
+                        candidate(i + 1, xbest, ybest, ncx, ncy);
+                        const bool skip = (i + 1 >= n_prop_end) && ncx == xbest && ncy == ybest;
+                        if (!skip && (q.amask & patch_mask(ncx, ncy, bw, bh)) == 0x1FFu) {
+                            const float *b_base = D.b + ((size_t)ncy * bw + ncx) * C + j * 4;
+                            const float *rb[3] = {b_base - (ptrdiff_t)bw * C, b_base, b_base + (ptrdiff_t)bw * C};
+    #pragma unroll
+                            for (int pi = 0; pi < 9; ++pi) pref[SPEC ? pi : 0] = ldg4(rb[pi / 3] + (pi % 3 - 1) * C);
+                            have_pref = true;
+                            pcx = ncx;
+                            pcy = ncy;
+                        }
+                    }
+                    float acc0 = 0.f, acc1 = 0.f;  // the interior path of u_eval (C = 64: even pixels -> acc0, odd -> acc1)
+    #pragma unroll
+                    for (int pi = 0; pi < 9; ++pi) {
+                        if (pi & 1) acc1 = fma4(q.a[(T::A_IN_REGS && !AS) ? pi : 0], bv[pi], acc1);
+                        else acc0 = fma4(q.a[(T::A_IN_REGS && !AS) ? pi : 0], bv[pi], acc0);
+                    }
+                    d = u_finish<C, HALF>(acc0, acc1, mask, 9);
+                } else {
+                    d = u_eval<C, HALF, AS>(q, D.b, cx, cy, bw, bh, j, mask);
+                }
+                const float dcmp = is_rand ? __fadd_rn(d, FLT_MIN) : d;
+                if (i < n_first || dcmp < dbest) {
+                    dbest = d;
+                    xbest = cx;
+                    ybest = cy;
+                }
             }
-            n_eval += (j == 0);
-            const float d = u_eval<C, HALF, AS>(q, D.b, cx, cy, bw, bh, j, mask);
-            const float dcmp = is_rand ? __fadd_rn(d, FLT_MIN) : d;
-            if (i < n_first || dcmp < dbest) {
-                dbest = d;
-                xbest = cx;
-                ybest = cy;
+        } else {
+    #pragma unroll 1
+            for (int i = 0; i < total; ++i) {
+                int cx, cy;
+                const bool is_rand = i >= n_prop_end;
+                if (!is_rand) {
+                    const int k = i - n_first;
+                    const uint32_t cv = (i < n_first) ? v0 : (k == 0 ? q0.c0 : (k == 1 ? q0.c1 : (k == 2 ? q0.c2 : q0.c3)));
+                    cx = int_to_x(cv);
+                    cy = int_to_y(cv);
+                    if (i < n_first) n_ref += (j == 0);
+                } else {
+                    const int m = i - n_prop_end;
+                    const int mag = D.rs_start >> m;
+                    const int xmin = max(xbest - mag, 0), xmax = min(xbest + mag + 1, bw);
+                    const int ymin = max(ybest - mag, 0), ymax = min(ybest + mag + 1, bh);
+                    const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
+                    const int wx = xmax - xmin, wy = ymax - ymin;
+                    const int tx = (int)(__fmul_rn(u1, (float)wx)), ty = (int)(__fmul_rn(u2, (float)wy));
+                    cx = xmin + (tx >= wx ? tx - wx : tx);
+                    cy = ymin + (ty >= wy ? ty - wy : ty);
+                    n_ref += (j == 0);
+                    if (cx == xbest && cy == ybest) continue;  // D3
+                }
+                n_eval += (j == 0);
+                const float d = u_eval<C, HALF, AS>(q, D.b, cx, cy, bw, bh, j, mask);
+                const float dcmp = is_rand ? __fadd_rn(d, FLT_MIN) : d;
+                if (i < n_first || dcmp < dbest) {
+                    dbest = d;
+                    xbest = cx;
+                    ybest = cy;
+                }
             }
         }
         if (j == 0) {
@@ -1101,7 +1189,9 @@ struct StepLauncher<C, true> {
             static const bool a_smem = getenv("NCT_PM_ASMEM") != nullptr;  // A/B: query patch in shared memory
             const int tile = pm_tile_size(s.nq_total, 148);
             const int blocks = nct_div_up(nct_div_up(s.nq_total, tile), 4);
-            if (a_smem) pm_step_t_kernel<C, true, true><<<blocks, 128, 0, st>>>(s, tile);
+            static const bool spec = getenv("NCT_PM_SPEC") != nullptr;     // experimental: speculative next-candidate fetch (C = 64)
+            if (spec && C == 64) pm_step_t_kernel<64, true, false, true><<<blocks, 128, 0, st>>>(s, tile);
+            else if (a_smem) pm_step_t_kernel<C, true, true><<<blocks, 128, 0, st>>>(s, tile);
             else pm_step_t_kernel<C, true><<<blocks, 128, 0, st>>>(s, tile);
         }
     }
