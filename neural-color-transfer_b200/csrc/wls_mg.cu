@@ -701,8 +701,8 @@ __global__ void __launch_bounds__(TPB) pcg_update_kernel(int n, double *__restri
 
 // optional in-stream trace of one PCG iteration (NCT_WLS_TRACE=1): an event after every launch, printed per kernel
 struct TraceRec { const char *name; int n; cudaEvent_t e; };
-static std::vector<TraceRec> g_tr;
-static bool g_tr_on = false;
+static thread_local std::vector<TraceRec> g_tr;  // (one context per host thread; the trace is a single-thread dev aid)
+static thread_local bool g_tr_on = false;
 #define TR(name, n)                                              \
     do {                                                         \
         if (g_tr_on) {                                           \
@@ -892,7 +892,7 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
         const int block = hs.iters == 0 ? 16 : (hs.iters == 16 ? 8 : check_every);
         for (int it = 0; it < block; ++it) {
             static const bool trace_env = getenv("NCT_WLS_TRACE") != nullptr;
-            static int trace_count = 0;
+            static thread_local int trace_count = 0;
             g_tr_on = trace_env && (++trace_count == 70);  // one iteration in the middle of the second solve
             TR("start", 0);
             int rc = vcycle(ctx, h, sc, partials, counter);
