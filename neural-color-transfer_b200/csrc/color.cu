@@ -13,6 +13,7 @@
 // gamma lookup tables, 11-bit fixed-point bilinear resize with the 2x2-area shortcut for exact 2:1
 // downscales, float-coefficient bilinear for 64F) and verified bit-for-bit against cv2 over all
 // 2^24 colours in tests/.  All kernels here are trivially HBM-bound streaming kernels.
+#include <mutex>
 #include "device_utils.cuh"
 #include <cmath>
 #include <cstring>
@@ -370,12 +371,9 @@ const LabTables *lab_tables(nct_ctx *ctx)
     if (it != ctx->scratch.end() && it->second.ptr) return (const LabTables *)it->second.ptr;
     void *d = nct_scratch(ctx, "lab_tables", sizeof(LabTables));
     if (!d) return nullptr;
-    static LabTables host;  // identical for every ctx
-    static bool built = false;
-    if (!built) {
-        build_lab_tables(host);
-        built = true;
-    }
+    static LabTables host;  // identical for every ctx; contexts may be driven from several host threads at once
+    static std::once_flag built;
+    std::call_once(built, [] { build_lab_tables(host); });
     if (cudaMemcpyAsync(d, &host, sizeof(LabTables), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return nullptr;
     cudaStreamSynchronize(ctx->stream);
     return (const LabTables *)d;
