@@ -34,10 +34,14 @@
  *   D3  Candidates equal to the entry's value at step start or to an earlier
  *       candidate of the same step are not re-evaluated (provably the same result:
  *       acceptance needs d < dbest strictly).  Both counts are reported.
- *   D4  NNF upsample uses fmaf for `ax + (bxh-axh)*ratio` (what nvcc's default
- *       -fmad=true emits for the reference's device code, :571-572).
+ *   D4  Unchanged-source skip: a propagation candidate whose source entry has not
+ *       changed since the same (query, jump, direction) slot last judged it is not
+ *       re-evaluated (it would be rejected again); details at orc_patchmatch_opts.
+ *       Like D3 it cannot change the field, only the number of evaluations.
  *   D5  L2 normalise: a pixel with zero norm yields zeros (reference: 0/0 = NaN,
  *       NCT/GeneralizedPatchMatch.cu:276-277).
+ *   D6  NNF upsample uses fmaf for `ax + (bxh-axh)*ratio` (what nvcc's default
+ *       -fmad=true emits for the reference's device code, :571-572).
  */
 #include <math.h>
 #include <float.h>
@@ -126,7 +130,7 @@ void orc_nnf_init(int ah, int aw, int bh, int bw, uint32_t *ann)
 
 static inline int clampi(int x, int hi, int lo) { return x > hi ? hi : (x < lo ? lo : x); }
 
-/* ---- upSample_kernel: NCT/GeneralizedPatchMatch.cu:546-580 (decision D4) ---- */
+/* ---- upSample_kernel: NCT/GeneralizedPatchMatch.cu:546-580 (decision D6) ---- */
 void orc_nnf_upsample(const uint32_t *ann_half, int ah_half, int aw_half,
                       int ah, int aw, int bh, int bw, uint32_t *ann)
 {
