@@ -32,8 +32,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 PM_CHANNELS = [512, 512, 256, 128, 64]
-ENGINE_NAME = {0: "fp32 CUDA cores", 1: "tcgen05 kind::tf32", 2: "tcgen05 3xTF32 (hi/lo split, 2e-4 of the feature range vs fp32)"}
-ENGINE_DTYPE = {0: "f32", 1: "tf32", 2: "tf32x3"}
+ENGINE_NAME = {0: "fp32 CUDA cores", 1: "tcgen05 kind::tf32", 2: "tcgen05 3xTF32 (hi/lo split, 2e-4 of the feature range vs fp32)",
+               3: "tcgen05 kind::i8 exact fixed point (4x3 balanced base-256 digits, INT32 accumulation, bit-exact vs the oracle)"}
+ENGINE_DTYPE = {0: "f32", 1: "tf32", 2: "tf32x3", 3: "s8x(4x3) digits -> s32 -> f32"}
 
 
 def read_peaks():
@@ -386,7 +387,7 @@ def main():
     ap.add_argument("--cpu-side", type=int, default=256, help="side of the bounded CPU sample pair")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pairs-in-flight", type=int, default=6, help="independent pairs processed concurrently per GPU (one step = this many pairs per rank)")
-    ap.add_argument("--vgg-engine", type=int, default=2, choices=[0, 1, 2],
+    ap.add_argument("--vgg-engine", type=int, default=2, choices=[0, 1, 2, 3],
                     help="convolution engine: 0 fp32 CUDA cores, 1 tcgen05 tf32, 2 tcgen05 3xTF32 (default)")
     args = ap.parse_args()
     if not os.environ.get("NCT_BENCH_PROFILE"):  # (launch-list mode under ncu may use a shorter warm-up)

@@ -217,9 +217,19 @@ int nct_vgg19_set_weights(nct_ctx *ctx, int layer, const float *w_oihw_host, con
 /* Convolution engine: 0 = FP32 on CUDA cores (exact FP32 products, fixed summation order: bit-exact vs
  * oracle/conv_oracle.c; the default of a new context), 1 = tcgen05 tensor cores, kind::tf32 operands from TMA-staged
  * shared memory, FP32 accumulation in TMEM (~1e-2 of the feature range after 13 layers), 2 = the same with the
- * 3xTF32 hi/lo operand split (FP32-accurate, ~2e-4 of the feature range; the CLI's and bench.py's default).
+ * 3xTF32 hi/lo operand split (FP32-accurate, ~2e-4 of the feature range), 3 = tcgen05 kind::i8 EXACT fixed point
+ * (conv_i8.cu: activations and weights as balanced base-256 digit planes, 9 INT8 MMAs per K step into four INT32 TMEM
+ * accumulators, combined exactly -- no unspecified accumulation order anywhere, bit-exact vs oracle/vgg.py::
+ * features_fixedpoint, 3-6e-7 of the layer range against an FP64 convolution; the CLI's and bench.py's default).
  * Tensor-core engines cover the layers with Cin >= 64; conv1_1 always runs on CUDA cores. */
 int nct_vgg19_set_engine(nct_ctx *ctx, int engine);
+/* One convolution layer (3x3, pad 1, stride 1, + bias, ReLU: cudnnConvolutionForward + cudnnAddTensor + ReLU,
+ * caffe/layers/cudnn_conv_layer.cu:20-37) through the exact fixed-point tensor-core engine, from plain FP32 tensors:
+ * in_dev NHWC FP32 (values >= 0), w_oihw_host / bias_host in Caffe's blob layout (host), out_dev NHWC FP32.  Cin and
+ * Cout multiples of 64.  acc_dbg_dev (optional, device int32 [4][H*W][Cout]) receives the raw INT32 accumulators.
+ * Diagnostic / unit-test entry point: the trunk (nct_vgg19_features) keeps digit planes and weights resident. */
+int nct_conv3x3_fixedpoint(nct_ctx *ctx, const float *in_dev, const float *w_oihw_host, const float *bias_host, float *out_dev,
+                           int *acc_dbg_dev, int H, int W, int Cin, int Cout);
 /* Feature-map sizes {C, H, W} per level for an h x w image under Caffe's ceil-mode pooling
  * (caffe/layers/pooling_layer.cpp:90-93); replaces the Dim outputs of Classifier::Predict (NCT/Classifier.h:30-43). */
 int nct_vgg19_level_dims(int h, int w, int dims[5][3]);

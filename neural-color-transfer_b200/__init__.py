@@ -75,6 +75,7 @@ ABI = {
     "nct_vgg19_layer_shape": (_i, [_i, C.POINTER(_i), C.POINTER(_i)]),
     "nct_vgg19_set_weights": (_i, [c_ctx_p, _i, _p, _p]),
     "nct_vgg19_set_engine": (_i, [c_ctx_p, _i]),
+    "nct_conv3x3_fixedpoint": (_i, [c_ctx_p, _p, _p, _p, _p, _p, _i, _i, _i, _i]),
     "nct_vgg19_level_dims": (_i, [_i, _i, C.POINTER(_i * 3)]),
     "nct_vgg19_features": (_i, [c_ctx_p, _p, _i, _i, _i, C.POINTER(_p)]),
     "nct_config_default": (None, [C.POINTER(Config)]),
@@ -473,8 +474,25 @@ class Context:
             self._check(self.lib.nct_vgg19_set_weights(self.h, i, w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))
 
     def set_vgg_engine(self, engine):
-        """0 = FP32 CUDA cores, 1 = tcgen05 TF32 tensor cores"""
+        """0 = FP32 CUDA cores, 1 = tcgen05 TF32, 2 = tcgen05 3xTF32, 3 = tcgen05 INT8 exact fixed point"""
         self._check(self.lib.nct_vgg19_set_engine(self.h, engine))
+
+    def conv3x3_fixedpoint(self, x, w_oihw, bias, debug_acc=False):
+        """One 3x3 conv + bias + ReLU through the exact fixed-point tensor-core engine.  x: (H, W, Cin) float32 cuda
+        tensor (>= 0); w_oihw, bias: numpy (Caffe blob layout).  Returns out (H, W, Cout) [, acc int32 (4, H*W, Cout)]."""
+        import numpy as np
+        import torch
+        H, W, cin = x.shape
+        w = np.ascontiguousarray(w_oihw, np.float32)
+        b = np.ascontiguousarray(bias, np.float32)
+        cout = w.shape[0]
+        out = torch.empty((H, W, cout), dtype=torch.float32, device=x.device)
+        acc = torch.zeros((4, H * W, cout), dtype=torch.int32, device=x.device) if debug_acc else None
+        if acc is not None:
+            torch.cuda.synchronize()
+        self._check(self.lib.nct_conv3x3_fixedpoint(self.h, _ptr(x), w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), _ptr(out),
+                                                    _ptr(acc) if acc is not None else None, H, W, cin, cout))
+        return (out, acc) if debug_acc else out
 
     def level_dims(self, h, w):
         d = ((_i * 3) * 5)()

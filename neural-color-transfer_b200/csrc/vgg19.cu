@@ -36,14 +36,24 @@ struct VggState {
     float *wk_hi[13] = {nullptr};  // rne_tf32(wk)         (3xTF32 engine)
     float *wk_lo[13] = {nullptr};  // wk - wk_hi
     float *b[13] = {nullptr};
+    int8_t *wq[13] = {nullptr};    // [3][cout][9][cin] balanced base-256 digits of the weights  (exact fixed-point engine)
+    int *wexp[13] = {nullptr};     // per-output-channel weight exponents
+    uint32_t *max_slots = nullptr; // [16] FP32 bit patterns of the layer-output maxima (engine 3)
     bool have[13] = {false};
-    int engine = 0;             // 0 = FP32 CUDA cores, 1 = tcgen05 kind::tf32, 2 = tcgen05 3xTF32 (FP32-accurate)
+    // 0 = FP32 CUDA cores, 1 = tcgen05 kind::tf32, 2 = tcgen05 3xTF32 (FP32-accurate), 3 = tcgen05 kind::i8 exact fixed point
+    int engine = 0;
 };
 
 int nct_conv3x3_tensorcore(nct_ctx *ctx, const float *in, const float *in_lo, const float *w_kmajor, const float *w_lo, const float *bias,
                            float *out, float *out_hi, float *out_lo, int H, int W, int Cin, int Cout);
 int nct_tf32_split(nct_ctx *ctx, const float *x, float *hi, float *lo, size_t n);
 void nct_tf32_split_host(const float *x, float *hi, float *lo, size_t n);
+// conv_i8.cu
+void nct_q_weight_digits_host(const float *w_oihw, int cin, int cout, int8_t *planes, int *wexp);
+int nct_q_act_digits(nct_ctx *ctx, const float *x, const uint32_t *max_bits, uint8_t *planes, size_t pstride, size_t n);
+int nct_q_pool_digits(nct_ctx *ctx, const float *x, const uint32_t *max_bits, uint8_t *planes, size_t pstride, int H, int W, int C, int Ho, int Wo);
+int nct_conv3x3_i8(nct_ctx *ctx, const uint8_t *planes, size_t pstride, const uint32_t *in_max_bits, const int8_t *wplanes, const int *wexp,
+                   const float *bias, float *out, uint32_t *out_max_bits, int *dbg_acc, int H, int W, int Cin, int Cout);
 
 namespace {
 
@@ -61,7 +71,8 @@ __global__ void preprocess_kernel(const uint8_t *__restrict__ bgr, float *__rest
 // ------------------------------------------------------------------ conv1_1: Cin = 3 (K = 27), direct
 // one thread = one pixel x 16 output channels; weights [27][64] in shared memory
 __global__ void __launch_bounds__(256) conv_first_kernel(const float *__restrict__ in, const float *__restrict__ wt,
-                                                         const float *__restrict__ bias, float *__restrict__ out, int H, int W)
+                                                         const float *__restrict__ bias, float *__restrict__ out, int H, int W,
+                                                         uint32_t *__restrict__ max_bits)
 {
     __shared__ float sw[27 * 64];
     __shared__ float sb[64];
@@ -70,7 +81,10 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float *__restrict
     __syncthreads();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int p = t >> 2, cg = (t & 3) * 16;
-    if (p >= H * W) return;
+    if (p >= H * W) {   // (whole warps stay alive for the maximum reduction below)
+        if (max_bits) __reduce_max_sync(0xFFFFFFFFu, 0u);
+        return;
+    }
     const int x = p % W, y = p / W;
     float acc[16];
 #pragma unroll
@@ -91,10 +105,18 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float *__restrict
             }
         }
     float4 *op = reinterpret_cast<float4 *>(out + (size_t)p * 64 + cg);
+    float vmax = 0.f;
 #pragma unroll
-    for (int o = 0; o < 16; o += 4)
-        op[o / 4] = make_float4(fmaxf(acc[o] + sb[cg + o], 0.f), fmaxf(acc[o + 1] + sb[cg + o + 1], 0.f),
-                                fmaxf(acc[o + 2] + sb[cg + o + 2], 0.f), fmaxf(acc[o + 3] + sb[cg + o + 3], 0.f));
+    for (int o = 0; o < 16; o += 4) {
+        const float4 r = make_float4(fmaxf(acc[o] + sb[cg + o], 0.f), fmaxf(acc[o + 1] + sb[cg + o + 1], 0.f),
+                                     fmaxf(acc[o + 2] + sb[cg + o + 2], 0.f), fmaxf(acc[o + 3] + sb[cg + o + 3], 0.f));
+        op[o / 4] = r;
+        vmax = fmaxf(fmaxf(vmax, fmaxf(r.x, r.y)), fmaxf(r.z, r.w));
+    }
+    if (max_bits) {   // tensor maximum for the fixed-point engine's quantisation of the next layer's input
+        const uint32_t mb = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));
+        if ((threadIdx.x & 31) == 0) atomicMax(max_bits, mb);
+    }
 }
 
 // ------------------------------------------------------------------ generic 3x3 conv, implicit GEMM on CUDA cores
@@ -222,7 +244,10 @@ void nct_vgg_free(nct_ctx *ctx)
         if (ctx->vgg->wk_lo[i]) cudaFree(ctx->vgg->wk_lo[i]);
         if (ctx->vgg->wk_hi[i]) cudaFree(ctx->vgg->wk_hi[i]);
         if (ctx->vgg->b[i]) cudaFree(ctx->vgg->b[i]);
+        if (ctx->vgg->wq[i]) cudaFree(ctx->vgg->wq[i]);
+        if (ctx->vgg->wexp[i]) cudaFree(ctx->vgg->wexp[i]);
     }
+    if (ctx->vgg->max_slots) cudaFree(ctx->vgg->max_slots);
     delete ctx->vgg;
     ctx->vgg = nullptr;
 }
@@ -266,6 +291,16 @@ int nct_vgg19_set_weights(nct_ctx *ctx, int layer, const float *w_oihw_host, con
         NCT_CUDA(ctx, cudaMemcpy(v->wk_hi[layer], hi.data(), wkm.size() * sizeof(float), cudaMemcpyHostToDevice));
         NCT_CUDA(ctx, cudaMemcpy(v->wk_lo[layer], lo.data(), wkm.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
+    if (cin >= 64) {   // balanced base-256 digit planes for the exact fixed-point engine
+        std::vector<int8_t> wd(3 * wkm.size());
+        std::vector<int> we(cout);
+        nct_q_weight_digits_host(w_oihw_host, cin, cout, wd.data(), we.data());
+        if (!v->wq[layer]) NCT_CUDA(ctx, cudaMalloc(&v->wq[layer], wd.size()));
+        if (!v->wexp[layer]) NCT_CUDA(ctx, cudaMalloc(&v->wexp[layer], cout * sizeof(int)));
+        NCT_CUDA(ctx, cudaMemcpy(v->wq[layer], wd.data(), wd.size(), cudaMemcpyHostToDevice));
+        NCT_CUDA(ctx, cudaMemcpy(v->wexp[layer], we.data(), cout * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (!v->max_slots) NCT_CUDA(ctx, cudaMalloc(&v->max_slots, 16 * sizeof(uint32_t)));
     if (!v->w[layer]) NCT_CUDA(ctx, cudaMalloc(&v->w[layer], wt.size() * sizeof(float)));
     if (!v->b[layer]) NCT_CUDA(ctx, cudaMalloc(&v->b[layer], cout * sizeof(float)));
     NCT_CUDA(ctx, cudaMemcpy(v->w[layer], wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -277,7 +312,7 @@ int nct_vgg19_set_weights(nct_ctx *ctx, int layer, const float *w_oihw_host, con
 int nct_vgg19_set_engine(nct_ctx *ctx, int engine)
 {
     NCT_ENTER(ctx);
-    NCT_REQUIRE(ctx, engine >= 0 && engine <= 2, "engine must be 0 (FP32 CUDA cores), 1 (tcgen05 TF32) or 2 (tcgen05 3xTF32)");
+    NCT_REQUIRE(ctx, engine >= 0 && engine <= 3, "engine must be 0 (FP32 CUDA cores), 1 (tcgen05 TF32), 2 (tcgen05 3xTF32) or 3 (tcgen05 INT8 exact fixed point)");
     if (!ctx->vgg) ctx->vgg = new VggState();
     ctx->vgg->engine = engine;
     return NCT_OK;
@@ -317,6 +352,45 @@ int nct_vgg19_features(nct_ctx *ctx, const uint8_t *bgr_dev, int h, int w, int d
     float *buf1 = (float *)nct_scratch(ctx, "vgg_act1", sizeof(float) * max_act);
     float *inp = (float *)nct_scratch(ctx, "vgg_input", sizeof(float) * (size_t)h * w * 3);
     if (!buf0 || !buf1 || !inp) return NCT_ERR_NOMEM;
+    if (v->engine == 3) {
+        // ---- exact fixed-point engine (conv_i8.cu): conv1_1 on CUDA cores in the canonical FP32 order, every other layer
+        // as 9 INT8 digit products on the tensor cores; activations travel as 4 digit planes scaled by the tensor maximum
+        uint8_t *planes = (uint8_t *)nct_scratch(ctx, "vgg_qplanes", 4 * max_act);
+        if (!planes) return NCT_ERR_NOMEM;
+        NCT_CUDA(ctx, cudaMemsetAsync(v->max_slots, 0, 16 * sizeof(uint32_t), ctx->stream));
+        preprocess_kernel<<<nct_div_up(h * w, 256), 256, 0, ctx->stream>>>(bgr_dev, inp, h * w);
+        NCT_CHECK_LAUNCH(ctx);
+        int H = h, W = w;
+        float *bufs[2] = {buf0, buf1};
+        int flip = 0;
+        const float *cur = inp;
+        for (int i = 0; i <= last_layer; ++i) {
+            const ConvSpec &L = kTrunk[i];
+            float *dst = (L.level >= 0) ? feat_dev[L.level] : bufs[flip];
+            if (L.level < 0) flip ^= 1;
+            if (dst == cur) return nct_fail(ctx, NCT_ERR_STATE, "internal: aliasing activation buffers");
+            if (i == 0) {
+                conv_first_kernel<<<nct_div_up(H * W * 4, 256), 256, 0, ctx->stream>>>(cur, v->w[0], v->b[0], dst, H, W, v->max_slots + 0);
+                NCT_CHECK_LAUNCH(ctx);
+            } else {
+                int rc;
+                if (L.pool_before) {
+                    const int Ho = pooled(H), Wo = pooled(W);
+                    rc = nct_q_pool_digits(ctx, cur, v->max_slots + (i - 1), planes, max_act, H, W, L.cin, Ho, Wo);
+                    H = Ho;
+                    W = Wo;
+                } else {
+                    rc = nct_q_act_digits(ctx, cur, v->max_slots + (i - 1), planes, max_act, (size_t)H * W * L.cin);
+                }
+                if (rc) return rc;
+                rc = nct_conv3x3_i8(ctx, planes, max_act, v->max_slots + (i - 1), v->wq[i], v->wexp[i], v->b[i], dst, v->max_slots + i, nullptr,
+                                    H, W, L.cin, L.cout);
+                if (rc) return rc;
+            }
+            cur = dst;
+        }
+        return NCT_OK;
+    }
     // 3xTF32: every activation travels with its truncation residual
     const bool x3 = v->engine == 2;
     float *lo_bufs[2] = {nullptr, nullptr}, *lo_feat[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -373,7 +447,7 @@ int nct_vgg19_features(nct_ctx *ctx, const uint8_t *bgr_dev, int h, int w, int d
         if (L.level < 0) flip ^= 1;
         if (dst == cur) return nct_fail(ctx, NCT_ERR_STATE, "internal: aliasing activation buffers");
         if (i == 0) {
-            conv_first_kernel<<<nct_div_up(H * W * 4, 256), 256, 0, ctx->stream>>>(cur, v->w[0], v->b[0], dst, H, W);
+            conv_first_kernel<<<nct_div_up(H * W * 4, 256), 256, 0, ctx->stream>>>(cur, v->w[0], v->b[0], dst, H, W, nullptr);
         } else if (v->engine >= 1) {
             int rc = nct_conv3x3_tensorcore(ctx, x3 ? cur_hi : cur, x3 ? cur_lo : nullptr, x3 ? v->wk_hi[i] : v->wk[i],
                                             x3 ? v->wk_lo[i] : nullptr, v->b[i], dst, dst_hi, dst_lo, H, W, L.cin, L.cout);
