@@ -1292,7 +1292,7 @@ int check_params(nct_ctx *ctx, const int *p)
                 "image sides must be in [1, 4096] (12-bit NNF packing)");
     NCT_REQUIRE(ctx, p[5] == 3, "patch size %d unsupported (reference uses 3, CT/Config.h:70)", p[5]);
     NCT_REQUIRE(ctx, p[6] >= 0 && p[6] <= 31, "iters %d out of range [0, 31] (the reference uses 10, NCT/main.cu:65)", p[6]);
-    NCT_REQUIRE(ctx, p[7] >= 1, "rs_max must be >= 1");
+    NCT_REQUIRE(ctx, p[7] >= 0, "rs_max must be >= 0 (0 = no random search, as in the reference for sides below 64: NCT/main.cu:77-83)");
     NCT_REQUIRE(ctx, p[8] == 0, "flag_constraint must be 0 (the reference never enables it, NCT/main.cu:66)");
     return NCT_OK;
 }

@@ -106,7 +106,8 @@ def test_pipeline_end_to_end_psnr_vs_independent_oracle(pctx, dev, weights):
     assert ps >= 35.0  # see DESIGN.md: FP32 conv summation order differs -> a few NNF entries flip -> bounded colour drift
 
 
-@pytest.mark.parametrize("seed,ch,cw,sh,sw", [(4, 128, 128, 128, 128), (8, 120, 152, 136, 104), (9, 256, 256, 256, 256)])
+@pytest.mark.parametrize("seed,ch,cw,sh,sw", [(4, 128, 128, 128, 128), (8, 120, 152, 136, 104), (9, 256, 256, 256, 256),
+                                              (3, 48, 40, 56, 48)])  # sides < 64: rs_max = maxLen/64 = 0 at level 3 (no random search)
 def test_pipeline_end_to_end_against_independent_canonical_oracle(pctx, dev, weights, seed, ch, cw, sh, sw):
     """The north star's end-to-end bar (final image PSNR >= 50 dB), on fully INDEPENDENT runs: the oracle computes its
     own features (oracle/conv_oracle.c, canonical order), its own NNFs, votes, neighbours, weights (host libm), the

@@ -89,7 +89,9 @@ def test_every_tile_configuration_gives_the_same_bits(qctx, dev, weights, bn, kb
     same feature maps as the default configuration."""
     img, _ = synth.pair(12, 80, 112)
     t = to_dev(img, dev)
-    base = [f.cpu().numpy() for f in qctx.predict(t, 0)]
+    base = qctx.predict(t, 0)
+    qctx.synchronize()  # the context runs on its own non-blocking stream: results are only there after this
+    base = [f.cpu().numpy() for f in base]
     os.environ["NCT_I8_BN"], os.environ["NCT_I8_KB"] = str(bn), str(kb)
     try:
         got = qctx.predict(t, 0)
