@@ -108,7 +108,6 @@ def cpu_pipeline_mps(side, pm_mode, threads):
     from oracle import pipeline, synth
 
     torch.set_num_threads(threads)
-    os.environ["OMP_NUM_THREADS"] = str(threads)
     w = synth.vgg19_weights(19)
     cnt, stl = synth.pair(0, side, side)
     t = {}
@@ -118,29 +117,51 @@ def cpu_pipeline_mps(side, pm_mode, threads):
     return side * side / 1e6 / dt, dt, {k: round(v, 3) for k, v in t.items()}
 
 
+def workload_config(side, P, world, engine):
+    """the `config` object of the JSON line -- the reference arm prints the same one (it runs on OUR arm's config)"""
+    return {"workload": f"{side}x{side} pairs, full L=5->1 pyramid, BDS=2.0 (BASELINE configs[{1 if side == 700 else 3 if side == 1000 else '-'}]); "
+                        f"one step = {P} independent pairs per GPU",
+            "pairs_per_step": world * P, "pairs_in_flight_per_gpu": P,
+            "l2_policy": "inputs larger than L2: ~1.1 GB working set per pair, alternating distinct pairs",
+            "vgg_weights": "synthetic He-normal (seed 19)", "vgg_engine": ENGINE_NAME[engine],
+            "collective": ("NCCL point-to-point gather of every step's result images on rank 0 inside the timed region "
+                           "(grouped ncclSend/ncclRecv per step on a side stream, overlapped with the next step)") if world > 1 else "none"}
+
+
 def run_reference(args):
     """CPU arm: the reference's own algorithmic path restated on the host (the reference binary cannot be built here:
-    Windows-only sources, Caffe, OpenCV 2.4.10, MKL PARDISO, legacy cuSPARSE -- DESIGN.md section 7)."""
+    Windows-only sources, Caffe, OpenCV 2.4.10, MKL PARDISO, legacy cuSPARSE -- DESIGN.md section 7).  Each step is a
+    BOUNDED sample (one --cpu-sample-side pair, default 256 x 256: the driver runs 25 steps and a 700 x 700 pair costs
+    minutes of CPU); one full-size pair is timed once after the steps and reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = len(os.sched_getaffinity(0))
-    sample_side = args.cpu_side
+    sample_side = args.cpu_sample_side
     vals = []
     for i in range(args.warmup + args.steps):
-        mps, dt, stages = cpu_pipeline_mps(sample_side, "reference", threads)
+        mps, dt, stages = cpu_pipeline_mps(sample_side, "canonical", threads)
         if i >= args.warmup:
             vals.append((mps, dt, stages))
     mps = sum(v[0] for v in vals) / len(vals)
     ms = 1e3 * sum(v[1] for v in vals) / len(vals)
-    sample = f"one {sample_side}x{sample_side} synthetic pair per step, full L=5->1 pipeline (bounded sample of the {args.side}x{args.side} workload)"
+    sample = (f"one {sample_side}x{sample_side} synthetic pair per step, full L=5->1 pipeline (bounded sample of the {args.side}x{args.side} "
+              f"workload; MP/s = sample pixels / seconds), oracle port with the OpenMP PatchMatch, im2col+SGEMM VGG, scipy solves")
+    cpu = {"value": round(mps, 5), "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample, "stage_seconds": vals[-1][2]}
+    if not args.no_full_size_check:
+        fm, fdt, fst = cpu_pipeline_mps(args.side, "canonical", threads)
+        cpu["full_size_check"] = {"value": round(fm, 5), "unit": "MP/s", "seconds": round(fdt, 1), "stage_seconds": fst,
+                                  "what": f"ONE {args.side}x{args.side} pair through the same port, timed once after the steps (the headline size)"}
+    if args.serial_reference_check:
+        rm, rdt, rst = cpu_pipeline_mps(sample_side, "reference", threads)
+        cpu["reference_layout_serial_patchmatch"] = {"value": round(rm, 5), "unit": "MP/s", "seconds": round(rdt, 1),
+                                                      "what": "same sample with the reference's planar layout and in-place serial PatchMatch order"}
     line = {
         "impl": "reference", "metric": "MP/s full L=5->1 pipeline", "value": round(mps, 5), "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-        "config": {"workload": f"single {args.side}x{args.side} pair, full L=5->1 pyramid, BDS=2.0", "cpu_sample": sample},
-        "cpu_baseline": {"value": round(mps, 5), "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample,
-                         "stage_seconds": vals[-1][2]},
+        "config": workload_config(args.side, args.pairs_in_flight, max(args.gpus, 1), args.vgg_engine),
+        "cpu_baseline": cpu,
         "e2e": {"value": round(mps, 5), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -152,11 +173,11 @@ def run_ours(args):
 
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         g.wait_for_cuda()  # (a transient first-initialisation failure was seen once on a fresh box)
+    import importlib
+
     import numpy as np
     import torch
     import torch.distributed as dist
-
-    from oracle import synth  # synthetic inputs only (numpy); no oracle compute on this path
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -169,15 +190,15 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     pkg = g.load_package()
-    # pairs in flight per GPU: each needs a host thread that issues ~8k launches per pair, so never more than the
-    # host cores this rank can count on
-    cores = len(os.sched_getaffinity(0))
-    P = max(1, min(args.pairs_in_flight, cores // max(world, 1)))
+    synth = importlib.import_module("nct_b200.synth")  # synthetic inputs (numpy); the product arm never imports oracle/
+    # P pairs in flight per GPU, the SAME at every N (weak scaling compares equal per-GPU batches): one libnct context +
+    # stream + host thread each (pairs are independent; the coarse pyramid levels and the solvers' small kernels do not fill
+    # 148 SMs on their own).  The host threads sleep in blocking waits most of the time, so they may outnumber the cores.
+    P = max(1, args.pairs_in_flight)
     side, K = args.side, args.steps
     weights = synth.vgg19_weights(19)
-    # P pairs in flight per GPU: one libnct context + stream + host thread each (pairs are independent; the coarse
-    # pyramid levels and the solvers' small kernels do not fill 148 SMs on their own)
     streams = [torch.cuda.Stream(device=dev) for _ in range(P)]
+    comm = torch.cuda.Stream(device=dev)  # side stream of the per-step gather / result read-back
     ctxs = []
     for j in range(P):
         c = pkg.Context(local, streams[j])
@@ -188,10 +209,14 @@ def run_ours(args):
     pairs = [[synth.pair((rank * P + j) * npairs + q, side, side) for q in range(npairs)] for j in range(P)]
     dev_pairs = [[(torch.from_numpy(c).to(dev), torch.from_numpy(s).to(dev)) for c, s in pj] for pj in pairs]
     pin_pairs = [[(torch.from_numpy(c).pin_memory(), torch.from_numpy(s).pin_memory()) for c, s in pj] for pj in pairs]
+    stage_in = [(torch.empty((side, side, 3), dtype=torch.uint8, device=dev), torch.empty((side, side, 3), dtype=torch.uint8, device=dev))
+                for _ in range(P)]
     torch.cuda.synchronize(dev)  # inputs resident before any context stream touches them
     out_dev = torch.empty((K, P, side, side, 3), dtype=torch.uint8, device=dev)
     out_pin = [torch.empty((side, side, 3), dtype=torch.uint8).pin_memory() for _ in range(P)]
-    gather_list = [torch.empty_like(out_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # rank 0 of a multi-GPU run: receive slots for every step's remote results, and the host copy of one step's results
+    recv_dev = torch.empty((K, (world - 1) * P, side, side, 3), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+    host_all = torch.empty((world * P, side, side, 3), dtype=torch.uint8).pin_memory() if (world > 1 and rank == 0) else None
     cfg = ctxs[0].default_config()
 
     def barrier():
@@ -199,34 +224,82 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def run_threads(fn):
+    def run_steps(n, mode, record=None):
+        """n steps of P pairs per rank.  mode "dev": inputs resident in HBM (nct_transfer_pair_dev); "api": the host-buffer
+        C-ABI call nct_transfer_pair (pinned host in / out, N = 1); "copies": N > 1 end to end = pinned H2D copies of the
+        inputs + nct_transfer_pair_dev + gather + D2H of ALL results into rank 0's pinned host memory.
+        At N > 1 every step's results are gathered on rank 0: the ranks != 0 post one grouped ncclSend of their P images as
+        soon as the step's pairs are done, rank 0 the matching grouped ncclRecv, on the side stream `comm`, so the transfer
+        overlaps the next step's compute.  Returns the event that marks the end of everything queued."""
+        step_done = [[threading.Event() for _ in range(P)] for _ in range(n)]
+        done_ev = [[torch.cuda.Event() for _ in range(P)] for _ in range(n)]
         errors = []
 
-        def guarded(j):
+        def work(j):
+            i = 0
             try:
                 torch.cuda.set_device(dev)  # the current device is per host thread
-                fn(j)
+                if record is not None:
+                    record[0][j].record(streams[j])
+                for i in range(n):
+                    q = i % npairs
+                    if mode == "api":
+                        ctxs[j].transfer_pair(*pin_pairs[j][q], cfg, out_pin[j])
+                    else:
+                        src = dev_pairs[j][q]
+                        if mode == "copies":
+                            with torch.cuda.stream(streams[j]):
+                                stage_in[j][0].copy_(pin_pairs[j][q][0], non_blocking=True)
+                                stage_in[j][1].copy_(pin_pairs[j][q][1], non_blocking=True)
+                            src = stage_in[j]
+                        ctxs[j].transfer_pair_dev(*src, cfg, out_dev[i % K, j])
+                    done_ev[i][j].record(streams[j])
+                    step_done[i][j].set()
+                if record is not None:
+                    record[1][j].record(streams[j])
             except BaseException as e:  # a worker that dies silently would make the timing meaningless
                 errors.append(e)
+            finally:
+                for ii in range(n):
+                    step_done[ii][j].set()
 
-        ts = [threading.Thread(target=guarded, args=(j,)) for j in range(P)]
+        ts = [threading.Thread(target=work, args=(j,)) for j in range(P)]
         [t.start() for t in ts]
+        if world > 1:
+            for i in range(n):
+                for j in range(P):
+                    step_done[i][j].wait()
+                if errors:
+                    break
+                for j in range(P):
+                    comm.wait_event(done_ev[i][j])
+                with torch.cuda.stream(comm):
+                    if rank == 0:
+                        ops = [dist.P2POp(dist.irecv, recv_dev[i % K, (r - 1) * P + j], r) for r in range(1, world) for j in range(P)]
+                    else:
+                        ops = [dist.P2POp(dist.isend, out_dev[i % K, j], 0) for j in range(P)]
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()  # stream-ordered: `comm` waits for the NCCL kernels, the host does not
+                    if mode == "copies" and rank == 0:
+                        host_all[:P].copy_(out_dev[i % K], non_blocking=True)
+                        host_all[P:].copy_(recv_dev[i % K], non_blocking=True)
         [t.join() for t in ts]
         if errors:
             raise errors[0]
+        main_stream = torch.cuda.current_stream(dev)
+        for j in range(P):
+            main_stream.wait_event(done_ev[n - 1][j])
+        ce = torch.cuda.Event()
+        ce.record(comm)
+        main_stream.wait_event(ce)
+        e_end = torch.cuda.Event(enable_timing=True)
+        e_end.record(main_stream)
+        return e_end
 
-    def dev_steps(n, record=None):
-        def work(j):
-            if record is not None:
-                record[0][j].record(streams[j])
-            for i in range(n):
-                ctxs[j].transfer_pair_dev(*dev_pairs[j][i % npairs], cfg, out_dev[i % K, j])
-            if record is not None:
-                record[1][j].record(streams[j])
-        run_threads(work)
-
-    # ---- warm-up
-    dev_steps(args.warmup)
+    e2e_mode = "api" if world == 1 else "copies"
+    # ---- warm-up of both timed paths (also opens the NCCL point-to-point channels: their lazy set-up costs ~0.5 s per peer)
+    run_steps(args.warmup, "dev")
+    run_steps(1, e2e_mode)
     torch.cuda.synchronize(dev)
     # PatchMatch evaluation counts for the roofline: one untimed pass on context 0 with the kernel's counters on
     # (deterministic, so the timed steps evaluate exactly the same candidates)
@@ -242,7 +315,7 @@ def run_ours(args):
         c0.count_evals(False)
         evals_bytes.append(tot)
 
-    # ---- timed region: K steps, each = one batch of P pairs per rank, + the NCCL gather of all results
+    # ---- timed region: K steps, each = one batch of P pairs per rank (+ at N > 1 the gather of the step's results on rank 0)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -250,19 +323,11 @@ def run_ours(args):
         c.reset_launch_count()
     c0.profile(True)
     ev = ([torch.cuda.Event(enable_timing=True) for _ in range(P)], [torch.cuda.Event(enable_timing=True) for _ in range(P)])
-    e_end = torch.cuda.Event(enable_timing=True)
     nvtx_id = torch.cuda.nvtx.range_start("timed")  # process-wide start/end range: `ncu --nvtx --nvtx-include "timed"` lists exactly the timed launches
-    dev_steps(K, ev)
-    main_stream = torch.cuda.current_stream(dev)
-    for j in range(P):
-        main_stream.wait_event(ev[1][j])
-    if world > 1:
-        dist.gather(out_dev, gather_list, dst=0)
-    e_end.record(main_stream)
+    e_end = run_steps(K, "dev", ev)
     torch.cuda.synchronize(dev)
     torch.cuda.nvtx.range_end(nvtx_id)
     barrier()
-    sampler.stop_flag = True
     dev_ms = max(ev[0][j].elapsed_time(e_end) for j in range(P))
     launches = sum(c.launch_count for c in ctxs)
     prof = c0.profile_report()
@@ -270,17 +335,29 @@ def run_ours(args):
 
     if os.environ.get("NCT_BENCH_PROFILE"):
         # launch-list mode for `ncu` (profiles/): the warm-up and the timed region only, no auxiliary passes
+        sampler.stop_flag = True
         if rank == 0:
             print(json.dumps({"profile_mode": True, "ms_per_step": round(dev_ms / K, 2), "gpu_launches": int(launches)}), flush=True)
         for c in ctxs:
             c.close()
         return
 
+    # ---- end to end, same K steps: host buffers in, host buffers out (N > 1: all results in rank 0's host memory)
+    barrier()
+    ee = ([torch.cuda.Event(enable_timing=True) for _ in range(P)], [torch.cuda.Event(enable_timing=True) for _ in range(P)])
+    t0 = time.perf_counter()
+    e_end2 = run_steps(K, e2e_mode, ee)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    sampler.stop_flag = True
+
     # ---- single-stream pass (context 0 alone): kernel time of PatchMatch without co-running streams
     c0.profile(True)
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nsingle = min(K, 4)
     s0.record(streams[0])
-    for i in range(K):
+    for i in range(nsingle):
         c0.transfer_pair_dev(*dev_pairs[0][i % npairs], cfg, out_dev[i % K, 0])
     s1.record(streams[0])
     streams[0].synchronize()
@@ -288,93 +365,148 @@ def run_ours(args):
     prof1 = c0.profile_report()
     c0.profile(False)
 
-    # ---- the same steps with the FP32 CUDA-core convolution engine (the engine the 1e-4 VGG parity test pins)
-    fp32_ms = 0.0
-    if args.vgg_engine != 0:
-        for c in ctxs:
-            c.set_vgg_engine(0)
-        dev_steps(1)
-        torch.cuda.synchronize(dev)
-        fe = ([torch.cuda.Event(enable_timing=True) for _ in range(P)], [torch.cuda.Event(enable_timing=True) for _ in range(P)])
-        dev_steps(K, fe)
-        torch.cuda.synchronize(dev)
-        fp32_ms = max(fe[0][0].elapsed_time(fe[1][j]) for j in range(P))
-        for c in ctxs:
-            c.set_vgg_engine(args.vgg_engine)
-
-    # ---- end to end through the host-buffer C-ABI entry point (pinned host buffers, H2D + D2H inside)
-    def e2e_steps(n):
-        def work(j):
-            for i in range(n):
-                ctxs[j].transfer_pair(*pin_pairs[j][i % npairs], cfg, out_pin[j])
-        run_threads(work)
-    e2e_steps(1)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps(K)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    barrier()
-
-    t = torch.tensor([dev_ms, e2e_s * 1e3, fp32_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, fp32_ms = float(t[0]), float(t[1]), float(t[2])
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
     mp_per_step = world * P * side * side / 1e6
     value = mp_per_step * K / (dev_ms / 1e3)
     e2e = mp_per_step * K / (e2e_ms / 1e3)
 
     if rank == 0:
         peak, peak_src = read_peaks()
+        tensor_peak, tensor_src = read_tensor_peak()
         pm_bytes = sum(evals_bytes[i % npairs] for i in range(K))
+        pm_bytes1 = sum(evals_bytes[i % npairs] for i in range(nsingle))
+        l2_gbs = c0.probe_read_bandwidth(48 << 20, 20)
+        hbm_probe = c0.probe_read_bandwidth(4 << 30, 1)
 
-        def roof(p):
+        def roof(p, nbytes):
             pm_ms, pm_spans = p["patchmatch"]
             n = pm_spans * 4 * cfg.pm_iters
-            ach = pm_bytes / 1e9 / (pm_ms / 1e3) if pm_ms > 0 else None
+            ach = nbytes / 1e9 / (pm_ms / 1e3) if pm_ms > 0 else None
             return ach, n, pm_ms
-        ach, nl, pm_ms = roof(prof)
-        ach1, nl1, pm_ms1 = roof(prof1)
+        ach, nl, pm_ms = roof(prof, pm_bytes)
+        ach1, nl1, pm_ms1 = roof(prof1, pm_bytes1)
+        traffic = read_ncu_traffic()
+        # parity evidence in the line itself: context 0's first pair is synth.pair(0, 700, 700), the pair of the committed
+        # full-size golden image (tests/golden/fullsize_golden.npz: oracle with fixed-point features, canonical CG, DIRECT WLS solve)
+        parity = {}
+        c0.transfer_pair_dev(*dev_pairs[0][0], cfg, out_dev[0, 0])
+        c0.synchronize()
+        img3 = out_dev[0, 0].cpu().numpy()
+        gpath = os.path.join(ROOT, "tests", "golden", "fullsize_golden.npz")
+        if rank == 0 and side == 700 and args.vgg_engine == 3 and os.path.exists(gpath):
+            gold = np.load(gpath)["e2e700_out"]
+            parity["bytes_differing_from_committed_700x700_golden"] = int((gold != img3).sum())
+            parity["psnr_db_vs_committed_700x700_golden"] = psnr(gold, img3)
+        if args.vgg_engine != 0:
+            c0.set_vgg_engine(0)
+            c0.transfer_pair_dev(*dev_pairs[0][0], cfg, out_dev[0, 0])
+            c0.synchronize()
+            parity["psnr_db_vs_fp32_engine"] = psnr(out_dev[0, 0].cpu().numpy(), img3)
+            parity["psnr_note"] = ("engine 0 = FP32 CUDA cores in the canonical order; both engines are bit-exact against their own oracle; "
+                                   "the pyramid's feedback loop amplifies 1e-6 feature differences (DESIGN.md section 6)")
+            c0.set_vgg_engine(args.vgg_engine)
+        vgg_ms1 = prof1["vgg"][0] / nsingle
+        vgg_flops = vgg_flops_per_pair(side)
         line = {
             "metric": "MP/s full L=5->1 pipeline", "value": round(value, 4), "unit": "MP/s", "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": round(dev_ms / K, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": ENGINE_DTYPE[args.vgg_engine] + " (VGG) / f32 (PatchMatch) / f64 (colour solves) / u8 (images)",
             "data": "synthetic",
-            "config": {"workload": f"{side}x{side} pairs, full L=5->1 pyramid, BDS=2.0 (BASELINE configs[1]); one step = {P} independent pairs per GPU",
-                       "pairs_per_step": world * P, "pairs_in_flight_per_gpu": P,
-                       "l2_policy": "inputs larger than L2: ~1.1 GB working set per pair, alternating distinct pairs",
-                       "vgg_weights": "synthetic He-normal (seed 19)", "vgg_engine": ENGINE_NAME[args.vgg_engine],
-                       "collective": "NCCL gather of all result images to rank 0 inside the timed region" if world > 1 else "none"},
-            "e2e": {"value": round(e2e, 4), "unit": "MP/s", "h2d_bytes_per_step": P * 2 * side * side * 3, "d2h_bytes_per_step": P * side * side * 3,
-                    "ms_per_step": round(e2e_ms / K, 2)},
+            "config": workload_config(side, P, world, args.vgg_engine),
+            "e2e": {"value": round(e2e, 4), "unit": "MP/s", "h2d_bytes_per_step": P * 2 * side * side * 3,
+                    "d2h_bytes_per_step": (world if world > 1 else 1) * P * side * side * 3, "ms_per_step": round(e2e_ms / K, 2),
+                    "through": "nct_transfer_pair (host-buffer C-ABI call), pinned host buffers" if world == 1 else
+                               "pinned H2D input copies + nct_transfer_pair_dev + NCCL gather + D2H of all results into rank 0's pinned host memory "
+                               "(d2h bytes are rank 0's; the other ranks read nothing back)"},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "pm_step_t_kernel (PatchMatch propagate + random search, tiled step kernel)", "bound": "hbm",
-                         "achieved": round(ach, 1) if ach else None, "peak": peak, "unit": "GB/s",
-                         "frac": round(ach / peak, 3) if ach else None, "traffic": 946.8e6, "traffic_note":
-                         "dram__bytes_read+write of one finest-level random-search launch (ncu --set full, profiles/r1_pm_step_ncu.md; "
-                         "~15.9 GB algorithmic in that launch: candidate rows are re-used out of L2/L1, so DRAM traffic is far BELOW the "
-                         "algorithmic bytes and achieved can exceed the HBM peak)",
-                         "peak_source": peak_src, "launches": int(nl), "avg_launch_ms": round(pm_ms / max(nl, 1), 4),
+            "roofline": {"kernel": "pm_step_t_kernel (PatchMatch propagate + random search, tiled step kernel)", "bound": "l2",
+                         "achieved": round(ach, 1) if ach else None, "peak": round(l2_gbs, 1), "unit": "GB/s",
+                         "frac": round(ach / l2_gbs, 3) if ach else None,
+                         "peak_source": "L2 read bandwidth measured in this process (nct_probe_read_bandwidth: 48 MB buffer, coalesced LDG.128, 20 passes, best of 5)",
+                         "why_l2": "candidate rows are re-used out of L2/L1: ncu shows DRAM traffic ~6 % of the algorithmic bytes and an L2 hit rate of 87 % "
+                                   "(profiles/r1_pm_step_ncu.md), so the algorithmic rate may exceed the HBM peak",
+                         "hbm": {"peak": peak, "peak_source": peak_src, "frac": round(ach / peak, 3) if ach else None,
+                                 "probe_read_GBs": round(hbm_probe, 1)},
+                         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                         "traffic_note": traffic.get("note") if traffic else "no ncu capture summary under profiles/",
+                         "launches": int(nl), "avg_launch_ms": round(pm_ms / max(nl, 1), 4),
                          "algorithmic_GB_per_pair": round(evals_bytes[0] / 1e9, 1),
                          "measured_in": f"timed region, context 0 of {P} co-running streams",
-                         "single_stream": {"achieved": round(ach1, 1) if ach1 else None, "frac": round(ach1 / peak, 3) if ach1 else None,
-                                           "avg_launch_ms": round(pm_ms1 / max(nl1, 1), 4), "ms_per_pair": round(single_ms / K, 2)}},
-            "stage_ms_per_pair_single_stream": {k: round(v[0] / K, 2) for k, v in prof1.items()},
+                         "single_stream": {"achieved": round(ach1, 1) if ach1 else None, "frac": round(ach1 / l2_gbs, 3) if ach1 else None,
+                                           "hbm_frac": round(ach1 / peak, 3) if ach1 else None,
+                                           "avg_launch_ms": round(pm_ms1 / max(nl1, 1), 4), "ms_per_pair": round(single_ms / nsingle, 2)}},
+            "roofline_vgg": {"kernel": "conv3x3_i8_kernel / conv3x3_tc_kernel (tcgen05.mma, TMA operands, TMEM accumulators)" if args.vgg_engine else "conv3x3_kernel (FP32 CUDA cores)",
+                             "bound": "tensor", "achieved": round(vgg_flops / 1e12 / (vgg_ms1 / 1e3), 1), "unit": "TFLOP/s",
+                             "peak": tensor_peak, "peak_source": tensor_src, "frac": round(vgg_flops / 1e12 / (vgg_ms1 / 1e3) / tensor_peak, 4),
+                             "algorithmic_GFLOP_per_pair": round(vgg_flops / 1e9, 1), "ms_per_pair": round(vgg_ms1, 2),
+                             "note": "algorithmic FP32-equivalent flops (2*9*Cin*Cout*H*W, truncated re-forwards) over the VGG stage time of the single-stream pass "
+                                     "(conv + pool + digit-split kernels); engine 3 issues 9 INT8 MMAs per algorithmic MAC (4x3 digit planes), engine 2 three TF32 MMAs"},
+            "parity": parity,
+            "stage_ms_per_pair_single_stream": {k: round(v[0] / nsingle, 2) for k, v in prof1.items()},
             "clocks": sampler.summary(),
         }
-        if fp32_ms:
-            line["value_fp32_conv_engine"] = round(mp_per_step * K / (fp32_ms / 1e3), 4)
         if world == 1 and not args.no_cpu_baseline:
             threads = len(os.sched_getaffinity(0))
             mps, dt, stages = cpu_pipeline_mps(args.cpu_side, "canonical", threads)
             line["cpu_baseline"] = {"value": round(mps, 5), "unit": "MP/s", "cores": threads, "kind": "port",
-                                    "sample": f"one {args.cpu_side}x{args.cpu_side} synthetic pair, full L=5->1 pipeline, {dt:.1f} s",
+                                    "sample": f"one {args.cpu_side}x{args.cpu_side} synthetic pair, full L=5->1 pipeline, one repetition, {dt:.1f} s "
+                                              f"(oracle port: im2col+SGEMM VGG, OpenMP PatchMatch/votes/k-NN, scipy CG + splu)",
                                     "stage_seconds": stages}
         print(json.dumps(line), flush=True)
     for c in ctxs:
         c.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def psnr(a, b):
+    import numpy as np
+
+    mse = float(((a.astype(np.float64) - b.astype(np.float64)) ** 2).mean())
+    return None if mse == 0 else round(10.0 * float(np.log10(255.0 ** 2 / mse)), 2)
+
+
+def vgg_flops_per_pair(side):
+    """required conv flops of one pair: two full forwards + the truncated re-forwards after levels 0..3"""
+    def dims(n):
+        out = [n]
+        for _ in range(4):
+            out.append((out[-1] - 2 + 1) // 2 + 1)
+        return out
+    d = dims(side)
+    layers = [(3, 64, 0), (64, 64, 0), (64, 128, 1), (128, 128, 1), (128, 256, 2), (256, 256, 2), (256, 256, 2), (256, 256, 2),
+              (256, 512, 3), (512, 512, 3), (512, 512, 3), (512, 512, 3), (512, 512, 4)]
+    last_needed = {0: 12, 1: 8, 2: 4, 3: 2, 4: 0}  # trunk layer index of conv5_1, conv4_1, conv3_1, conv2_1, conv1_1
+
+    def fwd(deepest_level):
+        return sum(2.0 * 9 * ci * co * d[s] * d[s] for k, (ci, co, s) in enumerate(layers) if k <= last_needed[deepest_level])
+    return 2 * fwd(0) + fwd(1) + fwd(2) + fwd(3) + fwd(4)
+
+
+def read_tensor_peak():
+    """dense bf16 tensor throughput in TFLOP/s (sustained: the VGG stage runs inside a long step)"""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(p))
+        for k in ("bf16_tflops_sustained", "bf16_tflops"):
+            if isinstance(d.get(k), (int, float)) and d[k] > 0:
+                return float(d[k]), f"measured (MEASURED_PEAKS.json {k}); INT8 / TF32 peaks were not measured by the driver"
+    except Exception:
+        pass
+    return 2250.0, "fallback (nominal dense bf16 2.25 PFLOP/s)"
+
+
+def read_ncu_traffic():
+    """dram bytes per launch of the PatchMatch step kernel from the committed ncu summary (profiles/pm_traffic.json)"""
+    p = os.path.join(ROOT, "profiles", "pm_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 def main():
@@ -384,12 +516,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--side", type=int, default=700)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-side", type=int, default=256, help="side of the bounded CPU sample pair")
+    ap.add_argument("--cpu-side", type=int, default=700, help="side of the cpu_baseline pair of our arm (one repetition; the headline size)")
+    ap.add_argument("--cpu-sample-side", type=int, default=256, help="--impl reference: side of the bounded sample pair of each step")
+    ap.add_argument("--no-full-size-check", action="store_true", help="--impl reference: skip the single full-size pair timed after the steps")
+    ap.add_argument("--serial-reference-check", action="store_true", help="--impl reference: also time the reference-layout serial PatchMatch variant once")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pairs-in-flight", type=int, default=6, help="independent pairs processed concurrently per GPU (one step = this many pairs per rank)")
     ap.add_argument("--vgg-engine", type=int, default=3, choices=[0, 1, 2, 3],
                     help="convolution engine: 0 fp32 CUDA cores, 1 tcgen05 tf32, 2 tcgen05 3xTF32, 3 tcgen05 int8 exact fixed point (default)")
     args = ap.parse_args()
+    # before libgomp / MKL are loaded: all the host threads this process may use
+    os.environ.setdefault("OMP_NUM_THREADS", str(len(os.sched_getaffinity(0))))
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per context stream (default 8 < P + side streams)
     if not os.environ.get("NCT_BENCH_PROFILE"):  # (launch-list mode under ncu may use a shorter warm-up)
         args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

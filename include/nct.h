@@ -202,6 +202,11 @@ int nct_solve_wls_jacobi(nct_ctx *ctx, double *a_dev, double *b_dev, const doubl
 int nct_apply_coefficients(nct_ctx *ctx, const uint8_t *cnt_lab_full_dev, const double *a_dev, const double *b_dev,
                            int H, int W, uint8_t *out_bgr_dev, uint8_t *out_lab_dev);
 
+/* Measurement aid (no reference counterpart): read bandwidth in GB/s of coalesced 16-byte loads over
+ * a `bytes` buffer read `passes` times in one launch (best of 5 launches).  A buffer that fits the L2 (e.g. 48 MB)
+ * measures the L2 read roofline PatchMatch's candidate-row gathers run against; one far larger than L2 the HBM one. */
+int nct_probe_read_bandwidth(nct_ctx *ctx, size_t bytes, int passes, double *gbps_out);
+
 /* ---------------------------------------------------------------- VGG-19 features
  * Replaces Classifier (NCT/Classifier.h:51-61, NCT/Classifier.cpp:5-143) + caffe::Net<float> for the fixed graph of
  * demo/model/vgg19/VGG_ILSVRC_19_layers_deploy.prototxt, truncated after conv5_1.  Trunk layer index 0..12 =

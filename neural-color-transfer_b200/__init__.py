@@ -76,6 +76,7 @@ ABI = {
     "nct_vgg19_set_weights": (_i, [c_ctx_p, _i, _p, _p]),
     "nct_vgg19_set_engine": (_i, [c_ctx_p, _i]),
     "nct_conv3x3_fixedpoint": (_i, [c_ctx_p, _p, _p, _p, _p, _p, _i, _i, _i, _i]),
+    "nct_probe_read_bandwidth": (_i, [c_ctx_p, C.c_size_t, _i, C.POINTER(C.c_double)]),
     "nct_vgg19_level_dims": (_i, [_i, _i, C.POINTER(_i * 3)]),
     "nct_vgg19_features": (_i, [c_ctx_p, _p, _i, _i, _i, C.POINTER(_p)]),
     "nct_config_default": (None, [C.POINTER(Config)]),
@@ -493,6 +494,12 @@ class Context:
         self._check(self.lib.nct_conv3x3_fixedpoint(self.h, _ptr(x), w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), _ptr(out),
                                                     _ptr(acc) if acc is not None else None, H, W, cin, cout))
         return (out, acc) if debug_acc else out
+
+    def probe_read_bandwidth(self, nbytes, passes):
+        """GB/s of coalesced 16-byte reads over an nbytes buffer (fits L2: the L2 roofline; >> L2: the HBM one)."""
+        g = C.c_double(0.0)
+        self._check(self.lib.nct_probe_read_bandwidth(self.h, nbytes, passes, C.byref(g)))
+        return g.value
 
     def level_dims(self, h, w):
         d = ((_i * 3) * 5)()

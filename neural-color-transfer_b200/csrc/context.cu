@@ -99,6 +99,91 @@ const double *nct_knn_weight_table(nct_ctx *ctx)
     return dev;
 }
 
+// ---------------------------------------------------------------- captured launch sequences
+bool nct_graph_cached(nct_ctx *ctx, const char *name, const std::vector<unsigned long long> &key)
+{
+    auto it = ctx->graphs.find(name);
+    return it != ctx->graphs.end() && it->second.exec && it->second.key == key;
+}
+
+static void graph_release(NctGraph &g)
+{
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+    g.exec = nullptr;
+    g.graph = nullptr;
+    g.capturing = false;
+}
+
+int nct_graph_begin(nct_ctx *ctx, const char *name, const std::vector<unsigned long long> &key, cudaGraphConditionalHandle *while_handle)
+{
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    NCT_CUDA(ctx, cudaStreamIsCapturing(ctx->stream, &st));
+    if (st != cudaStreamCaptureStatusNone) {   // an earlier capture was abandoned by an error return: discard it
+        cudaGraph_t dead = nullptr;
+        cudaStreamEndCapture(ctx->stream, &dead);
+        if (dead) cudaGraphDestroy(dead);
+        cudaGetLastError();
+    }
+    NctGraph &g = ctx->graphs[name];
+    graph_release(g);
+    g.key = key;
+    g.launches_at_begin = ctx->launches;
+    // thread-local capture mode: other host threads (other contexts) keep allocating / synchronising freely
+    if (while_handle) {
+        NCT_CUDA(ctx, cudaGraphCreate(&g.graph, 0));
+        NCT_CUDA(ctx, cudaGraphConditionalHandleCreate(while_handle, g.graph, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams p = {};
+        p.type = cudaGraphNodeTypeConditional;
+        p.conditional.handle = *while_handle;
+        p.conditional.type = cudaGraphCondTypeWhile;
+        p.conditional.size = 1;
+        cudaGraphNode_t node;
+        NCT_CUDA(ctx, cudaGraphAddNode(&node, g.graph, nullptr, 0, &p));
+        NCT_CUDA(ctx, cudaStreamBeginCaptureToGraph(ctx->stream, p.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    } else {
+        NCT_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    }
+    g.capturing = true;
+    return NCT_OK;
+}
+
+int nct_graph_end(nct_ctx *ctx, const char *name)
+{
+    auto it = ctx->graphs.find(name);
+    if (it == ctx->graphs.end() || !it->second.capturing) return nct_fail(ctx, NCT_ERR_STATE, "graph '%s' is not being captured", name);
+    NctGraph &g = it->second;
+    g.capturing = false;
+    cudaGraph_t captured = nullptr;
+    NCT_CUDA(ctx, cudaStreamEndCapture(ctx->stream, &captured));
+    if (!g.graph) g.graph = captured;   // plain capture; (capture into a WHILE body returns the body graph, owned by g.graph)
+    g.nodes = ctx->launches - g.launches_at_begin;
+    ctx->launches = g.launches_at_begin;   // nothing has run yet
+    NCT_CUDA(ctx, cudaGraphInstantiate(&g.exec, g.graph, 0));
+    return NCT_OK;
+}
+
+int nct_graph_launch(nct_ctx *ctx, const char *name)
+{
+    auto it = ctx->graphs.find(name);
+    if (it == ctx->graphs.end() || !it->second.exec) return nct_fail(ctx, NCT_ERR_STATE, "graph '%s' has not been captured", name);
+    NCT_CUDA(ctx, cudaGraphLaunch(it->second.exec, ctx->stream));
+    ctx->launches += it->second.nodes;
+    return NCT_OK;
+}
+
+long long nct_graph_nodes(nct_ctx *ctx, const char *name)
+{
+    auto it = ctx->graphs.find(name);
+    return it == ctx->graphs.end() ? 0 : it->second.nodes;
+}
+
+void nct_graphs_free(nct_ctx *ctx)
+{
+    for (auto &kv : ctx->graphs) graph_release(kv.second);
+    ctx->graphs.clear();
+}
+
 NctStageTimer::NctStageTimer(nct_ctx *c, int stage) : ctx(c)
 {
     if (!c || !c->profile) return;
@@ -212,6 +297,7 @@ int nct_destroy(nct_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     nct_pipe_free(ctx);
     nct_vgg_free(ctx);
+    nct_graphs_free(ctx);
     for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     for (auto &e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->wait_event) cudaEventDestroy(ctx->wait_event);

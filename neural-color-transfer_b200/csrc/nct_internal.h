@@ -14,6 +14,18 @@ struct NctBuffer {
     size_t bytes = 0;
 };
 
+// A captured launch sequence, replayed with one cudaGraphLaunch (the solvers' iteration blocks: thousands of tiny
+// dependent launches per pair otherwise).  `key` = everything the captured kernels received by value (sizes, device
+// pointers): a replay is only valid while it is unchanged, otherwise the sequence is captured again.
+struct NctGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    std::vector<unsigned long long> key;
+    long long nodes = 0;                // kernel launches of one pass through the captured sequence
+    long long launches_at_begin = 0;
+    bool capturing = false;
+};
+
 struct nct_ctx {
     int device = 0;
     int num_sms = 148;
@@ -49,6 +61,9 @@ struct nct_ctx {
     // WLS warm start (set by the pair orchestrator around its per-level solves; off for direct nct_solve_wls callers)
     int wls_warm = 0;
     int wls_prev_n = 0;
+    int wls_last_iters = 0;  // iteration count of the previous solve: the size of the first batch queued without a host check
+
+    std::map<std::string, NctGraph> graphs;
 
     // opaque sub-module states (owned, freed in nct_destroy)
     struct VggState *vgg = nullptr;
@@ -61,6 +76,20 @@ int nct_fail(nct_ctx *ctx, int code, const char *fmt, ...);
 cudaError_t nct_stream_wait(nct_ctx *ctx);
 // returns device pointer of at least `bytes` bytes, stable until a larger request under the same name
 void *nct_scratch(nct_ctx *ctx, const char *name, size_t bytes);
+
+// ---- captured launch sequences (context.cu).  Usage:
+//   if (!nct_graph_cached(ctx, "name", key)) { nct_graph_begin(ctx, "name", key, &handle_or_null); ...launches on ctx->stream...;
+//                                               nct_graph_end(ctx, "name"); }
+//   nct_graph_launch(ctx, "name");
+// Nothing may allocate (nct_scratch) or synchronise between begin and end.  With `while_handle` != nullptr the sequence
+// becomes the body of a device-side WHILE loop (CUDA conditional graph node): it repeats until a kernel of the body calls
+// cudaGraphSetConditional(*while_handle, 0); the handle's value is reset to 1 at every launch.
+bool nct_graph_cached(nct_ctx *ctx, const char *name, const std::vector<unsigned long long> &key);
+int nct_graph_begin(nct_ctx *ctx, const char *name, const std::vector<unsigned long long> &key, cudaGraphConditionalHandle *while_handle);
+int nct_graph_end(nct_ctx *ctx, const char *name);
+int nct_graph_launch(nct_ctx *ctx, const char *name);   // adds the sequence's launch count to ctx->launches once
+long long nct_graph_nodes(nct_ctx *ctx, const char *name);
+void nct_graphs_free(nct_ctx *ctx);
 
 // [256 * 256] pow(|l1 * (1/255) - l0 * (1/255)|, alpha) at index l0 * 256 + l1 (compute_gradientMat, CT/ColorTransfer.cpp:519-546)
 const double *nct_pow_table(nct_ctx *ctx, double alpha);

@@ -649,13 +649,44 @@ int nct_solve_nonlocal(nct_ctx *ctx, double *a_dev, double *b_dev, const double 
     nl_init_kernel<<<blocks, TPB, 0, ctx->stream>>>(S, x, r, p0, sc, tol2, partials, counter);
     NCT_CHECK_LAUNCH(ctx);
     (void)p1;
-    for (int k = 1; k <= maxit; ++k) {
+    // maxit iterations of 3 launches each, all with device-side `active` flags (no host check): queued as replays of one
+    // captured block of 10 iterations (NCT_NL_GRAPH=0: plain stream launches, for ncu launch lists)
+    auto iteration = [&]() -> int {
         nl_pupdate_kernel<<<blocks, TPB, 0, ctx->stream>>>(n, r, p0, sc);
         NCT_CHECK_LAUNCH(ctx);
         nl_spmv_kernel<<<blocks, TPB, 0, ctx->stream>>>(S, p0, Ap, sc, partials, counter);
         NCT_CHECK_LAUNCH(ctx);
         nl_update_kernel<<<blocks, TPB, 0, ctx->stream>>>(n, x, r, p0, Ap, sc, tol2, partials, counter);
         NCT_CHECK_LAUNCH(ctx);
+        return NCT_OK;
+    };
+    const bool use_graph = !(getenv("NCT_NL_GRAPH") && atoi(getenv("NCT_NL_GRAPH")) == 0);
+    constexpr int kBlock = 10;
+    int k = 1;
+    if (use_graph && maxit >= kBlock) {
+        char gname[32];
+        snprintf(gname, sizeof(gname), "nl_cg_block_l%d", layer);   // one graph per pyramid level: a pair never re-captures
+        auto P = [](const void *q) { return (unsigned long long)(uintptr_t)q; };
+        std::vector<unsigned long long> key = {(unsigned long long)n, (unsigned long long)h, (unsigned long long)w, P(cnt_lab_dev), P(stl_lab_dev),
+                                               P(d2), P(wx2), P(wy2), P(knn_id_dev), P(kw2), P(rstart), P(rsrc), P(rw2), P(vec), P(partials), P(misc)};
+        if (!nct_graph_cached(ctx, gname, key)) {
+            rc = nct_graph_begin(ctx, gname, key, nullptr);
+            if (rc) return rc;
+            for (int q = 0; q < kBlock; ++q) {
+                rc = iteration();
+                if (rc) return rc;
+            }
+            rc = nct_graph_end(ctx, gname);
+            if (rc) return rc;
+        }
+        for (; k + kBlock - 1 <= maxit; k += kBlock) {
+            rc = nct_graph_launch(ctx, gname);
+            if (rc) return rc;
+        }
+    }
+    for (; k <= maxit; ++k) {
+        rc = iteration();
+        if (rc) return rc;
     }
     unpack_ab_kernel<<<nct_div_up(n3, TPB), TPB, 0, ctx->stream>>>(x, n3, a_dev, b_dev);
     NCT_CHECK_LAUNCH(ctx);

@@ -32,13 +32,15 @@ DEFAULT_CFG = dict(bds=2.0, eps=0.6, nl=2.0, l=0.125, w=0.024, clusters=10, knum
 
 
 def transfer_pair(cnt, stl, weights=None, cfg=None, features_fn=None, on_level=None, stop_after_level=4, timings=None,
-                  im2col=True, pm_mode="canonical", result_hook=None, cg_mode="reference"):
+                  im2col=True, pm_mode="canonical", result_hook=None, cg_mode="reference", pm_fn=None):
     """cnt, stl: uint8 BGR (H, W, 3).  Returns the uint8 BGR result (content size).
     pm_mode: "canonical" = deterministic jump-flood oracle (the parity target); "reference" = reference-semantics
     in-place serial PatchMatch in the reference's layout / summation order (CPU baseline only).
     cg_mode: "reference" = explicit A, A^T A by scipy (the reference's structure; summation order unspecified);
     "canonical" = the defined-order matrix-free CG of oracle/cg_oracle.c (decision N1) -- with canonical features
-    (vgg.features_canonical) this makes the whole oracle run a bit-level target for the product."""
+    (vgg.features_canonical) this makes the whole oracle run a bit-level target for the product.
+    pm_fn: optional replacement of the PatchMatch stage, pm_fn(nC, nS, ann, bnn, p_ab, p_ba) -> (ann, annd, bnn, bnnd)
+    (tests plug the reference's own racy kernel in here to measure the reference's run-to-run noise floor)."""
     cfg = DEFAULT_CFG | (cfg or {})
     t_acc = timings if timings is not None else {}
 
@@ -84,7 +86,10 @@ def transfer_pair(cnt, stl, weights=None, cfg=None, features_fn=None, on_level=N
         nC = _pm.l2norm_hwc(featC[l])
         p_ab = _pm.make_params(Cn, ah, aw, bh, bw, cfg["pm_iters"], rng[l])
         p_ba = _pm.make_params(Cn, bh, bw, ah, aw, cfg["pm_iters"], rng[l])
-        if pm_mode == "canonical":
+        if pm_fn is not None:
+            ann, annd, bnn, bnnd = pm_fn(nC, nS, ann, bnn, p_ab, p_ba)
+            st_a = st_b = (0, 0)
+        elif pm_mode == "canonical":
             ann, annd, st_a = _pm.patchmatch(nC, nS, ann, p_ab)
             bnn, bnnd, st_b = _pm.patchmatch(nS, nC, bnn, p_ba)
         else:

@@ -20,7 +20,7 @@ def _json_lines(text):
 
 
 def test_reference_arm_prints_one_contract_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cpu-side", "64", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--cpu-sample-side", "64", "--side", "96", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = _json_lines(r.stdout)
@@ -29,14 +29,21 @@ def test_reference_arm_prints_one_contract_line():
     assert KEYS <= set(d) and d["impl"] == "reference" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"].startswith("single 700x700 pair") and d["vs_baseline"] is None and d["gpu_launches"] == 0
+    sys.path.insert(0, ROOT)
+    import bench
+
+    # the reference arm runs on OUR arm's config: the same `config` object, the sample is described in cpu_baseline
+    assert d["config"] == bench.workload_config(96, 6, 1, 3) and d["vs_baseline"] is None and d["gpu_launches"] == 0
+    assert "64x64" in d["cpu_baseline"]["sample"]
+    full = d["cpu_baseline"]["full_size_check"]   # one full-size pair, timed once after the steps
+    assert full["value"] > 0 and full["seconds"] > 0
 
 
 def test_reference_arm_under_torchrun_only_rank0_prints():
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29631", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--cpu-side", "64",
-                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+                        "--master-port", "29631", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--cpu-sample-side", "64",
+                        "--no-full-size-check", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = _json_lines(r.stdout)
     assert len(lines) == 1 and lines[0]["impl"] == "reference" and lines[0]["n_gpus"] == 2

@@ -211,3 +211,47 @@ def test_solve_wls_matches_direct_solve(ctx, dev, H, W, lam):
     assert relerr(ja.cpu().numpy(), ga.cpu().numpy()) < 1e-7  # multigrid and Jacobi PCG agree
     print(f"WLS {H}x{W} lam={lam}: {its} MG-PCG iterations (Jacobi-PCG: {jits}), rel.res {res:.2e}, "
           f"max rel.err a {max(relerr(ga.cpu().numpy()[..., c], oa[..., c]) for c in range(3)):.2e}")
+
+
+@pytest.mark.parametrize("H,W,lam", [(128, 128, 0.096), (350, 280, 1.5), (96, 80, 6.07)])
+def test_solve_wls_loop_modes_are_bit_identical(ctx, dev, H, W, lam, monkeypatch):
+    """The stopping test runs on the device after every iteration, so the solution and the iteration count do not depend on
+    how the launches reach the GPU: device-side WHILE loop (CUDA conditional graph node, the default), replayed
+    two-iteration graph with host checks per batch, plain stream launches."""
+    rng = np.random.default_rng(H + W)
+    cnt, _ = synth.pair(5, H, W)
+    lab = color.bgr2lab_u8(cnt)
+    a = 1.0 + 0.5 * rng.standard_normal((H, W, 3))
+    b = 0.2 * rng.standard_normal((H, W, 3))
+    rough = np.where(rng.random((H, W)) < 0.1, 1e-6, 1.0)
+    got = {}
+    for mode in ("2", "1", "0", "2"):   # mode 2 twice: the second call replays the cached graph
+        monkeypatch.setenv("NCT_WLS_LOOP", mode)
+        ga, gb = to_dev(a, dev), to_dev(b, dev)
+        n0 = ctx.launch_count
+        its, res = ctx.solve_wls(ga, gb, to_dev(rough, dev), to_dev(lab, dev), lam, 1.2, rel_tol=1e-8)
+        ctx.synchronize()
+        r = (its, ga.cpu().numpy().copy(), gb.cpu().numpy().copy(), ctx.launch_count - n0)
+        assert res <= 1e-8
+        if mode in got:
+            assert r[0] == got[mode][0] and np.array_equal(r[1], got[mode][1])
+        got[mode] = r
+    for mode in ("1", "0"):
+        assert got[mode][0] == got["2"][0], f"iteration counts differ: {got[mode][0]} vs {got['2'][0]}"
+        assert np.array_equal(got[mode][1].view(np.uint64), got["2"][1].view(np.uint64))
+        assert np.array_equal(got[mode][2].view(np.uint64), got["2"][2].view(np.uint64))
+    print(f"WLS {H}x{W}: {got['2'][0]} iterations in every loop mode; launches counted: while {got['2'][3]}, graph {got['1'][3]}, stream {got['0'][3]}")
+
+
+def test_wls_converged_start_returns_immediately(ctx, dev):
+    """x0 that already solves the system (constant maps, roughness 1 everywhere): zero iterations, in particular the
+    device-side loop must terminate when nothing ever sets a new residual."""
+    H, W = 64, 64
+    cnt, _ = synth.pair(6, H, W)
+    lab = color.bgr2lab_u8(cnt)
+    a = np.full((H, W, 3), 1.25)
+    b = np.full((H, W, 3), -0.5)
+    ga, gb = to_dev(a, dev), to_dev(b, dev)
+    its, res = ctx.solve_wls(ga, gb, to_dev(np.ones((H, W)), dev), to_dev(lab, dev), 0.5, 1.2, rel_tol=1e-8)
+    assert its == 0 and res <= 1e-8
+    assert np.array_equal(ga.cpu().numpy(), a) and np.array_equal(gb.cpu().numpy(), b)

@@ -264,3 +264,32 @@ def test_caffemodel_v2_records_load_too(pkg, dev, weights, tmp_path):
     with pytest.raises(pkg.NctError):
         c.load_caffemodel(str(tmp_path / "missing.caffemodel"))
     c.close(); c2.close()
+
+
+def test_headline_700x700_pair_reproduces_the_committed_golden_image(pkg, dev, weights):
+    """BASELINE.json configs[1], the pair bench.py times (synth.pair(0, 700, 700)), with the DEFAULT engine (tcgen05
+    kind::i8 exact fixed point): the final image equals tests/golden/fullsize_golden.npz byte for byte.  The golden was
+    computed offline by the oracle alone (fixed-point features, deterministic PatchMatch, canonical-order CG, DIRECT WLS
+    solve; tests/golden/make_fullsize_golden.py, 140 s of CPU) -- the GPU result is not compared with itself."""
+    import os
+    import zlib
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_golden.npz"))
+    seed, ch, cw, sh, sw = (int(v) for v in g["e2e700_cfg"])
+    cnt, stl = synth.pair(seed, ch, cw, sh, sw)
+    c = pkg.Context(0)
+    c.load_vgg19_weights(weights)
+    c.set_vgg_engine(3)
+    try:
+        # per level: the intermediate result image of a run stopped after that level, against the oracle's checksum
+        for l in range(5):
+            out = c.transfer_pair(cnt, stl, c.default_config(stop_after_level=l))
+            crc = zlib.crc32(np.ascontiguousarray(out).tobytes())
+            print(f"700x700 level {l}: image crc {crc:08x} (oracle {int(g['e2e700_crc'][l][4]):08x})")
+            assert crc == int(g["e2e700_crc"][l][4]), f"level {l} result differs from the oracle's"
+        ref = g["e2e700_out"]
+        ndiff = int((out != ref).sum())
+        print(f"700x700 end to end vs committed golden: {ndiff} of {out.size} bytes differ, PSNR {pipeline.psnr(out, ref):.1f} dB")
+        assert ndiff == 0
+    finally:
+        c.close()

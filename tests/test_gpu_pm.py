@@ -244,3 +244,35 @@ def test_bad_arguments_are_rejected(pkg, ctx, dev):
         ctx.patchmatch_single(t, t, ann, annd, pkg.make_params(48, 16, 16, 16, 16))
     with pytest.raises(pkg.NctError):  # patch 5 unsupported (reference fixes 3, CT/Config.h:70)
         ctx.patchmatch_single(t, t, ann, annd, pkg.make_params(64, 16, 16, 16, 16, patch=5))
+
+
+def test_finest_level_700x700x64_ten_iterations_matches_the_committed_golden(pkg, ctx, dev):
+    """The finest PatchMatch level at BASELINE's headline size, all 10 iterations, both directions, against
+    tests/golden/fullsize_golden.npz (oracle run offline by tests/golden/make_fullsize_golden.py): CRC32 of the whole
+    NNF and distance arrays, every 97th entry stored in full, and the evaluation counters."""
+    import os
+    import zlib
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_golden.npz"))
+    Cn, ah, aw, bh, bw, iters, rs, sa, sb = (int(v) for v in g["pm700_cfg"])
+    a = to_dev(oracle.l2norm_hwc(synth.feature_volume(sa, ah, aw, Cn)), dev)
+    b = to_dev(oracle.l2norm_hwc(synth.feature_volume(sb, bh, bw, Cn)), dev)
+    import torch
+
+    ann = torch.empty(ah * aw, dtype=torch.int32, device=dev)
+    bnn = torch.empty(bh * bw, dtype=torch.int32, device=dev)
+    annd = torch.empty(ah * aw, dtype=torch.float32, device=dev)
+    bnnd = torch.empty(bh * bw, dtype=torch.float32, device=dev)
+    ctx.init_ann(ann, ah, aw, bh, bw)
+    ctx.init_ann(bnn, bh, bw, ah, aw)
+    ctx.count_evals(True)
+    ctx.patchmatch_bidir(a, b, ann, annd, bnn, bnnd, pkg.make_params(Cn, ah, aw, bh, bw, iters=iters, rs_max=rs))
+    ev, _ = ctx.patchmatch_stats()
+    ctx.count_evals(False)
+    ga, gb = ann.cpu().numpy().view(np.uint32), bnn.cpu().numpy().view(np.uint32)
+    gad, gbd = annd.cpu().numpy(), bnnd.cpu().numpy()
+    assert np.array_equal(ga[::97], g["pm700_ann_s97"]) and np.array_equal(gb[::97], g["pm700_bnn_s97"])
+    assert np.array_equal(gad[::97].view(np.uint32), g["pm700_annd_s97"].view(np.uint32))
+    crcs = [zlib.crc32(np.ascontiguousarray(v).tobytes()) for v in (ga, gad, gb, gbd)]
+    assert crcs == [int(v) for v in g["pm700_crc"]]
+    assert ev == int(g["pm700_evals"].sum())

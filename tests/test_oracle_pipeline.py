@@ -95,3 +95,21 @@ def test_end_to_end_golden_fixture_is_reproduced_by_the_canonical_oracle():
     assert np.array_equal(crc, g[f"case{i}_crc"]), "an oracle stage changed its result"
     assert np.array_equal(np.array([levels[l]["cg_iters"] for l in range(5)], np.int32), g[f"case{i}_cg_iters"])
     assert np.array_equal(out, g[f"case{i}_out"]) and zlib.crc32(out.tobytes()) == zlib.crc32(g[f"case{i}_out"].tobytes())
+
+
+def test_fullsize_golden_fixture_is_self_consistent():
+    """tests/golden/fullsize_golden.npz (made offline by tests/golden/make_fullsize_golden.py; re-running the 700 x 700 oracle
+    takes minutes, so the CPU suite only checks the fixture's integrity): the stored final image has the stored level-4
+    checksum, the CG iteration counts are the reference's budgets (CT/ColorTransfer.cpp:917), the shapes are the headline's."""
+    import os
+    import zlib
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize_golden.npz"))
+    out = g["e2e700_out"]
+    assert out.shape == (700, 700, 3) and out.dtype == np.uint8
+    assert zlib.crc32(np.ascontiguousarray(out).tobytes()) == int(g["e2e700_crc"][4][4])
+    assert g["e2e700_crc"].shape == (5, 5) and g["e2e700_cg_iters"].shape == (5, 3)
+    assert list(g["e2e700_cg_iters"][4]) == [50, 50, 50] and all(list(r) == [100, 100, 100] for r in g["e2e700_cg_iters"][:4])
+    assert g["pm700_ann_s97"].shape == ((700 * 700 + 96) // 97,) and g["pm700_crc"].shape == (4,)
+    cnt, stl = synth.pair(*[int(v) for v in g["e2e700_cfg"]])
+    assert cnt.shape == (700, 700, 3)  # the pair bench.py's first context runs

@@ -36,16 +36,17 @@ def _worker(rank, world, port, n_pairs, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     mine = sh.shard_indices(n_pairs, rank, world)
-    # stand-in for the per-pair transfer: a result image that encodes the pair index
-    local = [torch.full((4, 5, 3), i, dtype=torch.uint8) for i in mine]
+    # stand-in for the per-pair transfer: a result image that encodes the pair index; pairs.txt images differ in size
+    local = [torch.full((4 + i % 3, 5 + i % 2, 3), i, dtype=torch.uint8) for i in mine]
     out = sh.gather_results(local, n_pairs, rank, world, dist)
     if rank == 0:
+        assert all(tuple(t.shape) == (4 + i % 3, 5 + i % 2, 3) for i, t in enumerate(out))
         q.put([int(t[0, 0, 0]) for t in out])
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_pairs", [(2, 9), (2, 4), (3, 7)])
+@pytest.mark.parametrize("world,n_pairs", [(2, 9), (2, 4), (3, 7), (3, 2), (2, 1)])  # the last two: ranks without any pair
 def test_gather_over_gloo(world, n_pairs):
     import torch.multiprocessing as mp
 
