@@ -224,6 +224,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    stagger_ms = float(os.environ.get("NCT_BENCH_STAGGER_MS", args.stagger_ms))
+
     def run_steps(n, mode, record=None):
         """n steps of P pairs per rank.  mode "dev": inputs resident in HBM (nct_transfer_pair_dev); "api": the host-buffer
         C-ABI call nct_transfer_pair (pinned host in / out, N = 1); "copies": N > 1 end to end = pinned H2D copies of the
@@ -241,6 +243,10 @@ def run_ours(args):
                 torch.cuda.set_device(dev)  # the current device is per host thread
                 if record is not None:
                     record[0][j].record(streams[j])
+                if stagger_ms > 0:
+                    # the P streams start one P-th of a pair apart (inside the timed region: the idle time counts), so that
+                    # they sit in different stages of the pipeline: PatchMatch (fills the GPU) next to the solvers' small kernels
+                    time.sleep(j * stagger_ms / 1e3)
                 for i in range(n):
                     q = i % npairs
                     if mode == "api":
@@ -521,6 +527,7 @@ def main():
     ap.add_argument("--no-full-size-check", action="store_true", help="--impl reference: skip the single full-size pair timed after the steps")
     ap.add_argument("--serial-reference-check", action="store_true", help="--impl reference: also time the reference-layout serial PatchMatch variant once")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stagger-ms", type=float, default=0.0, help="start the P streams of a rank this many ms apart (inside the timed region)")
     ap.add_argument("--pairs-in-flight", type=int, default=6, help="independent pairs processed concurrently per GPU (one step = this many pairs per rank)")
     ap.add_argument("--vgg-engine", type=int, default=3, choices=[0, 1, 2, 3],
                     help="convolution engine: 0 fp32 CUDA cores, 1 tcgen05 tf32, 2 tcgen05 3xTF32, 3 tcgen05 int8 exact fixed point (default)")

@@ -312,6 +312,20 @@ int nct_png_write(const char *path, const uint8_t *bgr, int h, int w);
  * 1000 are shrunk first (MAX_SIZE, CT/Config.h:5).  A pair that cannot be read is reported and skipped. */
 int nct_run_pairs(nct_ctx *ctx, const char *input_dir, const char *output_dir, const nct_config *cfg, int rank, int world,
                   int *pairs_done);
+/* The same with options and counters.  flags: NCT_RUN_RESUME = skip a pair whose output file already exists (restart of an
+ * interrupted list; the reference recomputes everything, NCT/main.cu:471-540), NCT_RUN_VIS = also write the per-level debug
+ * artefacts of the reference's ENABLE_VIS build next to the result (nct_set_vis).  pairs_failed counts the owned pairs
+ * that could not be read, processed or written (each is reported on stdout and skipped, as nct_run_pairs does). */
+#define NCT_RUN_RESUME 1
+#define NCT_RUN_VIS 2
+int nct_run_pairs_ex(nct_ctx *ctx, const char *input_dir, const char *output_dir, const nct_config *cfg, int rank, int world,
+                     int flags, int *pairs_done, int *pairs_failed, int *pairs_skipped);
+/* Debug artefacts of the reference's ENABLE_VIS build (NCT/main.cu:169-173, 333-347, 361-364, 382-422; off by default there
+ * too, CT/Config.h:8): while `dir` is set, nct_transfer_pair(_dev) on this context writes, per pyramid level l,
+ * <dir>/<prefix>_{aFlow,bFlow,tCnt,tStl,knn,errMap,refine_init,refine_nonlocal,aVis,aVis_init,aVis_nonlocal,bVis,bVis_init,
+ * bVis_nonlocal}_<l>.png and <dir>/<prefix>_cluster_small.png (host rendering, slow: a debugging aid).  dir = NULL: off. */
+int nct_set_vis(nct_ctx *ctx, const char *dir, const char *prefix);
+
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,8 @@ ABI = {
     "nct_png_free": (None, [C.POINTER(C.c_uint8)]),
     "nct_png_write": (_i, [C.c_char_p, _p, _i, _i]),
     "nct_run_pairs": (_i, [c_ctx_p, C.c_char_p, C.c_char_p, C.POINTER(Config), _i, _i, C.POINTER(_i)]),
+    "nct_run_pairs_ex": (_i, [c_ctx_p, C.c_char_p, C.c_char_p, C.POINTER(Config), _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "nct_set_vis": (_i, [c_ctx_p, C.c_char_p, C.c_char_p]),
     "nct_cluster_features": (_i, [c_ctx_p, _p, _i, _i, _i, _i, _i, _p]),
     "nct_find_knns": (_i, [c_ctx_p, _p, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
     "nct_find_knns_brute": (_i, [c_ctx_p, _p, _i, _i, _i, _p, _i, _i, _i, _p, _p]),
@@ -565,3 +567,15 @@ class Context:
         self._check(self.lib.nct_run_pairs(self.h, input_dir.encode(), output_dir.encode(),
                                            C.byref(cfg) if cfg is not None else None, rank, world, C.byref(done)))
         return done.value
+
+    def run_pairs_ex(self, input_dir, output_dir, cfg=None, rank=0, world=1, resume=False, vis=False):
+        """nct_run_pairs_ex: the same with resume-by-existing-output / ENABLE_VIS artefacts; returns (done, failed, skipped)"""
+        done, failed, skipped = _i(0), _i(0), _i(0)
+        self._check(self.lib.nct_run_pairs_ex(self.h, input_dir.encode(), output_dir.encode(), C.byref(cfg) if cfg is not None else None,
+                                              rank, world, (1 if resume else 0) | (2 if vis else 0), C.byref(done), C.byref(failed),
+                                              C.byref(skipped)))
+        return done.value, failed.value, skipped.value
+
+    def set_vis(self, directory, prefix="pair"):
+        """per-level debug artefacts of the reference's ENABLE_VIS build; directory None switches them off"""
+        self._check(self.lib.nct_set_vis(self.h, directory.encode() if directory else None, prefix.encode() if prefix else None))

@@ -3,7 +3,9 @@
 // Same surface: <input_dir>/pairs.txt with lines "content style bds\n", images relative to input_dir, longer side
 // clamped to MAX_SIZE = 1000 (CT/Config.h:5, NCT/main.cu:500-522), output "<out>/<cnt>_<stl>_<bds %2.2f>.png",
 // same stdout lines.  Added: (rank, world) sharding -- rank r processes the lines i with i % world == r -- so one
-// process per GPU covers a pair list with no communication (pairs are independent).
+// process per GPU covers a pair list with no communication (pairs are independent); nct_run_pairs_ex adds
+// resume-by-existing-output, the ENABLE_VIS artefacts (8f-3) and counts of failed / skipped pairs.
+// Images are PNG only (no libjpeg / libtiff in this image; the reference's imread also takes JPEG, BMP, ...).
 #include "nct_internal.h"
 #include <sys/stat.h>
 #include <cstdio>
@@ -14,6 +16,7 @@ extern "C" {
 int nct_png_read(const char *path, uint8_t **bgr_out, int *h_out, int *w_out);
 void nct_png_free(uint8_t *p);
 int nct_png_write(const char *path, const uint8_t *bgr, int h, int w);
+int nct_set_vis(nct_ctx *ctx, const char *dir, const char *prefix);
 }
 
 namespace {
@@ -58,8 +61,17 @@ int clamp_size(nct_ctx *ctx, uint8_t *&img, int &h, int &w)
 
 extern "C" {
 
+int nct_run_pairs_ex(nct_ctx *ctx, const char *input_dir, const char *output_dir, const nct_config *cfg_in, int rank, int world,
+                     int flags, int *pairs_done, int *pairs_failed, int *pairs_skipped);
+
 int nct_run_pairs(nct_ctx *ctx, const char *input_dir, const char *output_dir, const nct_config *cfg_in, int rank, int world,
                   int *pairs_done)
+{
+    return nct_run_pairs_ex(ctx, input_dir, output_dir, cfg_in, rank, world, 0, pairs_done, nullptr, nullptr);
+}
+
+int nct_run_pairs_ex(nct_ctx *ctx, const char *input_dir, const char *output_dir, const nct_config *cfg_in, int rank, int world,
+                     int flags, int *pairs_done, int *pairs_failed, int *pairs_skipped)
 {
     if (!ctx || !input_dir || !output_dir) return NCT_ERR_ARG;
     cudaSetDevice(ctx->device);  // the calling thread may be a fresh worker thread (CLI -ngpu / -inflight)
@@ -77,7 +89,7 @@ int nct_run_pairs(nct_ctx *ctx, const char *input_dir, const char *output_dir, c
     }
     char cntFile[260], stlFile[260];
     float bdsWeight = 0.f;
-    int line = 0, done = 0;
+    int line = 0, done = 0, failed = 0, skipped = 0;
     while (fscanf(fp, "%259s %259s %f\n", cntFile, stlFile, &bdsWeight) == 3) {
         const int idx = line++;
         if (idx % world != rank) continue;
@@ -85,16 +97,29 @@ int nct_run_pairs(nct_ctx *ctx, const char *input_dir, const char *output_dir, c
         printf("-----------------***********************----------------------\n");
         printf("Content: %s, style: %s, BDS weight: %f.\n", cntFile, stlFile, cfg.bds_weight);
         const std::string cntStr = in_dir + "/" + cntFile, stlStr = in_dir + "/" + stlFile;
+        char stem[512], fileName[1024];
+        snprintf(stem, sizeof(stem), "%s_%s_%2.2f", base_name(cntStr).c_str(), base_name(stlStr).c_str(), cfg.bds_weight);
+        snprintf(fileName, sizeof(fileName), "%s/%s.png", out_dir.c_str(), stem);
+        if (flags & NCT_RUN_RESUME) {   // resume an interrupted pair list: a result that is already there is kept
+            struct stat st;
+            if (stat(fileName, &st) == 0 && st.st_size > 0) {
+                printf("Output %s exists, skipped (resume).\n\n", fileName);
+                skipped++;
+                continue;
+            }
+        }
         uint8_t *cnt = nullptr, *stl = nullptr;
         int ch = 0, cw = 0, sh = 0, sw = 0;
         if (nct_png_read(cntStr.c_str(), &cnt, &ch, &cw) != NCT_OK) {
             printf("Error: Fail reading content image: %s\n", cntStr.c_str());
+            failed++;
             continue;
         }
         printf("\n**Read content file: %s, w = %d, h = %d\n", cntStr.c_str(), cw, ch);
         if (nct_png_read(stlStr.c_str(), &stl, &sh, &sw) != NCT_OK) {
             printf("Error: Fail reading style image: %s\n", stlStr.c_str());
             nct_png_free(cnt);
+            failed++;
             continue;
         }
         printf("Read style file: %s, w = %d, h = %d\n", stlStr.c_str(), sw, sh);
@@ -102,11 +127,10 @@ int nct_run_pairs(nct_ctx *ctx, const char *input_dir, const char *output_dir, c
         if (!rc) rc = clamp_size(ctx, stl, sh, sw);
         uint8_t *out = (uint8_t *)malloc((size_t)ch * cw * 3);
         if (!rc && !out) rc = NCT_ERR_NOMEM;
+        if (flags & NCT_RUN_VIS) nct_set_vis(ctx, out_dir.c_str(), stem);   // ENABLE_VIS artefacts next to the result
         if (!rc) rc = nct_transfer_pair(ctx, cnt, ch, cw, stl, sh, sw, &cfg, out);
+        if (flags & NCT_RUN_VIS) nct_set_vis(ctx, nullptr, nullptr);
         if (!rc) {
-            char fileName[1024];
-            snprintf(fileName, sizeof(fileName), "%s/%s_%s_%2.2f.png", out_dir.c_str(), base_name(cntStr).c_str(), base_name(stlStr).c_str(),
-                     cfg.bds_weight);
             if (nct_png_write(fileName, out, ch, cw) != NCT_OK) rc = nct_fail(ctx, NCT_ERR_IO, "cannot write %s", fileName);
             else printf("Final output file: %s.\n\n", fileName);
         }
@@ -115,12 +139,15 @@ int nct_run_pairs(nct_ctx *ctx, const char *input_dir, const char *output_dir, c
         free(out);
         if (rc) {
             printf("Error: pair %d failed: %s\n", idx, nct_last_error(ctx));
+            failed++;
             continue;  // the reference has no error path; keep going with the next pair
         }
         done++;
     }
     fclose(fp);
     if (pairs_done) *pairs_done = done;
+    if (pairs_failed) *pairs_failed = failed;
+    if (pairs_skipped) *pairs_skipped = skipped;
     return NCT_OK;
 }
 

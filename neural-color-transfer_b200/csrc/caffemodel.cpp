@@ -14,6 +14,10 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <sys/stat.h>
 
 namespace {
 
@@ -143,10 +147,26 @@ bool parse_layer(Reader r, bool v1, Layer &L)
 
 extern "C" {
 
-int nct_vgg19_load_caffemodel(nct_ctx *ctx, const char *path)
+// parsed trunk weights of one file: layer i -> (weights O x I x 3 x 3, bias O)
+struct ParsedModel {
+    std::vector<std::vector<float>> W, B;
+};
+
+// The ~550 MB file is read and parsed ONCE per process: the CLI creates ngpu x inflight contexts that all load the same
+// model (every later context only uploads).  Keyed by path, size and modification time.
+static int parse_caffemodel_cached(nct_ctx *ctx, const char *path, std::shared_ptr<const ParsedModel> &out)
 {
-    if (!ctx || !path) return NCT_ERR_ARG;
-    cudaSetDevice(ctx->device);
+    static std::mutex mu;
+    static std::map<std::string, std::shared_ptr<const ParsedModel>> cache;
+    struct stat st;
+    if (stat(path, &st) != 0) return nct_fail(ctx, NCT_ERR_IO, "cannot open caffemodel '%s'", path);
+    char keybuf[64];
+    snprintf(keybuf, sizeof(keybuf), "|%lld|%lld", (long long)st.st_size, (long long)st.st_mtime);
+    const std::string key = std::string(path) + keybuf;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { out = it->second; return NCT_OK; }
+
     FILE *fp = fopen(path, "rb");
     if (!fp) return nct_fail(ctx, NCT_ERR_IO, "cannot open caffemodel '%s'", path);
     fseek(fp, 0, SEEK_END);
@@ -158,7 +178,9 @@ int nct_vgg19_load_caffemodel(nct_ctx *ctx, const char *path)
     if (sz <= 0 || got != buf.size()) return nct_fail(ctx, NCT_ERR_IO, "cannot read caffemodel '%s'", path);
 
     const int nlayers = nct_vgg19_num_layers();
-    std::vector<bool> found((size_t)nlayers, false);
+    auto model = std::make_shared<ParsedModel>();
+    model->W.resize((size_t)nlayers);
+    model->B.resize((size_t)nlayers);
     Reader r{buf.data(), buf.data() + buf.size()};
     uint32_t f, w;
     while (r.tag(f, w)) {
@@ -172,15 +194,14 @@ int nct_vgg19_load_caffemodel(nct_ctx *ctx, const char *path)
                 int cin = 0, cout = 0;
                 nct_vgg19_layer_shape(i, &cin, &cout);
                 if (L.blobs.size() < 2) return nct_fail(ctx, NCT_ERR_IO, "layer %s has %zu blobs, expected weights + bias", L.name.c_str(), L.blobs.size());
-                const Blob &W = L.blobs[0], &B = L.blobs[1];
+                Blob &W = L.blobs[0], &B = L.blobs[1];
                 if (W.data.size() != (size_t)cout * cin * 9 || B.data.size() != (size_t)cout)
                     return nct_fail(ctx, NCT_ERR_IO, "layer %s: blob sizes %zu / %zu do not match %d x %d x 3 x 3 / %d", L.name.c_str(),
                                     W.data.size(), B.data.size(), cout, cin, cout);
                 if (W.shape.size() == 4 && (W.shape[0] != cout || W.shape[1] != cin || W.shape[2] != 3 || W.shape[3] != 3))
                     return nct_fail(ctx, NCT_ERR_IO, "layer %s: unexpected weight shape", L.name.c_str());
-                int rc = nct_vgg19_set_weights(ctx, i, W.data.data(), B.data.data());
-                if (rc) return rc;
-                found[(size_t)i] = true;
+                model->W[(size_t)i] = std::move(W.data);
+                model->B[(size_t)i] = std::move(B.data);
             }
         } else {
             r.skip(w);
@@ -189,7 +210,23 @@ int nct_vgg19_load_caffemodel(nct_ctx *ctx, const char *path)
     }
     if (!r.ok) return nct_fail(ctx, NCT_ERR_IO, "'%s' is not a valid serialized NetParameter", path);
     for (int i = 0; i < nlayers; ++i)
-        if (!found[(size_t)i]) return nct_fail(ctx, NCT_ERR_IO, "'%s' has no weights for layer %s", path, nct_vgg19_layer_name(i));
+        if (model->W[(size_t)i].empty()) return nct_fail(ctx, NCT_ERR_IO, "'%s' has no weights for layer %s", path, nct_vgg19_layer_name(i));
+    cache[key] = model;
+    out = model;
+    return NCT_OK;
+}
+
+int nct_vgg19_load_caffemodel(nct_ctx *ctx, const char *path)
+{
+    if (!ctx || !path) return NCT_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    std::shared_ptr<const ParsedModel> model;
+    int rc = parse_caffemodel_cached(ctx, path, model);
+    if (rc) return rc;
+    for (int i = 0; i < nct_vgg19_num_layers(); ++i) {
+        rc = nct_vgg19_set_weights(ctx, i, model->W[(size_t)i].data(), model->B[(size_t)i].data());
+        if (rc) return rc;
+    }
     return NCT_OK;
 }
 

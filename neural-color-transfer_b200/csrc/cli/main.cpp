@@ -7,7 +7,8 @@
 // i mod N; the reference is single-GPU (NCT/main.cu:563-565).  -inflight P keeps P pairs in flight per GPU (P contexts,
 // streams and host threads per GPU; pair i on worker i mod (N * P)): the coarse pyramid levels and the solvers' small
 // kernels do not fill a B200 on their own, so P = 4..6 raises the throughput of a long pair list by ~1.5x.  With P > 1
-// the progress lines of different pairs interleave on stdout.  -engine selects the convolution engine (the reference has
+// the progress lines of different pairs interleave on stdout.  -resume 1 skips pairs whose output exists, -vis 1 writes the
+// ENABLE_VIS debug images.  Exit code: 0 ok, -1 usage, 1 set-up failure, 2 at least one pair failed.  Images are PNG only.  -engine selects the convolution engine (the reference has
 // whatever algorithm cuDNN picks): 3 = tensor cores, exact fixed point (tcgen05 kind::i8 digit planes, INT32 accumulation;
 // default -- a pure function of the inputs, bit-identical to the oracle's fixed-point features); 2 = tensor cores, 3xTF32;
 // 1 = plain TF32; 0 = FP32 CUDA cores in the canonical FP32 summation order (bit-identical to the oracle's FP32 features).
@@ -21,7 +22,6 @@
 
 extern "C" int nct_vgg19_load_caffemodel(nct_ctx *ctx, const char *path);
 extern "C" int nct_vgg19_set_engine(nct_ctx *ctx, int engine);
-extern "C" int nct_run_pairs(nct_ctx *ctx, const char *input_dir, const char *output_dir, const nct_config *cfg, int rank, int world, int *pairs_done);
 
 struct Param { const char *arg; const char *desc; int kind; void *dst; };  // kind 0 string, 1 int, 2 double
 
@@ -38,7 +38,7 @@ int main(int argc, char **argv)
     nct_config cfg;
     nct_config_default(&cfg);
     std::string model_dir, input_dir, output_dir;
-    int gpu_id = 0, ngpu = 1, inflight = 1, engine = 3;
+    int gpu_id = 0, ngpu = 1, inflight = 1, engine = 3, resume = 0, vis = 0;
     std::vector<Param> params = {
         {"m", "Directory of network models.", 0, &model_dir},
         {"i", "Input directory of content and style images and pairs.txt.", 0, &input_dir},
@@ -51,6 +51,8 @@ int main(int argc, char **argv)
         {"w", "Initial value of WLS weight (default: 0.024).", 2, &cfg.wls_lambda_init},
         {"ngpu", "Number of GPUs to spread the pair list over, starting at -g (default: 1).", 1, &ngpu},
         {"inflight", "Pairs processed concurrently per GPU (default: 1).", 1, &inflight},
+        {"resume", "1: skip pairs whose output file already exists (restart of an interrupted list; default: 0).", 1, &resume},
+        {"vis", "1: also write the per-level debug images of the reference's ENABLE_VIS build into the output directory (default: 0).", 1, &vis},
         {"engine", "Convolution engine: 0 FP32 CUDA cores, 1 tcgen05 TF32, 2 tcgen05 3xTF32, 3 tcgen05 INT8 exact fixed point (default: 3; 0 and 3 are bit-exact against the oracle).", 1, &engine},
     };
     int i = 1;
@@ -95,14 +97,21 @@ int main(int argc, char **argv)
         }
     }
     std::vector<std::thread> workers;
-    std::vector<int> done((size_t)nworkers, 0), rcs((size_t)nworkers, 0);
+    std::vector<int> done((size_t)nworkers, 0), failed((size_t)nworkers, 0), skipped((size_t)nworkers, 0), rcs((size_t)nworkers, 0);
+    const int flags = (resume ? NCT_RUN_RESUME : 0) | (vis ? NCT_RUN_VIS : 0);
     for (int r = 0; r < nworkers; ++r)
-        workers.emplace_back([&, r]() { rcs[r] = nct_run_pairs(ctxs[r], input_dir.c_str(), output_dir.c_str(), &cfg, r, nworkers, &done[r]); });
+        workers.emplace_back([&, r]() {
+            rcs[r] = nct_run_pairs_ex(ctxs[r], input_dir.c_str(), output_dir.c_str(), &cfg, r, nworkers, flags, &done[r], &failed[r], &skipped[r]);
+        });
     for (auto &t : workers) t.join();
-    int rc = 0;
+    int rc = 0, nfailed = 0;
     for (int r = 0; r < nworkers; ++r) {
         if (rcs[r]) { fprintf(stderr, "Error: %s\n", nct_last_error(ctxs[r])); rc = 1; }
+        nfailed += failed[r];
         nct_destroy(ctxs[r]);
     }
+    // the reference has no error path at all (a bad image is reported and skipped, the exit code stays 0); a batch tool
+    // that silently drops pairs is worse: 2 = finished, but at least one pair failed
+    if (!rc && nfailed) { fprintf(stderr, "Error: %d pair(s) failed.\n", nfailed); rc = 2; }
     return rc;
 }

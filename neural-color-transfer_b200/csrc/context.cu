@@ -286,16 +286,14 @@ int nct_create(int gpu_id, nct_ctx **out)
     return NCT_OK;
 }
 
-// defined by vgg19.cu / pipeline.cu
+// defined by vgg19.cu
 extern "C++" void nct_vgg_free(nct_ctx *ctx);
-extern "C++" void nct_pipe_free(nct_ctx *ctx);
 
 int nct_destroy(nct_ctx *ctx)
 {
     if (!ctx) return NCT_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    nct_pipe_free(ctx);
     nct_vgg_free(ctx);
     nct_graphs_free(ctx);
     for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }

@@ -81,7 +81,7 @@ int nct_png_read(const char *path, uint8_t **bgr_out, int *h_out, int *w_out)
         pos += 12 + (size_t)len;
     }
     if (!have_ihdr || W == 0 || H == 0 || W > 32768 || H > 32768 || interlace != 0) return NCT_ERR_IO;
-    if (!(depth == 8 || depth == 16) && !(ctype == 3 && (depth == 1 || depth == 2 || depth == 4 || depth == 8))) return NCT_ERR_IO;
+    if (!(depth == 8 || depth == 16) && !((ctype == 3 || ctype == 0) && (depth == 1 || depth == 2 || depth == 4))) return NCT_ERR_IO;
     int channels;
     switch (ctype) {
     case 0: channels = 1; break;
@@ -135,6 +135,10 @@ int nct_png_read(const char *path, uint8_t **bgr_out, int *h_out, int *w_out)
                 }
                 if ((size_t)idx * 3 + 2 < plte.size()) { r = plte[idx * 3]; g = plte[idx * 3 + 1]; b = plte[idx * 3 + 2]; }
                 else r = g = b = 0;
+            } else if (ctype == 0 && depth < 8) {   // packed greyscale samples, scaled to 8 bits
+                const int per = 8 / depth, maxv = (1 << depth) - 1;
+                const int v = (cur[x / per] >> ((per - 1 - x % per) * depth)) & maxv;
+                r = g = b = (uint8_t)(v * 255 / maxv);
             } else if (channels <= 2) {
                 r = g = b = cur[(size_t)x * channels * step];
             } else {

@@ -65,9 +65,11 @@ struct nct_ctx {
 
     std::map<std::string, NctGraph> graphs;
 
+    // ENABLE_VIS artefacts (vis.cpp): written per level into vis_dir when it is not empty
+    std::string vis_dir, vis_prefix;
+
     // opaque sub-module states (owned, freed in nct_destroy)
     struct VggState *vgg = nullptr;
-    struct PipeState *pipe = nullptr;
 };
 
 int nct_fail(nct_ctx *ctx, int code, const char *fmt, ...);
@@ -134,5 +136,16 @@ struct NctStageTimer {
     NctStageTimer(nct_ctx *c, int stage);
     ~NctStageTimer();
 };
+
+// vis.cpp (debug artefacts of the reference's ENABLE_VIS build)
+int nct_vis_cluster_small(nct_ctx *ctx, const int *labels_dev, int lh, int lw);
+int nct_vis_flows(nct_ctx *ctx, int level, const uint32_t *ann_dev, const uint32_t *bnn_dev, const uint8_t *cnt_dev, const uint8_t *stl_dev,
+                  int ah, int aw, int bh, int bw);
+int nct_vis_knn_clusters(nct_ctx *ctx, int level, const int *labels_dev, int lh, int lw, int h, int w, int samples);
+int nct_vis_error_map(nct_ctx *ctx, int level, const float *err_dev, int h, int w);
+int nct_vis_coefficients(nct_ctx *ctx, int level, const char *suffix, const double *a_dev, const double *b_dev, int mh, int mw, int H, int W,
+                         int samples, std::vector<double> *a_up, std::vector<double> *b_up);
+int nct_vis_refine(nct_ctx *ctx, int level, const char *what, const uint8_t *cnt_lab_full_dev, const double *a_full_dev, const double *b_full_dev,
+                   int H, int W);
 
 static inline int nct_div_up(int a, int b) { return (a + b - 1) / b; }

@@ -1140,12 +1140,284 @@ __global__ void __launch_bounds__(128, SPEC ? 3 : (HALF ? (AS ? (C == 64 ? 6 : 5
     }
 }
 
+// ------------------------------------------------------------------ tiled step kernel with cp.async-staged candidates
+// pm_step_t_kernel is latency-bound on the candidate chain of a query: the rows of candidate i + 1 are only requested
+// after candidate i has been reduced -- for the random search necessarily so in program order, because the window of
+// candidate i + 1 is centred on the best match AFTER candidate i.  More loads in flight per thread cost registers (36
+// per candidate at C = 64) and with them resident warps: measured slower (profiles/r1_pm_tuning.md, NCT_PM_SPEC).
+// Here the rows of up to NB candidates of a query are in flight at once without holding registers: every lane copies
+// its 16-byte pieces global -> shared with cp.async (LDGSTS; .ca keeps the L1 allocation the neighbouring queries'
+// overlapping patches profit from) into NB staging buffers of its group and reads back only what it copied itself, so
+// no barrier is needed -- cp.async.wait_all orders a lane's own copies.  A ROUND = the next <= NB candidates of the
+// query: the propagation candidates are known; the random-search positions are computed from the current best, i.e.
+// under the assumption that no candidate of the round is accepted (the common case after the first iterations).  The
+// round is then consumed in order with the ordinary acceptance rule; every candidate's position is recomputed from
+// the best match at that point, and if it differs from the speculated one (an acceptance moved the window) the round
+// ends there and the next round starts from that candidate.  The sequence of (position, distance, decision) is
+// therefore exactly pm_step_t_kernel's -- same field, same distances, same evaluation counters (a mis-speculated copy is
+// not an evaluation) -- and the arithmetic per distance is u_eval's predicated path, bit for bit.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int C, bool HALF, int NB>
+__global__ void __launch_bounds__(128) pm_step_ta_kernel(const PMStep s, const int tile)
+{
+    using T = UTraits<C, HALF>;
+    constexpr int GL = T::LANES, NV = T::NV, ST = T::STRIDE;
+    constexpr int BUF = 9 * NV * GL;   // float4 per candidate buffer, [patch pixel][vector][lane of the group]
+    extern __shared__ float4 pm_stage[];  // [group of the block][NB][BUF]
+    __shared__ TQueryState st_all[4][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    TQueryState *st = st_all[wib];
+    const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const int q_first = warp_global * tile;
+    if (q_first >= s.nq_total) return;  // whole warps leave together
+    const int jump = s.jump;
+    const int n_first = s.first ? 1 : 0;
+    unsigned n_eval = 0, n_ref = 0;
+
+    // ---- phase 1: one lane per query (identical to pm_step_t_kernel)
+    bool has_work = false;
+    {
+        const int qidx = q_first + lane;
+        if (lane < tile && qidx < s.nq_total) {
+            const int dsel = qidx >= s.nq0 ? 1 : 0;
+            const PMDir &D = s.d[dsel];
+            const int p = qidx - (dsel ? s.nq0 : 0);
+            const int aw = D.aw, ah = D.ah, bw = D.bw, bh = D.bh;
+            const int ax = p % aw, ay = p / aw;
+            const uint32_t v0 = D.nnf_in[p];
+            uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            int n = 0;
+            const int qx[4] = {ax - jump, ax + jump, ax, ax};
+            const int qy[4] = {ay, ay, ay - jump, ay + jump};
+            const int sx[4] = {jump, -jump, 0, 0};
+            const int sy[4] = {0, 0, jump, -jump};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (qx[k] >= 0 && qx[k] < aw && qy[k] >= 0 && qy[k] < ah) {
+                    const int qi = qy[k] * aw + qx[k];
+                    const uint32_t vp = D.nnf_in[qi];
+                    const int xp = int_to_x(vp) + sx[k], yp = int_to_y(vp) + sy[k];
+                    if (yp >= 0 && yp < bh && xp >= 0 && xp < bw) {
+                        n_ref++;
+                        const uint32_t cv = xy_to_int(xp, yp);
+                        const bool dup = (cv == v0) || (n > 0 && cv == c0) || (n > 1 && cv == c1) || (n > 2 && cv == c2);
+                        const bool stale = s.t >= 4 && (int)D.lc_in[qi] <= s.t - 5;  // D4
+                        if (!dup && !stale) {
+                            if (n == 0) c0 = cv;
+                            else if (n == 1) c1 = cv;
+                            else if (n == 2) c2 = cv;
+                            else c3 = cv;
+                            n++;
+                        }
+                    }
+                }
+            }
+            const int total = n_first + n + (s.do_random ? D.n_mag : 0);
+            if (total == 0) {  // nothing to compare: the entry stays
+                D.nnf_out[p] = v0;
+                D.lc_out[p] = D.lc_in[p];
+            } else {
+                has_work = true;
+                st[lane].v0 = v0; st[lane].c0 = c0; st[lane].c1 = c1; st[lane].c2 = c2; st[lane].c3 = c3;
+                st[lane].qidx = qidx;
+                st[lane].n = n;
+                st[lane].dbest = s.first ? 0.f : D.nnd[p];
+            }
+        }
+    }
+    const unsigned work = __ballot_sync(0xffffffffu, has_work);
+    __syncwarp();
+
+    // ---- phase 2: one group of 16 / 32 lanes per query with work
+    const int grp = HALF ? (lane >> 4) : 0;
+    const int j = HALF ? (lane & 15) : lane;
+    const unsigned mask = HALF ? (grp ? 0xffff0000u : 0x0000ffffu) : 0xffffffffu;
+    float4 *gbuf = pm_stage + (size_t)((wib * (HALF ? 2 : 1) + grp) * NB) * BUF + j;
+    const int nwork = __popc(work);
+#pragma unroll 1
+    for (int r = grp; r < nwork; r += (HALF ? 2 : 1)) {
+        const int src = (int)__fns(work, 0, r + 1);
+        const TQueryState q0 = st[src];
+        const int qidx = q0.qidx;
+        const int dsel = qidx >= s.nq0 ? 1 : 0;
+        const PMDir &D = s.d[dsel];
+        const int p = qidx - (dsel ? s.nq0 : 0);
+        const int aw = D.aw, ah = D.ah, bw = D.bw, bh = D.bh;
+        const int ax = p % aw, ay = p / aw;
+        const uint32_t v0 = q0.v0;
+        int xbest = int_to_x(v0), ybest = int_to_y(v0);
+        float dbest = q0.dbest;
+        const int n_prop_end = n_first + q0.n;
+        const int total = n_prop_end + (s.do_random ? D.n_mag : 0);
+        const unsigned amask = patch_mask(ax, ay, aw, ah);
+        const float *a_base = D.a + ((size_t)ay * aw + ax) * C + j * 4;
+        float4 areg[T::A_IN_REGS ? 9 * NV : 1];
+        if (T::A_IN_REGS) {
+#pragma unroll
+            for (int pi = 0; pi < 9; ++pi) {
+                const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if ((amask >> pi) & 1u) v = ldg4(a_base + ((ptrdiff_t)dy * aw + dx) * C + k * ST);
+                    areg[pi * NV + k] = v;
+                }
+            }
+        }
+        const float *u = D.rng + (size_t)ax * D.ndraws + (size_t)s.iter * 2 * D.n_mag;
+        // candidate i of this query given the best match (xb, yb): a propagation list entry, or the random-search draw
+        auto candidate = [&](int i, int xb, int yb, int &cx, int &cy) {
+            if (i < n_prop_end) {
+                const int k = i - n_first;
+                const uint32_t cv = (i < n_first) ? v0 : (k == 0 ? q0.c0 : (k == 1 ? q0.c1 : (k == 2 ? q0.c2 : q0.c3)));
+                cx = int_to_x(cv);
+                cy = int_to_y(cv);
+            } else {
+                const int m = i - n_prop_end;
+                const int mag = D.rs_start >> m;
+                const int xmin = max(xb - mag, 0), xmax = min(xb + mag + 1, bw);
+                const int ymin = max(yb - mag, 0), ymax = min(yb + mag + 1, bh);
+                const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
+                // (int)(u * w) % w with u in (0, 1]: the product is in [0, w], so the modulo only maps w to 0
+                const int wx = xmax - xmin, wy = ymax - ymin;
+                const int tx = (int)(__fmul_rn(u1, (float)wx)), ty = (int)(__fmul_rn(u2, (float)wy));
+                cx = xmin + (tx >= wx ? tx - wx : tx);
+                cy = ymin + (ty >= wy ? ty - wy : ty);
+            }
+        };
+        int i = 0;
+#pragma unroll 1
+        while (i < total) {
+            // ---- issue a round: copies of candidates i .. i + NB - 1, positions speculated from the current best
+            uint32_t pos[NB];
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                pos[k] = 0xFFFFFFFFu;  // "nothing staged in buffer k"
+                if (i + k < total) {
+                    int cx, cy;
+                    candidate(i + k, xbest, ybest, cx, cy);
+                    const bool d3 = (i + k >= n_prop_end) && cx == xbest && cy == ybest;  // would be skipped, not evaluated
+                    if (!d3) {
+                        pos[k] = xy_to_int(cx, cy);
+                        const unsigned valid = amask & patch_mask(cx, cy, bw, bh);
+                        const float *b_base = D.b + ((size_t)cy * bw + cx) * C + j * 4;
+                        float4 *buf = gbuf + k * BUF;
+#pragma unroll
+                        for (int pi = 0; pi < 9; ++pi) {
+                            const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+                            if ((valid >> pi) & 1u) {
+#pragma unroll
+                                for (int v = 0; v < NV; ++v) cp_async16(buf + (pi * NV + v) * GL, b_base + ((ptrdiff_t)dy * bw + dx) * C + v * ST);
+                            }
+                        }
+                    }
+                }
+            }
+            cp_async_wait_all();
+            // ---- consume the round in order
+            bool stop = false;
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                if (!stop && i < total) {
+                    int cx, cy;
+                    const bool is_rand = i >= n_prop_end;
+                    candidate(i, xbest, ybest, cx, cy);
+                    if (is_rand && cx == xbest && cy == ybest) {  // D3: d == dbest, never accepted
+                        n_ref += (j == 0);
+                        ++i;
+                    } else if (pos[k] != xy_to_int(cx, cy)) {
+                        stop = true;  // an acceptance moved the window: this candidate opens the next round
+                    } else {
+                        if (is_rand || i < n_first) n_ref += (j == 0);
+                        n_eval += (j == 0);
+                        const unsigned valid = amask & patch_mask(cx, cy, bw, bh);
+                        const float4 *buf = gbuf + k * BUF;
+                        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                        for (int pi = 0; pi < 9; ++pi) {
+                            const int dy = pi / 3 - 1, dx = pi % 3 - 1;
+                            if ((valid >> pi) & 1u) {
+                                float4 av[NV], bv[NV];
+#pragma unroll
+                                for (int v = 0; v < NV; ++v) {
+                                    if (T::A_IN_REGS) av[v] = areg[T::A_IN_REGS ? pi * NV + v : 0];
+                                    else av[v] = ldg4(a_base + ((ptrdiff_t)dy * aw + dx) * C + v * ST);
+                                    bv[v] = buf[(pi * NV + v) * GL];
+                                }
+                                u_accumulate<C, HALF>(acc0, acc1, pi, av, bv);
+                            }
+                        }
+                        const float d = u_finish<C, HALF>(acc0, acc1, mask, __popc(valid));
+                        const float dcmp = is_rand ? __fadd_rn(d, FLT_MIN) : d;
+                        if (i < n_first || dcmp < dbest) {
+                            dbest = d;
+                            xbest = cx;
+                            ybest = cy;
+                        }
+                        ++i;
+                    }
+                }
+            }
+        }
+        if (j == 0) {
+            const uint32_t vnew = xy_to_int(xbest, ybest);
+            D.nnf_out[p] = vnew;
+            D.lc_out[p] = vnew != v0 ? (int8_t)s.t : D.lc_in[p];
+            D.nnd[p] = dbest;
+        }
+    }
+    if (s.counters && (n_eval | n_ref)) {
+        atomicAdd(&s.counters[0], (unsigned long long)n_eval);
+        atomicAdd(&s.counters[1], (unsigned long long)n_ref);
+    }
+}
+
+template <int C, int NB>
+static void launch_ta(const PMStep &s, int tile, int blocks, cudaStream_t st)
+{
+    using T = UTraits<C, true>;
+    constexpr size_t smem = (size_t)(128 / T::LANES) * NB * 9 * T::NV * T::LANES * sizeof(float4);
+    static bool configured[64] = {false};   // per device (the attribute is per function and device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaFuncSetAttribute(pm_step_ta_kernel<C, true, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev] = true;
+    }
+    pm_step_ta_kernel<C, true, NB><<<blocks, 128, smem, st>>>(s, tile);
+}
+
 // queries per warp: 32 when that still leaves >= ~16 warps per SM, otherwise fewer (the coarse levels have few queries)
 static int pm_tile_size(int nq_total, int num_sms)
 {
     int tile = 32;
     while (tile > 2 && nq_total / tile < num_sms * 16) tile >>= 1;
     return tile;
+}
+
+// staging depth of pm_step_ta_kernel for channel count c from NCT_PM_ASYNC="n64,n128" (default: see PM_ASYNC_DEFAULT_*)
+#ifndef PM_ASYNC_DEFAULT_64
+#define PM_ASYNC_DEFAULT_64 0
+#endif
+#ifndef PM_ASYNC_DEFAULT_128
+#define PM_ASYNC_DEFAULT_128 0
+#endif
+static int pm_async_depth(int c)
+{
+    int n64 = PM_ASYNC_DEFAULT_64, n128 = PM_ASYNC_DEFAULT_128;
+    const char *e = getenv("NCT_PM_ASYNC");
+    if (e) {
+        n64 = atoi(e);
+        const char *comma = strchr(e, ',');
+        n128 = comma ? atoi(comma + 1) : n64 / 2;
+    }
+    return c == 64 ? n64 : n128;
 }
 
 template <int C>
@@ -1190,7 +1462,17 @@ struct StepLauncher<C, true> {
             const int tile = pm_tile_size(s.nq_total, 148);
             const int blocks = nct_div_up(nct_div_up(s.nq_total, tile), 4);
             static const bool spec = getenv("NCT_PM_SPEC") != nullptr;     // experimental: speculative next-candidate fetch (C = 64)
-            if (spec && C == 64) pm_step_t_kernel<64, true, false, true><<<blocks, 128, 0, st>>>(s, tile);
+            // cp.async-staged candidates: NCT_PM_ASYNC="<buffers at C = 64>,<buffers at C = 128>" (0 = the register kernel)
+            static const int nb64 = pm_async_depth(64), nb128 = pm_async_depth(128);
+            const int nb = C == 64 ? nb64 : nb128;
+            if (nb > 0 && C == 64) {
+                if (nb >= 6) launch_ta<64, 6>(s, tile, blocks, st);
+                else if (nb >= 4) launch_ta<64, 4>(s, tile, blocks, st);
+                else launch_ta<64, 3>(s, tile, blocks, st);
+            } else if (nb > 0 && C == 128) {
+                if (nb >= 3) launch_ta<128, 3>(s, tile, blocks, st);
+                else launch_ta<128, 2>(s, tile, blocks, st);
+            } else if (spec && C == 64) pm_step_t_kernel<64, true, false, true><<<blocks, 128, 0, st>>>(s, tile);
             else if (a_smem) pm_step_t_kernel<C, true, true><<<blocks, 128, 0, st>>>(s, tile);
             else pm_step_t_kernel<C, true><<<blocks, 128, 0, st>>>(s, tile);
         }

@@ -9,17 +9,6 @@
 #include <algorithm>
 #include <cstring>
 
-struct PipeState {
-    int dummy = 0;
-};
-
-void nct_pipe_free(nct_ctx *ctx)
-{
-    if (ctx && ctx->pipe) {
-        delete ctx->pipe;
-        ctx->pipe = nullptr;
-    }
-}
 
 extern "C" {
 
@@ -135,6 +124,8 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
     STEP(nct_l2norm(ctx, featC[0], normC, dc[0][0], dc[0][1], dc[0][2]));
     { NctStageTimer t(ctx, ST_KMEANS);
     STEP(nct_cluster_features(ctx, normC, dc[0][1], dc[0][2], dc[0][0], cfg.cluster_num, cfg.kmeans_iters, labels)); }
+    const bool vis = !ctx->vis_dir.empty();   // ENABLE_VIS artefacts (vis.cpp)
+    if (vis) STEP(nct_vis_cluster_small(ctx, labels, dc[0][1], dc[0][2]));
 
     const uint8_t *result = cnt_bgr_dev;
     for (int l = 0; l < L; ++l) {
@@ -155,6 +146,7 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
         // bidirectional PatchMatch (:283-284)
         const int params[11] = {C, ah, aw, bh, bw, cfg.patch_size, cfg.pm_iters, range[l], 0, 10, 1};
         { NctStageTimer t(ctx, ST_PM); STEP(nct_patchmatch_bidir(ctx, normC, normS, ann, annd, bnn, bnnd, params)); }
+        if (vis) STEP(nct_vis_flows(ctx, l, ann, bnn, cntImg[l], stlImg[l], ah, aw, bh, bw));
         // BDS colour reconstruction at level size (:291) and BDS feature error (:297-318)
         { NctStageTimer t(ctx, ST_BDS);
         STEP(nct_reconstruct_bds(ctx, cntImg[l], stlImg[l], ann, bnn, ah, aw, bh, bw, 1.0, (double)(float)cfg.bds_weight, smlRes));
@@ -164,9 +156,19 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
         STEP(nct_bgr2lab_u8(ctx, smlRes, stlLab, ah * aw));
         // non-local neighbours (:359); label cells are 2^l pixels wide
         { NctStageTimer t(ctx, ST_KNN); STEP(nct_find_knns(ctx, labels, dc[0][2], dc[0][1], cfg.cluster_num, cntLab, ah, aw, 1 << l, knn_id, knn_w)); }
+        if (vis) STEP(nct_vis_knn_clusters(ctx, l, labels, dc[0][1], dc[0][2], ah, aw, 1 << l));
         // transfer_color_downsample (CT/ColorTransfer.cpp:1180-1478)
         STEP(nct_local_fit(ctx, cntLab, stlLab, ah, aw, cfg.var_eps, a_lvl, b_lvl));
         STEP(nct_confidence_weights(ctx, err, ah * aw, weight));
+        if (vis) {
+            // the local fit, looked up at (y / samples, x / samples) with samples = 2^(4 - level) (NCT/main.cu:365)
+            std::vector<double> au, bu;
+            STEP(nct_vis_error_map(ctx, l, err, ah, aw));
+            STEP(nct_vis_coefficients(ctx, l, "_init", a_lvl, b_lvl, ah, aw, ch, cw, 1 << (L - 1 - l), &au, &bu));
+            NCT_CUDA(ctx, cudaMemcpyAsync(a_full, au.data(), sizeof(double) * nC * 3, cudaMemcpyHostToDevice, ctx->stream));
+            NCT_CUDA(ctx, cudaMemcpyAsync(b_full, bu.data(), sizeof(double) * nC * 3, cudaMemcpyHostToDevice, ctx->stream));
+            STEP(nct_vis_refine(ctx, l, "refine_init", cntLabFull, a_full, b_full, ch, cw));   // (waits for the copies: au / bu stay valid)
+        }
         const double normFactor = (double)(cw * ch) / (double)(aw * ah);
         double lam = cfg.wls_lambda_init * normFactor;
         { NctStageTimer t(ctx, ST_CG);
@@ -174,6 +176,10 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
                                 cfg.nonlocal_weight, cfg.k_num, normFactor, nullptr)); }
         STEP(nct_upsample_coefficients(ctx, a_lvl, b_lvl, ah, aw, cntLabFull, ch, cw, a_full, b_full, rough));
         if (ah == ch && aw == cw) lam = lam * 4;
+        if (vis) {
+            STEP(nct_vis_coefficients(ctx, l, "_nonlocal", a_full, b_full, ch, cw, ch, cw, 0, nullptr, nullptr));
+            STEP(nct_vis_refine(ctx, l, "refine_nonlocal", cntLabFull, a_full, b_full, ch, cw));
+        }
         { NctStageTimer t(ctx, ST_WLS);
         static const bool warm = !(getenv("NCT_WLS_WARM") && atoi(getenv("NCT_WLS_WARM")) == 0);  // default on
         ctx->wls_warm = warm ? 1 : 0;
@@ -181,6 +187,7 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
         rc = nct_solve_wls(ctx, a_full, b_full, rough, cntLabFull, ch, cw, lam, cfg.wls_alpha, cfg.wls_rel_tol, 0, nullptr, nullptr);
         ctx->wls_warm = 0;
         if (rc) return rc; }
+        if (vis) STEP(nct_vis_coefficients(ctx, l, "", a_full, b_full, ch, cw, ch, cw, 0, nullptr, nullptr));
         STEP(nct_apply_coefficients(ctx, cntLabFull, a_full, b_full, ch, cw, refine, nullptr));
         result = refine;
         if (l >= cfg.stop_after_level) break;

@@ -207,13 +207,60 @@ def test_cli_drop_in_pairs_txt_end_to_end(pkg, pctx, weights, tmp_path):
     (inp / "pairs.txt").write_text("in/in0.png in/tar0.png 2.0\nin/in1.png in/tar1.png 0.5\nin/missing.png in/tar1.png 2.0\n")
     out = tmp_path / "res"
     r = subprocess.run([cli, "-m", str(tmp_path / "model"), "-i", str(inp), "-o", str(out), "-g", "0", "-engine", "0"], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
+    # the unreadable third pair is reported and skipped like in the reference, but the exit code says so (2)
+    assert r.returncode == 2 and "1 pair(s) failed" in r.stderr, r.stderr
     assert "Fail reading content image" in r.stdout and r.stdout.count("Final output file") == 2
     pctx.set_vgg_engine(0)
     for i, bds in enumerate([2.0, 0.5]):
         got = pkg.png_read(str(out / f"in{i}_tar{i}_{bds:2.2f}.png"))
         ref = pctx.transfer_pair(pairs[i][0], pairs[i][1], pctx.default_config(bds_weight=bds))
         assert np.array_equal(got, ref)
+    # -resume 1: results that exist are kept, nothing is recomputed
+    stamp = [os.path.getmtime(out / f"in{i}_tar{i}_{bds:2.2f}.png") for i, bds in enumerate([2.0, 0.5])]
+    r = subprocess.run([cli, "-m", str(tmp_path / "model"), "-i", str(inp), "-o", str(out), "-g", "0", "-engine", "0", "-resume", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and r.stdout.count("skipped (resume)") == 2 and r.stdout.count("Final output file") == 0
+    assert stamp == [os.path.getmtime(out / f"in{i}_tar{i}_{bds:2.2f}.png") for i, bds in enumerate([2.0, 0.5])]
+
+
+def test_cli_vis_writes_the_enable_vis_artefacts(pkg, pctx, weights, tmp_path):
+    """-vis 1 = the reference's ENABLE_VIS build (NCT/main.cu:333-422): per-level flow maps, level images, cluster maps,
+    error heat maps and a / b visualisations next to the result, with the reference's file names; the result itself is
+    unchanged by the instrumentation."""
+    import subprocess, os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "neural-color-transfer_b200", "neural_color_transfer")
+    model = tmp_path / "model" / "vgg19"
+    model.mkdir(parents=True)
+    pkg.write_caffemodel(str(model / "VGG_ILSVRC_19_layers.caffemodel"), weights, v1=True)
+    inp = tmp_path / "example"
+    inp.mkdir()
+    c, s = synth.pair(41, 96, 80, 88, 104)
+    pkg.png_write(str(inp / "c.png"), c)
+    pkg.png_write(str(inp / "s.png"), s)
+    (inp / "pairs.txt").write_text("c.png s.png 2.0\n")
+    out = tmp_path / "res"
+    r = subprocess.run([cli, "-m", str(tmp_path / "model"), "-i", str(inp), "-o", str(out), "-g", "0", "-vis", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    pctx.set_vgg_engine(3)
+    assert np.array_equal(pkg.png_read(str(out / "c_s_2.00.png")), pctx.transfer_pair(c, s, pctx.default_config(bds_weight=2.0)))
+    pre = "c_s_2.00"
+    dims_c, dims_s = pctx.level_dims(96, 80), pctx.level_dims(88, 104)
+    assert pkg.png_read(str(out / f"{pre}_cluster_small.png")).shape == (dims_c[0][1], dims_c[0][2], 3)
+    for l in range(5):
+        ah, aw, bh, bw = dims_c[l][1], dims_c[l][2], dims_s[l][1], dims_s[l][2]
+        fa, fb = pkg.png_read(str(out / f"{pre}_aFlow_{l}.png")), pkg.png_read(str(out / f"{pre}_bFlow_{l}.png"))
+        assert fa.shape == (ah, aw, 3) and fb.shape == (bh, bw, 3) and not fa[..., 1].any()   # reconstruct_flow: G = 0
+        assert fa[..., 0].max() <= 255 * (bw - 1) // bw + 1 and fa[..., 2].max() > 0
+        assert pkg.png_read(str(out / f"{pre}_tCnt_{l}.png")).shape == (ah, aw, 3)
+        assert pkg.png_read(str(out / f"{pre}_tStl_{l}.png")).shape == (bh, bw, 3)
+        for name in ("knn", "errMap"):
+            assert pkg.png_read(str(out / f"{pre}_{name}_{l}.png")).shape == (ah, aw, 3)
+        for name in ("refine_init", "refine_nonlocal", "aVis", "aVis_init", "aVis_nonlocal", "bVis", "bVis_init", "bVis_nonlocal"):
+            assert pkg.png_read(str(out / f"{pre}_{name}_{l}.png")).shape == (96, 80, 3)
+    # the finest level's tCnt is the content image itself
+    assert np.array_equal(pkg.png_read(str(out / f"{pre}_tCnt_4.png")), c)
 
 
 def test_cli_pairs_in_flight_gives_the_same_files(pkg, pctx, weights, tmp_path):

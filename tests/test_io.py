@@ -37,6 +37,38 @@ def test_png_alpha_grey_and_16bit_match_imread(pkg, tmp_path):
         assert np.array_equal(pkg.png_read(p), cv2.imread(p))  # imread drops alpha / replicates grey (NCT/main.cu:483)
 
 
+def _png_bytes(width, height, depth, ctype, rows):
+    import struct
+    import zlib
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+    raw = b"".join(b"\x00" + bytes(r) for r in rows)
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", width, height, depth, ctype, 0, 0, 0)) +
+            chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+
+
+@pytest.mark.parametrize("depth", [1, 2, 4])
+def test_png_low_bit_depth_greyscale(pkg, tmp_path, depth):
+    """colour type 0 at 1 / 2 / 4 bits per sample (valid PNGs that imread accepts): samples scaled to 8 bits"""
+    import cv2
+
+    rng = np.random.default_rng(depth)
+    W, H = 13, 7
+    vals = rng.integers(0, 1 << depth, (H, W))
+    rows = []
+    for y in range(H):
+        bits = "".join(format(int(v), f"0{depth}b") for v in vals[y])
+        bits += "0" * (-len(bits) % 8)
+        rows.append([int(bits[i:i + 8], 2) for i in range(0, len(bits), 8)])
+    p = str(tmp_path / f"g{depth}.png")
+    open(p, "wb").write(_png_bytes(W, H, depth, 0, rows))
+    want = (vals * 255 // ((1 << depth) - 1)).astype(np.uint8)
+    got = pkg.png_read(p)
+    assert np.array_equal(got, np.repeat(want[..., None], 3, axis=2))
+    assert np.array_equal(got, cv2.imread(p))
+
+
 def test_png_reads_the_reference_demo_inputs(pkg):
     import cv2
 

@@ -8,6 +8,7 @@ side = int(sys.argv[1]) if len(sys.argv) > 1 else 700
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 pkg = g.load_package(); dev = torch.device("cuda:0"); ctx = pkg.Context(0)
 ctx.load_vgg19_weights(synth.vgg19_weights(19))
+ctx.set_vgg_engine(int(os.environ.get("NCT_ENGINE", "3")))
 c, s = synth.pair(0, side, side)
 tc, ts = torch.from_numpy(c).to(dev), torch.from_numpy(s).to(dev)
 for i in range(n):
