@@ -388,243 +388,11 @@ __global__ void __launch_bounds__(PM_TPB, (C <= 128) ? PM_MINB_SMALL : 1) pm_ste
     }
 }
 
-// ------------------------------------------------------------------ half-warp-per-query step kernel (C = 64, 128)
-// The finest levels are instruction-issue bound (profiles/r1_pm_tuning.md): of ~200 issued instructions per candidate
-// only 20 are FMAs.  Here a warp serves TWO queries: 16 lanes x float4 cover one 64-channel pixel row, so each lane
-// walks all nine patch pixels of its query (C = 128: two vectors per pixel) and every address / validity / dedup
-// instruction is shared by two queries.  The canonical reduction order (oracle D2) is preserved exactly: the two
-// 16-slot groups of the 32-slot order live in two accumulators per lane -- C = 64: patch pixels of even / odd index,
-// C = 128: vector j / vector j + 16 -- their sum is the butterfly's xor-16 step, the xor 8, 4, 2, 1 steps stay inside
-// the half warp.
-template <int C>
-struct HWTraits {
-    static constexpr int NV = C / 64;          // float4 vectors per lane per pixel (1 or 2)
-    static constexpr bool A_IN_REGS = (C == 64);
-};
-
-template <int C>
-struct HWQuery {
-    float4 a[HWTraits<C>::A_IN_REGS ? 9 : 1];
-    const float *a_base;
-    int aw;
-    unsigned amask;
-};
-
-template <int C>
-__device__ __forceinline__ float hw_eval(const HWQuery<C> &q, const float *__restrict__ b, int bx, int by, int bw, int bh, int j,
-                                         unsigned hmask)
-{
-    constexpr int NV = HWTraits<C>::NV;
-    const unsigned valid = q.amask & patch_mask(bx, by, bw, bh);
-    const float *b_base = b + ((size_t)by * bw + bx) * C + j * 4;
-    if (valid == 0x1FFu) {
-        // interior fast path (the common case): no per-pixel predicates, three row pointers and immediate offsets;
-        // exactly the same FMA sequence as the general path below
-        const float *rb[3] = {b_base - (ptrdiff_t)bw * C, b_base, b_base + (ptrdiff_t)bw * C};
-        float4 bv[9 * NV];
-#pragma unroll
-        for (int pi = 0; pi < 9; ++pi)
-#pragma unroll
-            for (int k = 0; k < NV; ++k) bv[pi * NV + k] = ldg4(rb[pi / 3] + (pi % 3 - 1) * C + k * 64);
-        float acc0 = 0.f, acc1 = 0.f;
-        if (NV == 1) {
-            if (HWTraits<C>::A_IN_REGS) {
-#pragma unroll
-                for (int pi = 0; pi < 9; ++pi) {
-                    if (pi & 1) acc1 = fma4(q.a[pi], bv[pi], acc1);
-                    else acc0 = fma4(q.a[pi], bv[pi], acc0);
-                }
-            } else {
-                const float *ra[3] = {q.a_base - (ptrdiff_t)q.aw * C, q.a_base, q.a_base + (ptrdiff_t)q.aw * C};
-#pragma unroll
-                for (int pi = 0; pi < 9; ++pi) {
-                    const float4 av = ldg4(ra[pi / 3] + (pi % 3 - 1) * C);
-                    if (pi & 1) acc1 = fma4(av, bv[pi], acc1);
-                    else acc0 = fma4(av, bv[pi], acc0);
-                }
-            }
-        } else {
-            const float *ra[3] = {q.a_base - (ptrdiff_t)q.aw * C, q.a_base, q.a_base + (ptrdiff_t)q.aw * C};
-#pragma unroll
-            for (int pi = 0; pi < 9; ++pi) {
-                const float4 a0 = ldg4(ra[pi / 3] + (pi % 3 - 1) * C);
-                const float4 a1 = ldg4(ra[pi / 3] + (pi % 3 - 1) * C + 64);
-                acc0 = fma4(a0, bv[pi * NV], acc0);
-                acc1 = fma4(a1, bv[pi * NV + 1], acc1);
-            }
-        }
-        float acc = __fadd_rn(acc0, acc1);
-        acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 8));
-        acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 4));
-        acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 2));
-        acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 1));
-        return __fdiv_rn(-acc, 9.0f);
-    }
-    float4 bv[9 * NV];
-#pragma unroll
-    for (int pi = 0; pi < 9; ++pi) {
-        const int dy = pi / 3 - 1, dx = pi % 3 - 1;
-        const bool ok = (valid >> pi) & 1u;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) v = ldg4(b_base + ((ptrdiff_t)dy * bw + dx) * C + k * 64);
-            bv[pi * NV + k] = v;
-        }
-    }
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-    for (int pi = 0; pi < 9; ++pi) {
-        const int dy = pi / 3 - 1, dx = pi % 3 - 1;
-        if ((valid >> pi) & 1u) {
-            if (NV == 1) {
-                float4 av;
-                if (HWTraits<C>::A_IN_REGS) av = q.a[pi];
-                else av = ldg4(q.a_base + ((ptrdiff_t)dy * q.aw + dx) * C);
-                if (pi & 1) acc1 = fma4(av, bv[pi], acc1);
-                else acc0 = fma4(av, bv[pi], acc0);
-            } else {
-                const float4 a0 = ldg4(q.a_base + ((ptrdiff_t)dy * q.aw + dx) * C);
-                const float4 a1 = ldg4(q.a_base + ((ptrdiff_t)dy * q.aw + dx) * C + 64);
-                acc0 = fma4(a0, bv[pi * NV], acc0);
-                acc1 = fma4(a1, bv[pi * NV + 1], acc1);
-            }
-        }
-    }
-    float acc = __fadd_rn(acc0, acc1);  // == the xor-16 step of the 32-slot butterfly
-    acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 8));
-    acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 4));
-    acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 2));
-    acc = __fadd_rn(acc, __shfl_xor_sync(hmask, acc, 1));
-    return __fdiv_rn(-acc, (float)__popc(valid));
-}
-
-template <int C>
-__global__ void __launch_bounds__(128, 4) pm_step_hw_kernel(const PMStep s)
-{
-    const int lane = threadIdx.x & 31, half = lane >> 4, j = lane & 15;
-    const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
-    const int qidx = (int)(((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5) * 2 + half);
-    if (qidx >= s.nq_total) return;  // whole half warps leave together; the shuffles below only name the own half
-    const int dsel = qidx >= s.nq0 ? 1 : 0;
-    const PMDir &D = s.d[dsel];
-    const int p = qidx - (dsel ? s.nq0 : 0);
-    const int aw = D.aw, ah = D.ah, bw = D.bw, bh = D.bh;
-    const int ax = p % aw, ay = p / aw;
-
-    const uint32_t v0 = D.nnf_in[p];
-    int xbest = int_to_x(v0), ybest = int_to_y(v0);
-    float dbest;
-    unsigned n_eval = 0, n_ref = 0;
-
-    const int jump = s.jump;
-    uint32_t cand[4];
-    bool use[4];
-    {
-        const int qx[4] = {ax - jump, ax + jump, ax, ax};
-        const int qy[4] = {ay, ay, ay - jump, ay + jump};
-        const int sx[4] = {jump, -jump, 0, 0};
-        const int sy[4] = {0, 0, jump, -jump};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            use[k] = false;
-            cand[k] = 0;
-            if (qx[k] >= 0 && qx[k] < aw && qy[k] >= 0 && qy[k] < ah) {
-                const uint32_t vp = D.nnf_in[qy[k] * aw + qx[k]];
-                const int xp = int_to_x(vp) + sx[k], yp = int_to_y(vp) + sy[k];
-                if (yp >= 0 && yp < bh && xp >= 0 && xp < bw) {
-                    n_ref++;
-                    cand[k] = xy_to_int(xp, yp);
-                    bool dup = (cand[k] == v0);
-#pragma unroll
-                    for (int t = 0; t < k; ++t) dup = dup || (use[t] && cand[t] == cand[k]);
-                    // D4 (unchanged-source skip, oracle/pm_oracle.c): the neighbour's entry has not changed since this
-                    // slot last judged it, so the candidate would be rejected again
-                    const bool stale = s.t >= 4 && (int)D.lc_in[qy[k] * aw + qx[k]] <= s.t - 5;
-                    use[k] = !dup && !stale;
-                }
-            }
-        }
-    }
-    // with D4 most queries of a converged region have nothing to evaluate in the jump 8/4/2 steps: the query patch is
-    // only fetched when something will be compared against it
-    HWQuery<C> q;
-    q.aw = aw;
-    q.amask = patch_mask(ax, ay, aw, ah);
-    q.a_base = D.a + ((size_t)ay * aw + ax) * C + j * 4;
-    if (HWTraits<C>::A_IN_REGS && (s.first || s.do_random || use[0] || use[1] || use[2] || use[3])) {
-#pragma unroll
-        for (int pi = 0; pi < 9; ++pi) {
-            const int dy = pi / 3 - 1, dx = pi % 3 - 1;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if ((q.amask >> pi) & 1u) v = ldg4(q.a_base + ((ptrdiff_t)dy * aw + dx) * C);
-            q.a[pi] = v;
-        }
-    }
-    if (s.first) {
-        dbest = hw_eval<C>(q, D.b, xbest, ybest, bw, bh, j, hmask);
-        n_eval++;
-        n_ref++;
-    } else {
-        dbest = D.nnd[p];
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (use[k]) {  // uniform inside a half warp
-            const float d = hw_eval<C>(q, D.b, int_to_x(cand[k]), int_to_y(cand[k]), bw, bh, j, hmask);
-            n_eval++;
-            if (d < dbest) {
-                dbest = d;
-                xbest = int_to_x(cand[k]);
-                ybest = int_to_y(cand[k]);
-            }
-        }
-    }
-    if (s.do_random) {
-        const float *u = D.rng + (size_t)ax * D.ndraws + (size_t)s.iter * 2 * D.n_mag;
-        int m = 0;
-        for (int mag = D.rs_start; mag >= 1; mag /= 2, ++m) {
-            const int xmin = max(xbest - mag, 0), xmax = min(xbest + mag + 1, bw);
-            const int ymin = max(ybest - mag, 0), ymax = min(ybest + mag + 1, bh);
-            const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
-            // (int)(u * w) % w with u in (0, 1]: the product is in [0, w], so the modulo only maps w to 0
-            const int wx = xmax - xmin, wy = ymax - ymin;
-            const int tx = (int)(__fmul_rn(u1, (float)wx)), ty = (int)(__fmul_rn(u2, (float)wy));
-            const int xp = xmin + (tx >= wx ? tx - wx : tx);
-            const int yp = ymin + (ty >= wy ? ty - wy : ty);
-            n_ref++;
-            if (xp == xbest && yp == ybest) continue;
-            n_eval++;
-            const float d = hw_eval<C>(q, D.b, xp, yp, bw, bh, j, hmask);
-            if (__fadd_rn(d, FLT_MIN) < dbest) {
-                dbest = d;
-                xbest = xp;
-                ybest = yp;
-            }
-        }
-    }
-    if (j == 0) {
-        const uint32_t vnew = xy_to_int(xbest, ybest);
-        D.nnf_out[p] = vnew;
-        D.lc_out[p] = vnew != v0 ? (int8_t)s.t : D.lc_in[p];
-        D.nnd[p] = dbest;
-        if (s.counters) {
-            atomicAdd(&s.counters[0], (unsigned long long)n_eval);
-            atomicAdd(&s.counters[1], (unsigned long long)n_ref);
-        }
-    }
-}
-
-// ------------------------------------------------------------------ unified-loop step kernel (C = 64 ... 512)
+// ------------------------------------------------------------------ group-per-query distance (C = 64 ... 512)
 // One candidate loop per query: [initial entry (first step only)] + compacted propagation candidates + random-search
-// candidates, all through ONE inlined copy of the distance code.  Compared with the unrolled kernels above:
-//   * after D4 most queries have 0-2 propagation candidates per step, in different slots; unrolled code evaluates
-//     slot k of one half warp and slot k' of the other at different program counters (serialised), the compacted
-//     loop evaluates them together;
-//   * the kernel is ~4x smaller (one distance body instead of six);
-//   * interior patches (all nine pixels valid on both sides -- almost all of them) take a predicate-free path with
-//     three row pointers and immediate offsets.
-// The FMA / reduction sequence per distance is unchanged, so the result is bit-identical (oracle D2).
+// candidates, all through ONE inlined copy of the distance code; interior patches (all nine pixels valid on both sides
+// -- almost all of them) take a predicate-free path with three row pointers and immediate offsets.  The FMA / reduction
+// sequence per distance is the canonical one (oracle D2), whatever the lane mapping.
 // HALF = true : 16 lanes per query (C = 64: 1 float4 per lane and pixel, C = 128: 2)
 // HALF = false: 32 lanes per query (C = 256: 2 float4 per lane and pixel, C = 512: 4)
 template <int C, bool HALF>
@@ -635,13 +403,10 @@ struct UTraits {
     static constexpr bool A_IN_REGS = (C == 64) || (C == 256);
 };
 
-// AS = true: the query patch lives in shared memory (a_s[vector][lane of the group]) instead of registers / L1:
-// 36 fewer registers per thread at C = 64, i.e. more resident warps for a latency-bound kernel
-template <int C, bool HALF, bool AS = false>
+template <int C, bool HALF>
 struct UQuery {
     using T = UTraits<C, HALF>;
-    float4 a[(T::A_IN_REGS && !AS) ? 9 * T::NV : 1];
-    const float4 *a_s;
+    float4 a[T::A_IN_REGS ? 9 * T::NV : 1];
     const float *a_base;
     int aw;
     unsigned amask;
@@ -683,11 +448,10 @@ __device__ __forceinline__ float u_finish(float acc0, float acc1, unsigned mask,
     return __fdiv_rn(-acc, (float)n);
 }
 
-template <int C, bool HALF, bool AS = false>
-__device__ __forceinline__ float u_eval(const UQuery<C, HALF, AS> &q, const float *__restrict__ b, int bx, int by, int bw, int bh, int j,
+template <int C, bool HALF>
+__device__ __forceinline__ float u_eval(const UQuery<C, HALF> &q, const float *__restrict__ b, int bx, int by, int bw, int bh, int j,
                                         unsigned mask)
 {
-    constexpr int GL = UTraits<C, HALF>::LANES;
     using T = UTraits<C, HALF>;
     constexpr int NV = T::NV, ST = T::STRIDE;
     const unsigned valid = q.amask & patch_mask(bx, by, bw, bh);
@@ -706,8 +470,7 @@ __device__ __forceinline__ float u_eval(const UQuery<C, HALF, AS> &q, const floa
             float4 av[NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
-                if (AS) av[k] = q.a_s[(pi * NV + k) * GL];
-                else if (T::A_IN_REGS) av[k] = q.a[pi * NV + k];
+                if (T::A_IN_REGS) av[k] = q.a[pi * NV + k];
                 else av[k] = ldg4(ra[pi / 3] + (pi % 3 - 1) * C + k * ST);
             }
             u_accumulate<C, HALF>(acc0, acc1, pi, av, &bv[pi * NV]);
@@ -733,8 +496,7 @@ __device__ __forceinline__ float u_eval(const UQuery<C, HALF, AS> &q, const floa
             float4 av[NV];
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
-                if (AS) av[k] = q.a_s[(pi * NV + k) * GL];
-                else if (T::A_IN_REGS) av[k] = q.a[pi * NV + k];
+                if (T::A_IN_REGS) av[k] = q.a[pi * NV + k];
                 else av[k] = ldg4(q.a_base + ((ptrdiff_t)dy * q.aw + dx) * C + k * ST);
             }
             u_accumulate<C, HALF>(acc0, acc1, pi, av, &bv[pi * NV]);
@@ -743,130 +505,8 @@ __device__ __forceinline__ float u_eval(const UQuery<C, HALF, AS> &q, const floa
     return u_finish<C, HALF>(acc0, acc1, mask, __popc(valid));
 }
 
-template <int C, bool HALF>
-__global__ void __launch_bounds__(128, HALF ? 4 : 2) pm_step_u_kernel(const PMStep s)
-{
-    using T = UTraits<C, HALF>;
-    const int lane = threadIdx.x & 31;
-    const int j = HALF ? (lane & 15) : lane;
-    const unsigned mask = HALF ? ((lane >> 4) ? 0xffff0000u : 0x0000ffffu) : 0xffffffffu;
-    const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    const int qidx = HALF ? warp_global * 2 + (lane >> 4) : warp_global;
-    if (qidx >= s.nq_total) return;  // whole (half) warps leave together; the shuffles only name the own group
-    const int dsel = qidx >= s.nq0 ? 1 : 0;
-    const PMDir &D = s.d[dsel];
-    const int p = qidx - (dsel ? s.nq0 : 0);
-    const int aw = D.aw, ah = D.ah, bw = D.bw, bh = D.bh;
-    const int ax = p % aw, ay = p / aw;
-
-    const uint32_t v0 = D.nnf_in[p];
-    int xbest = int_to_x(v0), ybest = int_to_y(v0);
-    unsigned n_eval = 0, n_ref = 0;
-
-    // ---- propagation candidates L, R, U, D from the previous step's field: de-duplicated (D3), unchanged sources
-    //      skipped (D4), compacted into c[0 .. n)
-    const int jump = s.jump;
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    int n = 0;
-    {
-        const int qx[4] = {ax - jump, ax + jump, ax, ax};
-        const int qy[4] = {ay, ay, ay - jump, ay + jump};
-        const int sx[4] = {jump, -jump, 0, 0};
-        const int sy[4] = {0, 0, jump, -jump};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (qx[k] >= 0 && qx[k] < aw && qy[k] >= 0 && qy[k] < ah) {
-                const int qi = qy[k] * aw + qx[k];
-                const uint32_t vp = D.nnf_in[qi];
-                const int xp = int_to_x(vp) + sx[k], yp = int_to_y(vp) + sy[k];
-                if (yp >= 0 && yp < bh && xp >= 0 && xp < bw) {
-                    n_ref++;
-                    const uint32_t cv = xy_to_int(xp, yp);
-                    bool dup = (cv == v0) || (n > 0 && cv == c0) || (n > 1 && cv == c1) || (n > 2 && cv == c2);
-                    const bool stale = s.t >= 4 && (int)D.lc_in[qi] <= s.t - 5;
-                    if (!dup && !stale) {
-                        if (n == 0) c0 = cv;
-                        else if (n == 1) c1 = cv;
-                        else if (n == 2) c2 = cv;
-                        else c3 = cv;
-                        n++;
-                    }
-                }
-            }
-        }
-    }
-    const int n_first = s.first ? 1 : 0;
-    const int n_prop_end = n_first + n;
-    const int total = n_prop_end + (s.do_random ? D.n_mag : 0);
-
-    UQuery<C, HALF> q;
-    q.aw = aw;
-    q.amask = patch_mask(ax, ay, aw, ah);
-    q.a_base = D.a + ((size_t)ay * aw + ax) * C + j * 4;
-    if (T::A_IN_REGS && total > 0) {  // the query patch is only fetched when something will be compared against it
-#pragma unroll
-        for (int pi = 0; pi < 9; ++pi) {
-            const int dy = pi / 3 - 1, dx = pi % 3 - 1;
-#pragma unroll
-            for (int k = 0; k < T::NV; ++k) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((q.amask >> pi) & 1u) v = ldg4(q.a_base + ((ptrdiff_t)dy * aw + dx) * C + k * T::STRIDE);
-                q.a[pi * T::NV + k] = v;
-            }
-        }
-    }
-    float dbest = s.first ? 0.f : D.nnd[p];
-    const float *u = D.rng + (size_t)ax * D.ndraws + (size_t)s.iter * 2 * D.n_mag;
-
-#pragma unroll 1
-    for (int i = 0; i < total; ++i) {
-        int cx, cy;
-        const bool is_rand = i >= n_prop_end;
-        if (!is_rand) {
-            const int k = i - n_first;
-            const uint32_t cv = (i < n_first) ? v0 : (k == 0 ? c0 : (k == 1 ? c1 : (k == 2 ? c2 : c3)));
-            cx = int_to_x(cv);
-            cy = int_to_y(cv);
-            if (i < n_first) n_ref++;
-        } else {
-            // random search around the current best (NCT/GeneralizedPatchMatch.cu:806-821); mag = rs_start / 2^m
-            const int m = i - n_prop_end;
-            const int mag = D.rs_start >> m;
-            const int xmin = max(xbest - mag, 0), xmax = min(xbest + mag + 1, bw);
-            const int ymin = max(ybest - mag, 0), ymax = min(ybest + mag + 1, bh);
-            const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
-            // (int)(u * w) % w with u in (0, 1]: the product is in [0, w], so the modulo only maps w to 0
-            const int wx = xmax - xmin, wy = ymax - ymin;
-            const int tx = (int)(__fmul_rn(u1, (float)wx)), ty = (int)(__fmul_rn(u2, (float)wy));
-            cx = xmin + (tx >= wx ? tx - wx : tx);
-            cy = ymin + (ty >= wy ? ty - wy : ty);
-            n_ref++;
-            if (cx == xbest && cy == ybest) continue;  // D3: d == dbest, never accepted
-        }
-        n_eval++;
-        const float d = u_eval<C, HALF>(q, D.b, cx, cy, bw, bh, j, mask);
-        const float dcmp = is_rand ? __fadd_rn(d, FLT_MIN) : d;
-        if (i < n_first || dcmp < dbest) {
-            dbest = d;
-            xbest = cx;
-            ybest = cy;
-        }
-    }
-
-    if (j == 0) {
-        const uint32_t vnew = xy_to_int(xbest, ybest);
-        D.nnf_out[p] = vnew;
-        D.lc_out[p] = vnew != v0 ? (int8_t)s.t : D.lc_in[p];
-        D.nnd[p] = dbest;
-        if (s.counters) {
-            atomicAdd(&s.counters[0], (unsigned long long)n_eval);
-            atomicAdd(&s.counters[1], (unsigned long long)n_ref);
-        }
-    }
-}
-
 // ------------------------------------------------------------------ tiled step kernel (C = 64 ... 512)
-// After D4 the late steps are sparse (about one candidate per query), and pm_step_u_kernel becomes bound by the
+// After D4 the late steps are sparse (about one candidate per query), and a kernel with one (half) warp per query is bound by the
 // LIFETIME of its short warps: field entry -> four neighbour entries -> patch rows is a chain of dependent global
 // loads (~2.5 us) paid by every (half) warp for one query (profiles/r1_pm_step_ncu.md).  Here a warp owns a TILE of
 // up to 32 consecutive queries:
@@ -874,7 +514,8 @@ __global__ void __launch_bounds__(128, HALF ? 4 : 2) pm_step_u_kernel(const PMSt
 //            once, queries with nothing to evaluate are finished right there (coalesced stores);
 //   phase 2, 16 (or 32) lanes = one query: the queries that do have work are walked one after the other by the two
 //            half warps (even / odd ranked work items), so the dependent-load chain is paid once per tile.
-// The per-query arithmetic is pm_step_u_kernel's, bit for bit.
+// Variants that keep more candidate rows of a query in flight (register prefetch, cp.async staging in shared memory, query
+// patch in shared memory for more resident warps) were measured in rounds 1-2 and lost: profiles/r2_pm_tuning.md.
 struct TQueryState {
     uint32_t v0, c0, c1, c2, c3;
     int qidx;
@@ -882,18 +523,11 @@ struct TQueryState {
     float dbest;
 };
 
-// SPEC = true (experimental, NCT_PM_SPEC=1, C = 64 only; not yet measured): while candidate i is being reduced, the rows
-// of candidate i + 1 are already in flight -- the next propagation candidate is known, the next random-search candidate
-// is computed from the CURRENT best, i.e. assuming candidate i is rejected (the common case).  The position is
-// recomputed after the acceptance test as usual and the prefetched rows are only used if it still matches, so the
-// result is unchanged; a wrong guess costs one wasted set of loads.
-template <int C, bool HALF, bool AS = false, bool SPEC = false>
-__global__ void __launch_bounds__(128, SPEC ? 3 : (HALF ? (AS ? (C == 64 ? 6 : 5) : 4) : 2)) pm_step_t_kernel(const PMStep s, const int tile)
+template <int C, bool HALF>
+__global__ void __launch_bounds__(128, HALF ? 4 : 2) pm_step_t_kernel(const PMStep s, const int tile)
 {
-    static_assert(!SPEC || (HALF && C == 64 && !AS), "the speculative variant exists for C = 64 only");
     using T = UTraits<C, HALF>;
     __shared__ TQueryState st_all[4][32];
-    __shared__ float4 a_sm[AS ? 128 * 9 * T::NV : 1];  // [group of the block][vector][lane of the group]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     TQueryState *st = st_all[wib];
     const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -980,27 +614,11 @@ __global__ void __launch_bounds__(128, SPEC ? 3 : (HALF ? (AS ? (C == 64 ? 6 : 5
         const int n_prop_end = n_first + q0.n;
         const int total = n_prop_end + (s.do_random ? D.n_mag : 0);
 
-        UQuery<C, HALF, AS> q;
+        UQuery<C, HALF> q;
         q.aw = aw;
         q.amask = patch_mask(ax, ay, aw, ah);
         q.a_base = D.a + ((size_t)ay * aw + ax) * C + j * 4;
-        q.a_s = nullptr;
-        if (AS) {
-            // this group's slice: groups are (warp, half); each vector slot holds LANES consecutive float4
-            float4 *slot = a_sm + (size_t)((wib * (HALF ? 2 : 1) + grp) * 9 * T::NV) * T::LANES + j;
-            __syncwarp(mask);  // the previous query's readers are done
-#pragma unroll
-            for (int pi = 0; pi < 9; ++pi) {
-                const int dy = pi / 3 - 1, dx = pi % 3 - 1;
-#pragma unroll
-                for (int k = 0; k < T::NV; ++k) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if ((q.amask >> pi) & 1u) v = ldg4(q.a_base + ((ptrdiff_t)dy * aw + dx) * C + k * T::STRIDE);
-                    slot[(pi * T::NV + k) * T::LANES] = v;
-                }
-            }
-            q.a_s = slot;  // every lane reads back only what it wrote itself: no barrier needed
-        } else if (T::A_IN_REGS) {
+        if (T::A_IN_REGS) {
 #pragma unroll
             for (int pi = 0; pi < 9; ++pi) {
                 const int dy = pi / 3 - 1, dx = pi % 3 - 1;
@@ -1013,356 +631,36 @@ __global__ void __launch_bounds__(128, SPEC ? 3 : (HALF ? (AS ? (C == 64 ? 6 : 5
             }
         }
         const float *u = D.rng + (size_t)ax * D.ndraws + (size_t)s.iter * 2 * D.n_mag;
-        if (SPEC) {
-            // candidate i of this query: propagation list entry, or the random-search draw around (xb, yb)
-            auto candidate = [&](int i, int xb, int yb, int &cx, int &cy) {
-                if (i < n_prop_end) {
-                    const int k = i - n_first;
-                    const uint32_t cv = (i < n_first) ? v0 : (k == 0 ? q0.c0 : (k == 1 ? q0.c1 : (k == 2 ? q0.c2 : q0.c3)));
-                    cx = int_to_x(cv);
-                    cy = int_to_y(cv);
-                } else {
-                    const int m = i - n_prop_end;
-                    const int mag = D.rs_start >> m;
-                    const int xmin = max(xb - mag, 0), xmax = min(xb + mag + 1, bw);
-                    const int ymin = max(yb - mag, 0), ymax = min(yb + mag + 1, bh);
-                    const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
-                    // (int)(u * w) % w with u in (0, 1]: the product is in [0, w], so the modulo only maps w to 0
-                    const int wx = xmax - xmin, wy = ymax - ymin;
-                    const int tx = (int)(__fmul_rn(u1, (float)wx)), ty = (int)(__fmul_rn(u2, (float)wy));
-                    cx = xmin + (tx >= wx ? tx - wx : tx);
-                    cy = ymin + (ty >= wy ? ty - wy : ty);
-                }
-            };
-            float4 pref[SPEC ? 9 : 1];  // rows of the speculatively fetched next candidate
-            bool have_pref = false;
-            int pcx = -1, pcy = -1;
-    #pragma unroll 1
-            for (int i = 0; i < total; ++i) {
-                int cx, cy;
-                const bool is_rand = i >= n_prop_end;
-                candidate(i, xbest, ybest, cx, cy);
-                if (!is_rand) {
-                    if (i < n_first) n_ref += (j == 0);
-                } else {
-                    n_ref += (j == 0);
-                    if (cx == xbest && cy == ybest) continue;  // D3
-                }
-                n_eval += (j == 0);
-                float d;
-                if (SPEC && (q.amask & patch_mask(cx, cy, bw, bh)) == 0x1FFu) {
-                    float4 bv[9];
-                    if (have_pref && pcx == cx && pcy == cy) {
-    #pragma unroll
-                        for (int pi = 0; pi < 9; ++pi) bv[pi] = pref[SPEC ? pi : 0];
-                    } else {
-                        const float *b_base = D.b + ((size_t)cy * bw + cx) * C + j * 4;
-                        const float *rb[3] = {b_base - (ptrdiff_t)bw * C, b_base, b_base + (ptrdiff_t)bw * C};
-    #pragma unroll
-                        for (int pi = 0; pi < 9; ++pi) bv[pi] = ldg4(rb[pi / 3] + (pi % 3 - 1) * C);
-                    }
-                    have_pref = false;
-                    if (i + 1 < total) {  // guess the next candidate assuming this one is rejected, and start its loads
-                        int ncx, ncy;
-                        candidate(i + 1, xbest, ybest, ncx, ncy);
-                        const bool skip = (i + 1 >= n_prop_end) && ncx == xbest && ncy == ybest;
-                        if (!skip && (q.amask & patch_mask(ncx, ncy, bw, bh)) == 0x1FFu) {
-                            const float *b_base = D.b + ((size_t)ncy * bw + ncx) * C + j * 4;
-                            const float *rb[3] = {b_base - (ptrdiff_t)bw * C, b_base, b_base + (ptrdiff_t)bw * C};
-    #pragma unroll
-                            for (int pi = 0; pi < 9; ++pi) pref[SPEC ? pi : 0] = ldg4(rb[pi / 3] + (pi % 3 - 1) * C);
-                            have_pref = true;
-                            pcx = ncx;
-                            pcy = ncy;
-                        }
-                    }
-                    float acc0 = 0.f, acc1 = 0.f;  // the interior path of u_eval (C = 64: even pixels -> acc0, odd -> acc1)
-    #pragma unroll
-                    for (int pi = 0; pi < 9; ++pi) {
-                        if (pi & 1) acc1 = fma4(q.a[(T::A_IN_REGS && !AS) ? pi : 0], bv[pi], acc1);
-                        else acc0 = fma4(q.a[(T::A_IN_REGS && !AS) ? pi : 0], bv[pi], acc0);
-                    }
-                    d = u_finish<C, HALF>(acc0, acc1, mask, 9);
-                } else {
-                    d = u_eval<C, HALF, AS>(q, D.b, cx, cy, bw, bh, j, mask);
-                }
-                const float dcmp = is_rand ? __fadd_rn(d, FLT_MIN) : d;
-                if (i < n_first || dcmp < dbest) {
-                    dbest = d;
-                    xbest = cx;
-                    ybest = cy;
-                }
-            }
-        } else {
-    #pragma unroll 1
-            for (int i = 0; i < total; ++i) {
-                int cx, cy;
-                const bool is_rand = i >= n_prop_end;
-                if (!is_rand) {
-                    const int k = i - n_first;
-                    const uint32_t cv = (i < n_first) ? v0 : (k == 0 ? q0.c0 : (k == 1 ? q0.c1 : (k == 2 ? q0.c2 : q0.c3)));
-                    cx = int_to_x(cv);
-                    cy = int_to_y(cv);
-                    if (i < n_first) n_ref += (j == 0);
-                } else {
-                    const int m = i - n_prop_end;
-                    const int mag = D.rs_start >> m;
-                    const int xmin = max(xbest - mag, 0), xmax = min(xbest + mag + 1, bw);
-                    const int ymin = max(ybest - mag, 0), ymax = min(ybest + mag + 1, bh);
-                    const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
-                    const int wx = xmax - xmin, wy = ymax - ymin;
-                    const int tx = (int)(__fmul_rn(u1, (float)wx)), ty = (int)(__fmul_rn(u2, (float)wy));
-                    cx = xmin + (tx >= wx ? tx - wx : tx);
-                    cy = ymin + (ty >= wy ? ty - wy : ty);
-                    n_ref += (j == 0);
-                    if (cx == xbest && cy == ybest) continue;  // D3
-                }
-                n_eval += (j == 0);
-                const float d = u_eval<C, HALF, AS>(q, D.b, cx, cy, bw, bh, j, mask);
-                const float dcmp = is_rand ? __fadd_rn(d, FLT_MIN) : d;
-                if (i < n_first || dcmp < dbest) {
-                    dbest = d;
-                    xbest = cx;
-                    ybest = cy;
-                }
-            }
-        }
-        if (j == 0) {
-            const uint32_t vnew = xy_to_int(xbest, ybest);
-            D.nnf_out[p] = vnew;
-            D.lc_out[p] = vnew != v0 ? (int8_t)s.t : D.lc_in[p];
-            D.nnd[p] = dbest;
-        }
-    }
-    if (s.counters && (n_eval | n_ref)) {
-        atomicAdd(&s.counters[0], (unsigned long long)n_eval);
-        atomicAdd(&s.counters[1], (unsigned long long)n_ref);
-    }
-}
-
-// ------------------------------------------------------------------ tiled step kernel with cp.async-staged candidates
-// pm_step_t_kernel is latency-bound on the candidate chain of a query: the rows of candidate i + 1 are only requested
-// after candidate i has been reduced -- for the random search necessarily so in program order, because the window of
-// candidate i + 1 is centred on the best match AFTER candidate i.  More loads in flight per thread cost registers (36
-// per candidate at C = 64) and with them resident warps: measured slower (profiles/r1_pm_tuning.md, NCT_PM_SPEC).
-// Here the rows of up to NB candidates of a query are in flight at once without holding registers: every lane copies
-// its 16-byte pieces global -> shared with cp.async (LDGSTS; .ca keeps the L1 allocation the neighbouring queries'
-// overlapping patches profit from) into NB staging buffers of its group and reads back only what it copied itself, so
-// no barrier is needed -- cp.async.wait_all orders a lane's own copies.  A ROUND = the next <= NB candidates of the
-// query: the propagation candidates are known; the random-search positions are computed from the current best, i.e.
-// under the assumption that no candidate of the round is accepted (the common case after the first iterations).  The
-// round is then consumed in order with the ordinary acceptance rule; every candidate's position is recomputed from
-// the best match at that point, and if it differs from the speculated one (an acceptance moved the window) the round
-// ends there and the next round starts from that candidate.  The sequence of (position, distance, decision) is
-// therefore exactly pm_step_t_kernel's -- same field, same distances, same evaluation counters (a mis-speculated copy is
-// not an evaluation) -- and the arithmetic per distance is u_eval's predicated path, bit for bit.
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
-{
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-template <int C, bool HALF, int NB>
-__global__ void __launch_bounds__(128) pm_step_ta_kernel(const PMStep s, const int tile)
-{
-    using T = UTraits<C, HALF>;
-    constexpr int GL = T::LANES, NV = T::NV, ST = T::STRIDE;
-    constexpr int BUF = 9 * NV * GL;   // float4 per candidate buffer, [patch pixel][vector][lane of the group]
-    extern __shared__ float4 pm_stage[];  // [group of the block][NB][BUF]
-    __shared__ TQueryState st_all[4][32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    TQueryState *st = st_all[wib];
-    const int warp_global = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-    const int q_first = warp_global * tile;
-    if (q_first >= s.nq_total) return;  // whole warps leave together
-    const int jump = s.jump;
-    const int n_first = s.first ? 1 : 0;
-    unsigned n_eval = 0, n_ref = 0;
-
-    // ---- phase 1: one lane per query (identical to pm_step_t_kernel)
-    bool has_work = false;
-    {
-        const int qidx = q_first + lane;
-        if (lane < tile && qidx < s.nq_total) {
-            const int dsel = qidx >= s.nq0 ? 1 : 0;
-            const PMDir &D = s.d[dsel];
-            const int p = qidx - (dsel ? s.nq0 : 0);
-            const int aw = D.aw, ah = D.ah, bw = D.bw, bh = D.bh;
-            const int ax = p % aw, ay = p / aw;
-            const uint32_t v0 = D.nnf_in[p];
-            uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-            int n = 0;
-            const int qx[4] = {ax - jump, ax + jump, ax, ax};
-            const int qy[4] = {ay, ay, ay - jump, ay + jump};
-            const int sx[4] = {jump, -jump, 0, 0};
-            const int sy[4] = {0, 0, jump, -jump};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (qx[k] >= 0 && qx[k] < aw && qy[k] >= 0 && qy[k] < ah) {
-                    const int qi = qy[k] * aw + qx[k];
-                    const uint32_t vp = D.nnf_in[qi];
-                    const int xp = int_to_x(vp) + sx[k], yp = int_to_y(vp) + sy[k];
-                    if (yp >= 0 && yp < bh && xp >= 0 && xp < bw) {
-                        n_ref++;
-                        const uint32_t cv = xy_to_int(xp, yp);
-                        const bool dup = (cv == v0) || (n > 0 && cv == c0) || (n > 1 && cv == c1) || (n > 2 && cv == c2);
-                        const bool stale = s.t >= 4 && (int)D.lc_in[qi] <= s.t - 5;  // D4
-                        if (!dup && !stale) {
-                            if (n == 0) c0 = cv;
-                            else if (n == 1) c1 = cv;
-                            else if (n == 2) c2 = cv;
-                            else c3 = cv;
-                            n++;
-                        }
-                    }
-                }
-            }
-            const int total = n_first + n + (s.do_random ? D.n_mag : 0);
-            if (total == 0) {  // nothing to compare: the entry stays
-                D.nnf_out[p] = v0;
-                D.lc_out[p] = D.lc_in[p];
-            } else {
-                has_work = true;
-                st[lane].v0 = v0; st[lane].c0 = c0; st[lane].c1 = c1; st[lane].c2 = c2; st[lane].c3 = c3;
-                st[lane].qidx = qidx;
-                st[lane].n = n;
-                st[lane].dbest = s.first ? 0.f : D.nnd[p];
-            }
-        }
-    }
-    const unsigned work = __ballot_sync(0xffffffffu, has_work);
-    __syncwarp();
-
-    // ---- phase 2: one group of 16 / 32 lanes per query with work
-    const int grp = HALF ? (lane >> 4) : 0;
-    const int j = HALF ? (lane & 15) : lane;
-    const unsigned mask = HALF ? (grp ? 0xffff0000u : 0x0000ffffu) : 0xffffffffu;
-    float4 *gbuf = pm_stage + (size_t)((wib * (HALF ? 2 : 1) + grp) * NB) * BUF + j;
-    const int nwork = __popc(work);
 #pragma unroll 1
-    for (int r = grp; r < nwork; r += (HALF ? 2 : 1)) {
-        const int src = (int)__fns(work, 0, r + 1);
-        const TQueryState q0 = st[src];
-        const int qidx = q0.qidx;
-        const int dsel = qidx >= s.nq0 ? 1 : 0;
-        const PMDir &D = s.d[dsel];
-        const int p = qidx - (dsel ? s.nq0 : 0);
-        const int aw = D.aw, ah = D.ah, bw = D.bw, bh = D.bh;
-        const int ax = p % aw, ay = p / aw;
-        const uint32_t v0 = q0.v0;
-        int xbest = int_to_x(v0), ybest = int_to_y(v0);
-        float dbest = q0.dbest;
-        const int n_prop_end = n_first + q0.n;
-        const int total = n_prop_end + (s.do_random ? D.n_mag : 0);
-        const unsigned amask = patch_mask(ax, ay, aw, ah);
-        const float *a_base = D.a + ((size_t)ay * aw + ax) * C + j * 4;
-        float4 areg[T::A_IN_REGS ? 9 * NV : 1];
-        if (T::A_IN_REGS) {
-#pragma unroll
-            for (int pi = 0; pi < 9; ++pi) {
-                const int dy = pi / 3 - 1, dx = pi % 3 - 1;
-#pragma unroll
-                for (int k = 0; k < NV; ++k) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if ((amask >> pi) & 1u) v = ldg4(a_base + ((ptrdiff_t)dy * aw + dx) * C + k * ST);
-                    areg[pi * NV + k] = v;
-                }
-            }
-        }
-        const float *u = D.rng + (size_t)ax * D.ndraws + (size_t)s.iter * 2 * D.n_mag;
-        // candidate i of this query given the best match (xb, yb): a propagation list entry, or the random-search draw
-        auto candidate = [&](int i, int xb, int yb, int &cx, int &cy) {
-            if (i < n_prop_end) {
+        for (int i = 0; i < total; ++i) {
+            int cx, cy;
+            const bool is_rand = i >= n_prop_end;
+            if (!is_rand) {
                 const int k = i - n_first;
                 const uint32_t cv = (i < n_first) ? v0 : (k == 0 ? q0.c0 : (k == 1 ? q0.c1 : (k == 2 ? q0.c2 : q0.c3)));
                 cx = int_to_x(cv);
                 cy = int_to_y(cv);
+                if (i < n_first) n_ref += (j == 0);
             } else {
                 const int m = i - n_prop_end;
                 const int mag = D.rs_start >> m;
-                const int xmin = max(xb - mag, 0), xmax = min(xb + mag + 1, bw);
-                const int ymin = max(yb - mag, 0), ymax = min(yb + mag + 1, bh);
+                const int xmin = max(xbest - mag, 0), xmax = min(xbest + mag + 1, bw);
+                const int ymin = max(ybest - mag, 0), ymax = min(ybest + mag + 1, bh);
                 const float u1 = __ldg(u + 2 * m), u2 = __ldg(u + 2 * m + 1);
-                // (int)(u * w) % w with u in (0, 1]: the product is in [0, w], so the modulo only maps w to 0
                 const int wx = xmax - xmin, wy = ymax - ymin;
                 const int tx = (int)(__fmul_rn(u1, (float)wx)), ty = (int)(__fmul_rn(u2, (float)wy));
                 cx = xmin + (tx >= wx ? tx - wx : tx);
                 cy = ymin + (ty >= wy ? ty - wy : ty);
+                n_ref += (j == 0);
+                if (cx == xbest && cy == ybest) continue;  // D3
             }
-        };
-        int i = 0;
-#pragma unroll 1
-        while (i < total) {
-            // ---- issue a round: copies of candidates i .. i + NB - 1, positions speculated from the current best
-            uint32_t pos[NB];
-#pragma unroll
-            for (int k = 0; k < NB; ++k) {
-                pos[k] = 0xFFFFFFFFu;  // "nothing staged in buffer k"
-                if (i + k < total) {
-                    int cx, cy;
-                    candidate(i + k, xbest, ybest, cx, cy);
-                    const bool d3 = (i + k >= n_prop_end) && cx == xbest && cy == ybest;  // would be skipped, not evaluated
-                    if (!d3) {
-                        pos[k] = xy_to_int(cx, cy);
-                        const unsigned valid = amask & patch_mask(cx, cy, bw, bh);
-                        const float *b_base = D.b + ((size_t)cy * bw + cx) * C + j * 4;
-                        float4 *buf = gbuf + k * BUF;
-#pragma unroll
-                        for (int pi = 0; pi < 9; ++pi) {
-                            const int dy = pi / 3 - 1, dx = pi % 3 - 1;
-                            if ((valid >> pi) & 1u) {
-#pragma unroll
-                                for (int v = 0; v < NV; ++v) cp_async16(buf + (pi * NV + v) * GL, b_base + ((ptrdiff_t)dy * bw + dx) * C + v * ST);
-                            }
-                        }
-                    }
-                }
-            }
-            cp_async_wait_all();
-            // ---- consume the round in order
-            bool stop = false;
-#pragma unroll
-            for (int k = 0; k < NB; ++k) {
-                if (!stop && i < total) {
-                    int cx, cy;
-                    const bool is_rand = i >= n_prop_end;
-                    candidate(i, xbest, ybest, cx, cy);
-                    if (is_rand && cx == xbest && cy == ybest) {  // D3: d == dbest, never accepted
-                        n_ref += (j == 0);
-                        ++i;
-                    } else if (pos[k] != xy_to_int(cx, cy)) {
-                        stop = true;  // an acceptance moved the window: this candidate opens the next round
-                    } else {
-                        if (is_rand || i < n_first) n_ref += (j == 0);
-                        n_eval += (j == 0);
-                        const unsigned valid = amask & patch_mask(cx, cy, bw, bh);
-                        const float4 *buf = gbuf + k * BUF;
-                        float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-                        for (int pi = 0; pi < 9; ++pi) {
-                            const int dy = pi / 3 - 1, dx = pi % 3 - 1;
-                            if ((valid >> pi) & 1u) {
-                                float4 av[NV], bv[NV];
-#pragma unroll
-                                for (int v = 0; v < NV; ++v) {
-                                    if (T::A_IN_REGS) av[v] = areg[T::A_IN_REGS ? pi * NV + v : 0];
-                                    else av[v] = ldg4(a_base + ((ptrdiff_t)dy * aw + dx) * C + v * ST);
-                                    bv[v] = buf[(pi * NV + v) * GL];
-                                }
-                                u_accumulate<C, HALF>(acc0, acc1, pi, av, bv);
-                            }
-                        }
-                        const float d = u_finish<C, HALF>(acc0, acc1, mask, __popc(valid));
-                        const float dcmp = is_rand ? __fadd_rn(d, FLT_MIN) : d;
-                        if (i < n_first || dcmp < dbest) {
-                            dbest = d;
-                            xbest = cx;
-                            ybest = cy;
-                        }
-                        ++i;
-                    }
-                }
+            n_eval += (j == 0);
+            const float d = u_eval<C, HALF>(q, D.b, cx, cy, bw, bh, j, mask);
+            const float dcmp = is_rand ? __fadd_rn(d, FLT_MIN) : d;
+            if (i < n_first || dcmp < dbest) {
+                dbest = d;
+                xbest = cx;
+                ybest = cy;
             }
         }
         if (j == 0) {
@@ -1376,21 +674,6 @@ __global__ void __launch_bounds__(128) pm_step_ta_kernel(const PMStep s, const i
         atomicAdd(&s.counters[0], (unsigned long long)n_eval);
         atomicAdd(&s.counters[1], (unsigned long long)n_ref);
     }
-}
-
-template <int C, int NB>
-static void launch_ta(const PMStep &s, int tile, int blocks, cudaStream_t st)
-{
-    using T = UTraits<C, true>;
-    constexpr size_t smem = (size_t)(128 / T::LANES) * NB * 9 * T::NV * T::LANES * sizeof(float4);
-    static bool configured[64] = {false};   // per device (the attribute is per function and device)
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaFuncSetAttribute(pm_step_ta_kernel<C, true, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured[dev] = true;
-    }
-    pm_step_ta_kernel<C, true, NB><<<blocks, 128, smem, st>>>(s, tile);
 }
 
 // queries per warp: 32 when that still leaves >= ~16 warps per SM, otherwise fewer (the coarse levels have few queries)
@@ -1401,80 +684,22 @@ static int pm_tile_size(int nq_total, int num_sms)
     return tile;
 }
 
-// staging depth of pm_step_ta_kernel for channel count c from NCT_PM_ASYNC="n64,n128" (default: see PM_ASYNC_DEFAULT_*)
-#ifndef PM_ASYNC_DEFAULT_64
-#define PM_ASYNC_DEFAULT_64 0
-#endif
-#ifndef PM_ASYNC_DEFAULT_128
-#define PM_ASYNC_DEFAULT_128 0
-#endif
-static int pm_async_depth(int c)
-{
-    int n64 = PM_ASYNC_DEFAULT_64, n128 = PM_ASYNC_DEFAULT_128;
-    const char *e = getenv("NCT_PM_ASYNC");
-    if (e) {
-        n64 = atoi(e);
-        const char *comma = strchr(e, ',');
-        n128 = comma ? atoi(comma + 1) : n64 / 2;
-    }
-    return c == 64 ? n64 : n128;
-}
-
 template <int C>
 struct UseHalfWarp { static constexpr bool value = (C == 64 || C == 128); };
 
-template <int C, bool HW = UseHalfWarp<C>::value>
+// C >= 64: the tiled kernel (16 lanes per distance at C = 64 / 128, 32 at C = 256 / 512); C = 16, 32 (not used by the
+// VGG levels; accepted by the ABI): the plain warp-per-query kernel
+template <int C>
 struct StepLauncher {
     static void go(const PMStep &s, cudaStream_t st)
     {
-        static const char *legacy = getenv("NCT_PM_LEGACY");  // A/B switch for profiling
-        if (C >= 256 && !legacy) {
+        if constexpr (C >= 64) {
             const int tile = pm_tile_size(s.nq_total, 148);
             const int blocks = nct_div_up(nct_div_up(s.nq_total, tile), 4);  // 4 warps per block, `tile` queries per warp
-            pm_step_t_kernel<(C >= 256 ? C : 256), false><<<blocks, 128, 0, st>>>(s, tile);
-            return;
-        }
-        if (C >= 256 && legacy[0] == 'u') {
-            const int blocks = nct_div_up(s.nq_total, 4);  // 128 threads = 4 warps = 4 queries
-            pm_step_u_kernel<(C >= 256 ? C : 256), false><<<blocks, 128, 0, st>>>(s);
-            return;
-        }
-        const int blocks = nct_div_up(s.nq_total, PM_TPB / 32);
-        pm_step_kernel<C><<<blocks, PM_TPB, 0, st>>>(s);
-    }
-};
-template <int C>
-struct StepLauncher<C, true> {
-    static void go(const PMStep &s, cudaStream_t st)
-    {
-        static const char *legacy = getenv("NCT_PM_LEGACY");  // A/B switch for profiling: "1" warp kernel, "hw" unrolled half warp
-        if (legacy && legacy[0] == '1') {
+            pm_step_t_kernel<C, UseHalfWarp<C>::value><<<blocks, 128, 0, st>>>(s, tile);
+        } else {
             const int blocks = nct_div_up(s.nq_total, PM_TPB / 32);
             pm_step_kernel<C><<<blocks, PM_TPB, 0, st>>>(s);
-        } else if (legacy && legacy[0] == 'h') {
-            const int blocks = nct_div_up(s.nq_total, 8);  // 128 threads = 4 warps = 8 queries
-            pm_step_hw_kernel<C><<<blocks, 128, 0, st>>>(s);
-        } else if (legacy) {
-            const int blocks = nct_div_up(s.nq_total, 8);
-            pm_step_u_kernel<C, true><<<blocks, 128, 0, st>>>(s);
-        } else {
-            static const bool a_smem = getenv("NCT_PM_ASMEM") != nullptr;  // A/B: query patch in shared memory
-            const int tile = pm_tile_size(s.nq_total, 148);
-            const int blocks = nct_div_up(nct_div_up(s.nq_total, tile), 4);
-            static const bool spec = getenv("NCT_PM_SPEC") != nullptr;     // experimental: speculative next-candidate fetch (C = 64)
-            // cp.async-staged candidates: NCT_PM_ASYNC="<buffers at C = 64>,<buffers at C = 128>" (0 = the register kernel)
-            static const int nb64 = pm_async_depth(64), nb128 = pm_async_depth(128);
-            const int nb = C == 64 ? nb64 : nb128;
-            if (nb > 0 && C == 64) {
-                if (nb >= 6) launch_ta<64, 6>(s, tile, blocks, st);
-                else if (nb >= 4) launch_ta<64, 4>(s, tile, blocks, st);
-                else launch_ta<64, 3>(s, tile, blocks, st);
-            } else if (nb > 0 && C == 128) {
-                if (nb >= 3) launch_ta<128, 3>(s, tile, blocks, st);
-                else launch_ta<128, 2>(s, tile, blocks, st);
-            } else if (spec && C == 64) pm_step_t_kernel<64, true, false, true><<<blocks, 128, 0, st>>>(s, tile);
-            else if (a_smem) pm_step_t_kernel<C, true, true><<<blocks, 128, 0, st>>>(s, tile);
-            else pm_step_t_kernel<C, true><<<blocks, 128, 0, st>>>(s, tile);
         }
     }
 };
