@@ -81,6 +81,8 @@ int nct_hwc_to_chw(nct_ctx *ctx, const float *src_hwc_dev, float *dst_chw_dev, i
  * dst[p][c] = src[p][c] / sqrt(sum_c src[p][c]^2); zero-norm pixels give zeros.
  * One fused kernel instead of 5 launches + 4 cudaMalloc/Free.  In-place allowed. */
 int nct_l2norm(nct_ctx *ctx, const float *src_hwc_dev, float *dst_hwc_dev, int C, int H, int W);
+/* The same normalisation, each value then rounded to FP16 (round to nearest even): dst = C*H*W halves. */
+int nct_l2norm_f16(nct_ctx *ctx, const float *src_dev, uint16_t *dst_f16_dev, int C, int H, int W);
 
 /* ---------------------------------------------------------------- NNF */
 
@@ -107,6 +109,13 @@ int nct_patchmatch(nct_ctx *ctx, const float *a_hwc_dev, const float *b_hwc_dev,
 int nct_patchmatch_bidir(nct_ctx *ctx, const float *a_hwc_dev, const float *b_hwc_dev,
                          uint32_t *ann_dev, float *annd_dev, uint32_t *bnn_dev, float *bnnd_dev,
                          const int params_ab[11]);
+/* FP16 feature store (throughput mode, no counterpart in the reference): the same kernels gathering from volumes stored as
+ * IEEE half (uint16 storage, produced by nct_l2norm_f16).  Every half is converted to FP32 exactly and the arithmetic is
+ * unchanged, so the result is bit-identical to nct_patchmatch* on the FP16-rounded volumes.  C >= 64, iters >= 1. */
+int nct_patchmatch_f16(nct_ctx *ctx, const uint16_t *a_f16_dev, const uint16_t *b_f16_dev, uint32_t *ann_dev, float *annd_dev,
+                       const int params[11]);
+int nct_patchmatch_bidir_f16(nct_ctx *ctx, const uint16_t *a_f16_dev, const uint16_t *b_f16_dev, uint32_t *ann_dev, float *annd_dev,
+                             uint32_t *bnn_dev, float *bnnd_dev, const int params[11]);
 
 /* The per-column XORWOW uniforms the reference draws (curand_init(seed = column, 0, 0),
  * NCT/GeneralizedPatchMatch.cu:54-66): out[col*ndraws + k].  Exposed for tests. */
@@ -281,6 +290,11 @@ typedef struct nct_config {
     int kmeans_iters;        /* 11 (CT/ColorTransfer.cpp:373) */
     double wls_rel_tol;      /* relative residual at which the WLS PCG stops (stands in for PARDISO's exact solve) */
     int stop_after_level;    /* 4 = full pyramid; smaller values stop early (test hook: intermediates stay in scratch) */
+    int feature_store;       /* 0 = FP32 PatchMatch volumes (the reference's storage; default), 1 = FP16: the L2-normalised
+                              * volumes PatchMatch gathers from are rounded to FP16 (half the bytes of the L2-bound kernel;
+                              * throughput mode beyond the reference).  The result then equals the oracle
+                              * run with FP16-rounded volumes (oracle/pipeline.py feature_store="f16") bit for bit, not the
+                              * FP32 one. */
 } nct_config;
 
 void nct_config_default(nct_config *cfg);

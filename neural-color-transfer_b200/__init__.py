@@ -26,7 +26,7 @@ class Config(C.Structure):
     """nct_config (CT/Config.h:55-98 + NCT/main.cu:64-83)"""
     _fields_ = [("bds_weight", _d), ("var_eps", _d), ("nonlocal_weight", _d), ("local_weight", _d), ("wls_lambda_init", _d),
                 ("cluster_num", _i), ("k_num", _i), ("patch_size", _i), ("wls_alpha", _d), ("pm_iters", _i),
-                ("kmeans_iters", _i), ("wls_rel_tol", _d), ("stop_after_level", _i)]
+                ("kmeans_iters", _i), ("wls_rel_tol", _d), ("stop_after_level", _i), ("feature_store", _i)]
 
 
 # name -> (restype, argtypes); every symbol include/nct.h declares must be listed here
@@ -49,10 +49,13 @@ ABI = {
     "nct_chw_to_hwc": (_i, [c_ctx_p, _p, _p, _i, _i, _i]),
     "nct_hwc_to_chw": (_i, [c_ctx_p, _p, _p, _i, _i, _i]),
     "nct_l2norm": (_i, [c_ctx_p, _p, _p, _i, _i, _i]),
+    "nct_l2norm_f16": (_i, [c_ctx_p, _p, _p, _i, _i, _i]),
     "nct_nnf_init": (_i, [c_ctx_p, _p, _i, _i, _i, _i]),
     "nct_nnf_upsample": (_i, [c_ctx_p, _p, _i, _i, _p, _i, _i, _i, _i]),
     "nct_patchmatch": (_i, [c_ctx_p, _p, _p, _p, _p, C.POINTER(_i)]),
     "nct_patchmatch_bidir": (_i, [c_ctx_p, _p, _p, _p, _p, _p, _p, C.POINTER(_i)]),
+    "nct_patchmatch_f16": (_i, [c_ctx_p, _p, _p, _p, _p, C.POINTER(_i)]),
+    "nct_patchmatch_bidir_f16": (_i, [c_ctx_p, _p, _p, _p, _p, _p, _p, C.POINTER(_i)]),
     "nct_xorwow_table": (_i, [c_ctx_p, _p, _i, _i]),
     "nct_patchmatch_stats": (_i, [c_ctx_p, C.POINTER(_ll)]),
     "nct_patchmatch_count_evals": (_i, [c_ctx_p, _i]),
@@ -298,6 +301,14 @@ class Context:
         self._check(self.lib.nct_l2norm(self.h, _ptr(src_hwc), _ptr(dst), Cn, H, W))
         return dst
 
+    def norm_f16(self, src_hwc):
+        """the same normalisation rounded to FP16 (torch.float16 tensor): the FP16 feature store of the PatchMatch volumes"""
+        import torch
+        H, W, Cn = src_hwc.shape
+        dst = torch.empty((H, W, Cn), dtype=torch.float16, device=src_hwc.device)
+        self._check(self.lib.nct_l2norm_f16(self.h, _ptr(src_hwc), _ptr(dst), Cn, H, W))
+        return dst
+
     # -- NNF
     def init_ann(self, ann, ah, aw, bh, bw):
         """init_Ann_kernel (NCT/GeneralizedPatchMatch.cu:527-544); ann: int32/uint32 [ah*aw] cuda tensor."""
@@ -310,14 +321,21 @@ class Context:
         return ann
 
     def patchmatch_single(self, a, b, ann, annd, params):
-        """patchmatch_single<<<>>> (NCT/GeneralizedPatchMatch.cu:677-831); a, b L2-normalised HWC."""
-        self._check(self.lib.nct_patchmatch(self.h, _ptr(a), _ptr(b), _ptr(ann), _ptr(annd), params))
+        """patchmatch_single<<<>>> (NCT/GeneralizedPatchMatch.cu:677-831); a, b L2-normalised HWC, float32 or (FP16
+        feature store) float16."""
+        import torch
+        fn = self.lib.nct_patchmatch_f16 if a.dtype == torch.float16 else self.lib.nct_patchmatch
+        if a.dtype != b.dtype:
+            raise NctError("a and b must have the same dtype")
+        self._check(fn(self.h, _ptr(a), _ptr(b), _ptr(ann), _ptr(annd), params))
 
     def patchmatch_bidir(self, a, b, ann, annd, bnn, bnnd, params_ab):
-        """Both launches of NCT/main.cu:283-284 fused."""
-        self._check(
-            self.lib.nct_patchmatch_bidir(self.h, _ptr(a), _ptr(b), _ptr(ann), _ptr(annd), _ptr(bnn), _ptr(bnnd), params_ab)
-        )
+        """Both launches of NCT/main.cu:283-284 fused (float32 or float16 volumes)."""
+        import torch
+        fn = self.lib.nct_patchmatch_bidir_f16 if a.dtype == torch.float16 else self.lib.nct_patchmatch_bidir
+        if a.dtype != b.dtype:
+            raise NctError("a and b must have the same dtype")
+        self._check(fn(self.h, _ptr(a), _ptr(b), _ptr(ann), _ptr(annd), _ptr(bnn), _ptr(bnnd), params_ab))
 
     def xorwow_table(self, ncols, ndraws):
         import torch

@@ -213,6 +213,15 @@ int nct_profile_enable(nct_ctx *ctx, int enable)
 {
     NCT_ENTER(ctx);
     ctx->profile = enable ? 1 : 0;
+    if (enable) {
+        // events for ~4 pairs up front: creating them inside the measured region (cudaEventCreate takes driver-wide locks the
+        // other contexts' launching threads contend for) slowed the profiled context measurably
+        while (ctx->prof_pool.size() < 256) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) break;
+            ctx->prof_pool.push_back(e);
+        }
+    }
     return NCT_OK;
 }
 

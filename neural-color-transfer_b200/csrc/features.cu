@@ -7,6 +7,7 @@
 // order of oracle/pm_oracle.c (decision D2/D5) and writes the normalised row.
 // HBM-bound: 8 bytes per element (read + write).
 #include "nct_internal.h"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -20,8 +21,21 @@ __device__ __forceinline__ float butterfly(float acc)
     return acc;
 }
 
+// four normalised values -> the output row: FP32 as they are, or rounded to FP16 (round to nearest even: the FP16
+// feature store of the PatchMatch volumes, nct_l2norm_f16)
+__device__ __forceinline__ void store4(float *row, int vi, float4 o) { reinterpret_cast<float4 *>(row)[vi] = o; }
+__device__ __forceinline__ void store4(__half *row, int vi, float4 o)
+{
+    const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const unsigned *>(&lo);
+    u.y = *reinterpret_cast<const unsigned *>(&hi);
+    reinterpret_cast<uint2 *>(row)[vi] = u;
+}
+
 // one warp per pixel; V = C/4 vectors, lane handles vectors lane, lane+32, ...
-__global__ void __launch_bounds__(256) l2norm_kernel(const float *__restrict__ src, float *__restrict__ dst, int npix,
+template <typename O>
+__global__ void __launch_bounds__(256) l2norm_kernel(const float *__restrict__ src, O *__restrict__ dst, int npix,
                                                      int C)
 {
     const int lane = threadIdx.x & 31;
@@ -29,7 +43,7 @@ __global__ void __launch_bounds__(256) l2norm_kernel(const float *__restrict__ s
     const int V = C >> 2;
     for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < npix; p += warps_per_grid) {
         const float4 *x = reinterpret_cast<const float4 *>(src + (size_t)p * C);
-        float4 *y = reinterpret_cast<float4 *>(dst + (size_t)p * C);
+        O *y = dst + (size_t)p * C;
         float4 v[4];  // C <= 512 -> at most 4 vectors per lane
         float acc = 0.f;
 #pragma unroll
@@ -63,7 +77,7 @@ __global__ void __launch_bounds__(256) l2norm_kernel(const float *__restrict__ s
                 } else {
                     o = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                y[vi] = o;
+                store4(y, vi, o);
             }
         }
     }
@@ -100,7 +114,24 @@ int nct_l2norm(nct_ctx *ctx, const float *src, float *dst, int C, int H, int W)
     int blocks = nct_div_up(npix, 8);
     const int max_blocks = ctx->num_sms * 8;
     if (blocks > max_blocks) blocks = max_blocks;
-    l2norm_kernel<<<blocks, 256, 0, ctx->stream>>>(src, dst, npix, C);
+    l2norm_kernel<float><<<blocks, 256, 0, ctx->stream>>>(src, dst, npix, C);
+    NCT_CHECK_LAUNCH(ctx);
+    return NCT_OK;
+}
+
+// the same normalisation (bit-identical FP32 values), each value then rounded to FP16 (RN-even): the PatchMatch volumes
+// of the FP16 feature store.  dst: C*H*W halves (uint16 storage).
+int nct_l2norm_f16(nct_ctx *ctx, const float *src, uint16_t *dst, int C, int H, int W)
+{
+    NCT_ENTER(ctx);
+    NCT_REQUIRE(ctx, src && dst, "null device pointer");
+    NCT_REQUIRE(ctx, C > 0 && C % 4 == 0 && C <= 512, "channel count %d must be a multiple of 4, <= 512", C);
+    NCT_REQUIRE(ctx, H > 0 && W > 0, "bad size");
+    const int npix = H * W;
+    int blocks = nct_div_up(npix, 8);
+    const int max_blocks = ctx->num_sms * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    l2norm_kernel<__half><<<blocks, 256, 0, ctx->stream>>>(src, reinterpret_cast<__half *>(dst), npix, C);
     NCT_CHECK_LAUNCH(ctx);
     return NCT_OK;
 }

@@ -16,6 +16,7 @@
 //   * per-column XORWOW streams are materialised once per call into a small table.
 #include "nct_internal.h"
 #include <cfloat>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -101,8 +102,8 @@ __global__ void xorwow_table_kernel(float *__restrict__ out, int ncols, int ndra
 #endif
 
 struct PMDir {
-    const float *a;          // query features   [ah][aw][C]
-    const float *b;          // target features  [bh][bw][C]
+    const void *a;           // query features   [ah][aw][C], FP32 or (FP16 feature store) FP16
+    const void *b;           // target features  [bh][bw][C]
     const uint32_t *nnf_in;  // NNF at the end of the previous step
     uint32_t *nnf_out;
     float *nnd;              // own entry only: read + write in place
@@ -135,6 +136,15 @@ struct PMTraits {
 };
 
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+// FP16 feature store: four halves (8 bytes) -> four floats, exactly (every FP16 value is an FP32 value), so the products and
+// sums below are those of the oracle run on the FP16-rounded volumes
+__device__ __forceinline__ float4 ldg4(const __half *p)
+{
+    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&r.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&r.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 
 __device__ __forceinline__ float butterfly(float acc)
 {
@@ -314,9 +324,9 @@ __global__ void __launch_bounds__(PM_TPB, (C <= 128) ? PM_MINB_SMALL : 1) pm_ste
     // with D4 most queries of a converged region have nothing to evaluate in the jump 8/4/2 steps: the query patch is
     // only fetched when something will be compared against it
     QueryPatch<C> q;
-    load_query<C>(q, D.a, ax, ay, aw, ah, lane, s.first || s.do_random || use[0] || use[1] || use[2] || use[3]);
+    load_query<C>(q, (const float *)D.a, ax, ay, aw, ah, lane, s.first || s.do_random || use[0] || use[1] || use[2] || use[3]);
     if (s.first) {
-        dbest = eval_dist<C>(q, D.b, xbest, ybest, bw, bh, lane);
+        dbest = eval_dist<C>(q, (const float *)D.b, xbest, ybest, bw, bh, lane);
         n_eval++;
         n_ref++;
     } else {
@@ -332,7 +342,7 @@ __global__ void __launch_bounds__(PM_TPB, (C <= 128) ? PM_MINB_SMALL : 1) pm_ste
         unsigned valid[BATCH];
 #pragma unroll
         for (int j = 0; j < BATCH; ++j)
-            if (use[k0 + j]) load_cand<C>(q, D.b, int_to_x(cand[k0 + j]), int_to_y(cand[k0 + j]), bw, bh, lane, bv[j], valid[j]);
+            if (use[k0 + j]) load_cand<C>(q, (const float *)D.b, int_to_x(cand[k0 + j]), int_to_y(cand[k0 + j]), bw, bh, lane, bv[j], valid[j]);
 #pragma unroll
         for (int j = 0; j < BATCH; ++j) {
             dc[k0 + j] = 0.f;
@@ -367,7 +377,7 @@ __global__ void __launch_bounds__(PM_TPB, (C <= 128) ? PM_MINB_SMALL : 1) pm_ste
             n_ref++;
             if (xp == xbest && yp == ybest) continue;
             n_eval++;
-            const float d = eval_dist<C>(q, D.b, xp, yp, bw, bh, lane);
+            const float d = eval_dist<C>(q, (const float *)D.b, xp, yp, bw, bh, lane);
             if (__fadd_rn(d, FLT_MIN) < dbest) {
                 dbest = d;
                 xbest = xp;
@@ -403,11 +413,11 @@ struct UTraits {
     static constexpr bool A_IN_REGS = (C == 64) || (C == 256);
 };
 
-template <int C, bool HALF>
+template <int C, bool HALF, typename E = float>
 struct UQuery {
     using T = UTraits<C, HALF>;
     float4 a[T::A_IN_REGS ? 9 * T::NV : 1];
-    const float *a_base;
+    const E *a_base;
     int aw;
     unsigned amask;
 };
@@ -448,18 +458,18 @@ __device__ __forceinline__ float u_finish(float acc0, float acc1, unsigned mask,
     return __fdiv_rn(-acc, (float)n);
 }
 
-template <int C, bool HALF>
-__device__ __forceinline__ float u_eval(const UQuery<C, HALF> &q, const float *__restrict__ b, int bx, int by, int bw, int bh, int j,
+template <int C, bool HALF, typename E>
+__device__ __forceinline__ float u_eval(const UQuery<C, HALF, E> &q, const E *__restrict__ b, int bx, int by, int bw, int bh, int j,
                                         unsigned mask)
 {
     using T = UTraits<C, HALF>;
     constexpr int NV = T::NV, ST = T::STRIDE;
     const unsigned valid = q.amask & patch_mask(bx, by, bw, bh);
-    const float *b_base = b + ((size_t)by * bw + bx) * C + j * 4;
+    const E *b_base = b + ((size_t)by * bw + bx) * C + j * 4;
     float acc0 = 0.f, acc1 = 0.f;
     if (valid == 0x1FFu) {
-        const float *rb[3] = {b_base - (ptrdiff_t)bw * C, b_base, b_base + (ptrdiff_t)bw * C};
-        const float *ra[3] = {q.a_base - (ptrdiff_t)q.aw * C, q.a_base, q.a_base + (ptrdiff_t)q.aw * C};
+        const E *rb[3] = {b_base - (ptrdiff_t)bw * C, b_base, b_base + (ptrdiff_t)bw * C};
+        const E *ra[3] = {q.a_base - (ptrdiff_t)q.aw * C, q.a_base, q.a_base + (ptrdiff_t)q.aw * C};
         float4 bv[9 * NV];
 #pragma unroll
         for (int pi = 0; pi < 9; ++pi)
@@ -523,7 +533,7 @@ struct TQueryState {
     float dbest;
 };
 
-template <int C, bool HALF>
+template <int C, bool HALF, typename E>
 __global__ void __launch_bounds__(128, HALF ? 4 : 2) pm_step_t_kernel(const PMStep s, const int tile)
 {
     using T = UTraits<C, HALF>;
@@ -614,10 +624,10 @@ __global__ void __launch_bounds__(128, HALF ? 4 : 2) pm_step_t_kernel(const PMSt
         const int n_prop_end = n_first + q0.n;
         const int total = n_prop_end + (s.do_random ? D.n_mag : 0);
 
-        UQuery<C, HALF> q;
+        UQuery<C, HALF, E> q;
         q.aw = aw;
         q.amask = patch_mask(ax, ay, aw, ah);
-        q.a_base = D.a + ((size_t)ay * aw + ax) * C + j * 4;
+        q.a_base = (const E *)D.a + ((size_t)ay * aw + ax) * C + j * 4;
         if (T::A_IN_REGS) {
 #pragma unroll
             for (int pi = 0; pi < 9; ++pi) {
@@ -655,7 +665,7 @@ __global__ void __launch_bounds__(128, HALF ? 4 : 2) pm_step_t_kernel(const PMSt
                 if (cx == xbest && cy == ybest) continue;  // D3
             }
             n_eval += (j == 0);
-            const float d = u_eval<C, HALF>(q, D.b, cx, cy, bw, bh, j, mask);
+            const float d = u_eval<C, HALF, E>(q, (const E *)D.b, cx, cy, bw, bh, j, mask);
             const float dcmp = is_rand ? __fadd_rn(d, FLT_MIN) : d;
             if (i < n_first || dcmp < dbest) {
                 dbest = d;
@@ -691,12 +701,13 @@ struct UseHalfWarp { static constexpr bool value = (C == 64 || C == 128); };
 // VGG levels; accepted by the ABI): the plain warp-per-query kernel
 template <int C>
 struct StepLauncher {
-    static void go(const PMStep &s, cudaStream_t st)
+    static void go(const PMStep &s, cudaStream_t st, bool f16)
     {
         if constexpr (C >= 64) {
             const int tile = pm_tile_size(s.nq_total, 148);
             const int blocks = nct_div_up(nct_div_up(s.nq_total, tile), 4);  // 4 warps per block, `tile` queries per warp
-            pm_step_t_kernel<C, UseHalfWarp<C>::value><<<blocks, 128, 0, st>>>(s, tile);
+            if (f16) pm_step_t_kernel<C, UseHalfWarp<C>::value, __half><<<blocks, 128, 0, st>>>(s, tile);
+            else pm_step_t_kernel<C, UseHalfWarp<C>::value, float><<<blocks, 128, 0, st>>>(s, tile);
         } else {
             const int blocks = nct_div_up(s.nq_total, PM_TPB / 32);
             pm_step_kernel<C><<<blocks, PM_TPB, 0, st>>>(s);
@@ -716,15 +727,17 @@ __global__ void __launch_bounds__(PM_TPB) pm_init_dist_kernel(const PMStep s)
     const int p = warp_global - (dsel ? s.nq0 : 0);
     const int ax = p % D.aw, ay = p / D.aw;
     QueryPatch<C> q;
-    load_query<C>(q, D.a, ax, ay, D.aw, D.ah, lane);
+    load_query<C>(q, (const float *)D.a, ax, ay, D.aw, D.ah, lane);
     const uint32_t v0 = D.nnf_in[p];
-    float d = eval_dist<C>(q, D.b, int_to_x(v0), int_to_y(v0), D.bw, D.bh, lane);
+    float d = eval_dist<C>(q, (const float *)D.b, int_to_x(v0), int_to_y(v0), D.bw, D.bh, lane);
     if (lane == 0) D.nnd[p] = d;
 }
 
 template <int C>
-int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1, int ndir, int8_t *lc)
+int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1, int ndir, int8_t *lc, bool f16)
 {
+    if (f16 && (C < 64 || iters == 0))
+        return nct_fail(ctx, NCT_ERR_ARG, "the FP16 feature store covers C >= 64 and iters >= 1 (got C = %d, iters = %d)", C, iters);
     const int warps_per_block = PM_TPB / 32;
     const int blocks = nct_div_up(s.nq_total, warps_per_block);
     s.counters = ctx->pm_count_evals ? ctx->pm_counters : nullptr;
@@ -755,13 +768,13 @@ int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1
                 s.d[d].lc_in = lcbuf[step & 1][d];
                 s.d[d].lc_out = lcbuf[(step & 1) ^ 1][d];
             }
-            StepLauncher<C>::go(s, ctx->stream);
+            StepLauncher<C>::go(s, ctx->stream, f16);
             NCT_CHECK_LAUNCH(ctx);
         }
     return NCT_OK;
 }
 
-int fill_dir(nct_ctx *ctx, PMDir &D, const float *a, const float *b, uint32_t *ann, float *annd, int ah, int aw,
+int fill_dir(nct_ctx *ctx, PMDir &D, const void *a, const void *b, uint32_t *ann, float *annd, int ah, int aw,
              int bh, int bw, int iters, int rs_max, const char *rng_name)
 {
     D.a = a;
@@ -804,17 +817,17 @@ int check_params(nct_ctx *ctx, const int *p)
     return NCT_OK;
 }
 
-int dispatch_pm(nct_ctx *ctx, int C, PMStep &s, int iters, uint32_t *t0, uint32_t *t1, int ndir)
+int dispatch_pm(nct_ctx *ctx, int C, PMStep &s, int iters, uint32_t *t0, uint32_t *t1, int ndir, bool f16 = false)
 {
     int8_t *lc = (int8_t *)nct_scratch(ctx, "pm_last_change", 2 * (size_t)s.nq_total);
     if (!lc) return NCT_ERR_NOMEM;
     switch (C) {
-    case 16: return launch_pm<16>(ctx, s, iters, t0, t1, ndir, lc);
-    case 32: return launch_pm<32>(ctx, s, iters, t0, t1, ndir, lc);
-    case 64: return launch_pm<64>(ctx, s, iters, t0, t1, ndir, lc);
-    case 128: return launch_pm<128>(ctx, s, iters, t0, t1, ndir, lc);
-    case 256: return launch_pm<256>(ctx, s, iters, t0, t1, ndir, lc);
-    case 512: return launch_pm<512>(ctx, s, iters, t0, t1, ndir, lc);
+    case 16: return launch_pm<16>(ctx, s, iters, t0, t1, ndir, lc, f16);
+    case 32: return launch_pm<32>(ctx, s, iters, t0, t1, ndir, lc, f16);
+    case 64: return launch_pm<64>(ctx, s, iters, t0, t1, ndir, lc, f16);
+    case 128: return launch_pm<128>(ctx, s, iters, t0, t1, ndir, lc, f16);
+    case 256: return launch_pm<256>(ctx, s, iters, t0, t1, ndir, lc, f16);
+    case 512: return launch_pm<512>(ctx, s, iters, t0, t1, ndir, lc, f16);
     }
     return nct_fail(ctx, NCT_ERR_ARG, "unsupported channel count %d", C);
 }
@@ -854,7 +867,7 @@ int nct_xorwow_table(nct_ctx *ctx, float *out_dev, int ncols, int ndraws)
     return NCT_OK;
 }
 
-int nct_patchmatch(nct_ctx *ctx, const float *a, const float *b, uint32_t *ann, float *annd, const int params[11])
+static int patchmatch_single_impl(nct_ctx *ctx, const void *a, const void *b, uint32_t *ann, float *annd, const int params[11], bool f16)
 {
     NCT_ENTER(ctx);
     int rc = check_params(ctx, params);
@@ -871,11 +884,21 @@ int nct_patchmatch(nct_ctx *ctx, const float *a, const float *b, uint32_t *ann, 
     uint32_t *t0 = (uint32_t *)nct_scratch(ctx, "pm_nnf_tmp0", sizeof(uint32_t) * (size_t)ah * aw);
     if (!t0) return NCT_ERR_NOMEM;
     if (ctx->pm_count_evals) NCT_CUDA(ctx, cudaMemsetAsync(ctx->pm_counters, 0, 16, ctx->stream));
-    return dispatch_pm(ctx, C, s, iters, t0, nullptr, 1);
+    return dispatch_pm(ctx, C, s, iters, t0, nullptr, 1, f16);
 }
 
-int nct_patchmatch_bidir(nct_ctx *ctx, const float *a, const float *b, uint32_t *ann, float *annd, uint32_t *bnn,
-                         float *bnnd, const int params[11])
+int nct_patchmatch(nct_ctx *ctx, const float *a, const float *b, uint32_t *ann, float *annd, const int params[11])
+{
+    return patchmatch_single_impl(ctx, a, b, ann, annd, params, false);
+}
+
+int nct_patchmatch_f16(nct_ctx *ctx, const uint16_t *a, const uint16_t *b, uint32_t *ann, float *annd, const int params[11])
+{
+    return patchmatch_single_impl(ctx, a, b, ann, annd, params, true);
+}
+
+static int patchmatch_bidir_impl(nct_ctx *ctx, const void *a, const void *b, uint32_t *ann, float *annd, uint32_t *bnn, float *bnnd,
+                                 const int params[11], bool f16)
 {
     NCT_ENTER(ctx);
     int rc = check_params(ctx, params);
@@ -894,7 +917,19 @@ int nct_patchmatch_bidir(nct_ctx *ctx, const float *a, const float *b, uint32_t 
     uint32_t *t1 = (uint32_t *)nct_scratch(ctx, "pm_nnf_tmp1", sizeof(uint32_t) * (size_t)bh * bw);
     if (!t0 || !t1) return NCT_ERR_NOMEM;
     if (ctx->pm_count_evals) NCT_CUDA(ctx, cudaMemsetAsync(ctx->pm_counters, 0, 16, ctx->stream));
-    return dispatch_pm(ctx, C, s, iters, t0, t1, 2);
+    return dispatch_pm(ctx, C, s, iters, t0, t1, 2, f16);
+}
+
+int nct_patchmatch_bidir(nct_ctx *ctx, const float *a, const float *b, uint32_t *ann, float *annd, uint32_t *bnn,
+                         float *bnnd, const int params[11])
+{
+    return patchmatch_bidir_impl(ctx, a, b, ann, annd, bnn, bnnd, params, false);
+}
+
+int nct_patchmatch_bidir_f16(nct_ctx *ctx, const uint16_t *a, const uint16_t *b, uint32_t *ann, float *annd, uint32_t *bnn,
+                             float *bnnd, const int params[11])
+{
+    return patchmatch_bidir_impl(ctx, a, b, ann, annd, bnn, bnnd, params, true);
 }
 
 int nct_patchmatch_count_evals(nct_ctx *ctx, int enable)

@@ -29,6 +29,7 @@ void nct_config_default(nct_config *cfg)
     cfg->kmeans_iters = 11;        // CT/ColorTransfer.cpp:373
     cfg->wls_rel_tol = 1e-8;       // relative residual; the maps then agree with a direct solve to ~1e-10
     cfg->stop_after_level = 4;
+    cfg->feature_store = 0;        // FP32 PatchMatch volumes, the reference's storage
 }
 
 int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int cw, const uint8_t *stl_bgr_dev, int sh, int sw,
@@ -42,6 +43,7 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
     if (cfg_in) cfg = *cfg_in;
     else nct_config_default(&cfg);
     NCT_REQUIRE(ctx, cfg.patch_size == 3 && cfg.k_num == 8, "patch_size must be 3 and k_num 8 (CT/Config.h:68-70)");
+    NCT_REQUIRE(ctx, cfg.feature_store == 0 || cfg.feature_store == 1, "feature_store must be 0 (FP32) or 1 (FP16)");
     const int L = 5;
     int dc[5][3], ds[5][3];
     nct_vgg19_level_dims(ch, cw, dc);
@@ -73,6 +75,12 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
     }
     float *normC = (float *)nct_scratch(ctx, "pipe_normC", sizeof(float) * maxFeatAll);
     float *normS = (float *)nct_scratch(ctx, "pipe_normS", sizeof(float) * maxFeatAll);
+    uint16_t *normC16 = nullptr, *normS16 = nullptr;   // FP16 feature store: the volumes PatchMatch gathers from
+    if (cfg.feature_store == 1) {
+        normC16 = (uint16_t *)nct_scratch(ctx, "pipe_normC16", sizeof(uint16_t) * maxFeatAll);
+        normS16 = (uint16_t *)nct_scratch(ctx, "pipe_normS16", sizeof(uint16_t) * maxFeatAll);
+        if (!normC16 || !normS16) return NCT_ERR_NOMEM;
+    }
     uint32_t *ann = (uint32_t *)nct_scratch(ctx, "pipe_ann", sizeof(uint32_t) * nC);
     uint32_t *bnn = (uint32_t *)nct_scratch(ctx, "pipe_bnn", sizeof(uint32_t) * nS);
     uint32_t *ann_prev = (uint32_t *)nct_scratch(ctx, "pipe_ann_prev", sizeof(uint32_t) * nC);
@@ -145,7 +153,17 @@ int nct_transfer_pair_dev(nct_ctx *ctx, const uint8_t *cnt_bgr_dev, int ch, int 
         STEP(nct_l2norm(ctx, featC[l], normC, C, ah, aw));
         // bidirectional PatchMatch (:283-284)
         const int params[11] = {C, ah, aw, bh, bw, cfg.patch_size, cfg.pm_iters, range[l], 0, 10, 1};
-        { NctStageTimer t(ctx, ST_PM); STEP(nct_patchmatch_bidir(ctx, normC, normS, ann, annd, bnn, bnnd, params)); }
+        if (cfg.feature_store == 1) {
+            // FP16 feature store: PatchMatch reads half-precision copies (half the bytes); the BDS feature error below still
+            // uses the FP32 content volume and the un-normalised style features
+            STEP(nct_l2norm_f16(ctx, featS[l], normS16, C, bh, bw));
+            STEP(nct_l2norm_f16(ctx, featC[l], normC16, C, ah, aw));
+            NctStageTimer t(ctx, ST_PM);
+            STEP(nct_patchmatch_bidir_f16(ctx, normC16, normS16, ann, annd, bnn, bnnd, params));
+        } else {
+            NctStageTimer t(ctx, ST_PM);
+            STEP(nct_patchmatch_bidir(ctx, normC, normS, ann, annd, bnn, bnnd, params));
+        }
         if (vis) STEP(nct_vis_flows(ctx, l, ann, bnn, cntImg[l], stlImg[l], ah, aw, bh, bw));
         // BDS colour reconstruction at level size (:291) and BDS feature error (:297-318)
         { NctStageTimer t(ctx, ST_BDS);

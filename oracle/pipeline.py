@@ -32,13 +32,16 @@ DEFAULT_CFG = dict(bds=2.0, eps=0.6, nl=2.0, l=0.125, w=0.024, clusters=10, knum
 
 
 def transfer_pair(cnt, stl, weights=None, cfg=None, features_fn=None, on_level=None, stop_after_level=4, timings=None,
-                  im2col=True, pm_mode="canonical", result_hook=None, cg_mode="reference", pm_fn=None):
+                  im2col=True, pm_mode="canonical", result_hook=None, cg_mode="reference", pm_fn=None, feature_store="f32"):
     """cnt, stl: uint8 BGR (H, W, 3).  Returns the uint8 BGR result (content size).
     pm_mode: "canonical" = deterministic jump-flood oracle (the parity target); "reference" = reference-semantics
     in-place serial PatchMatch in the reference's layout / summation order (CPU baseline only).
     cg_mode: "reference" = explicit A, A^T A by scipy (the reference's structure; summation order unspecified);
     "canonical" = the defined-order matrix-free CG of oracle/cg_oracle.c (decision N1) -- with canonical features
     (vgg.features_canonical) this makes the whole oracle run a bit-level target for the product.
+    feature_store: "f32" (the reference's storage) or "f16" = the product's FP16 feature-store mode: the two normalised
+    volumes PatchMatch gathers from are rounded to IEEE half (round to nearest even) and used as exact FP32 values; every
+    other stage (BDS votes, feature error, clustering) keeps the FP32 volumes.
     pm_fn: optional replacement of the PatchMatch stage, pm_fn(nC, nS, ann, bnn, p_ab, p_ba) -> (ann, annd, bnn, bnnd)
     (tests plug the reference's own racy kernel in here to measure the reference's run-to-run noise floor)."""
     cfg = DEFAULT_CFG | (cfg or {})
@@ -86,12 +89,18 @@ def transfer_pair(cnt, stl, weights=None, cfg=None, features_fn=None, on_level=N
         nC = _pm.l2norm_hwc(featC[l])
         p_ab = _pm.make_params(Cn, ah, aw, bh, bw, cfg["pm_iters"], rng[l])
         p_ba = _pm.make_params(Cn, bh, bw, ah, aw, cfg["pm_iters"], rng[l])
+        nC_pm, nS_pm = nC, nS
+        if feature_store == "f16":
+            nC_pm = nC.astype(np.float16).astype(np.float32)
+            nS_pm = nS.astype(np.float16).astype(np.float32)
+        elif feature_store != "f32":
+            raise ValueError("feature_store must be 'f32' or 'f16'")
         if pm_fn is not None:
             ann, annd, bnn, bnnd = pm_fn(nC, nS, ann, bnn, p_ab, p_ba)
             st_a = st_b = (0, 0)
         elif pm_mode == "canonical":
-            ann, annd, st_a = _pm.patchmatch(nC, nS, ann, p_ab)
-            bnn, bnnd, st_b = _pm.patchmatch(nS, nC, bnn, p_ba)
+            ann, annd, st_a = _pm.patchmatch(nC_pm, nS_pm, ann, p_ab)
+            bnn, bnnd, st_b = _pm.patchmatch(nS_pm, nC_pm, bnn, p_ba)
         else:
             nC_chw = np.ascontiguousarray(nC.transpose(2, 0, 1))
             nS_chw = np.ascontiguousarray(nS.transpose(2, 0, 1))

@@ -340,3 +340,27 @@ def test_headline_700x700_pair_reproduces_the_committed_golden_image(pkg, dev, w
         assert ndiff == 0
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("seed,ch,cw,sh,sw", [(4, 128, 128, 128, 128), (8, 120, 152, 136, 104)])
+def test_fp16_feature_store_pipeline_equals_the_oracle_in_the_same_mode(pkg, dev, weights, seed, ch, cw, sh, sw):
+    """cfg.feature_store = 1 (FP16 PatchMatch volumes): the whole pipeline against an independent oracle run in the same
+    mode (oracle/pipeline.py feature_store="f16") -- byte-identical; and the mode is a different (not a broken) result:
+    close to the FP32-store image."""
+    from oracle import vgg
+
+    c = pkg.Context(0)
+    c.load_vgg19_weights(weights)
+    c.set_vgg_engine(3)
+    try:
+        cnt, stl = synth.pair(seed, ch, cw, sh, sw)
+        out16 = c.transfer_pair(cnt, stl, c.default_config(feature_store=1))
+        out32 = c.transfer_pair(cnt, stl, c.default_config(feature_store=0))
+        ref16 = pipeline.transfer_pair(cnt, stl, None, features_fn=lambda img, deepest: vgg.features_fixedpoint(img, weights, deepest),
+                                       cg_mode="canonical", feature_store="f16")
+        ndiff = int((out16 != ref16).sum())
+        print(f"FP16 feature store ({ch}x{cw}): {ndiff} bytes differ from the oracle in the same mode; PSNR vs the FP32 store {pipeline.psnr(out16, out32):.1f} dB")
+        assert ndiff == 0
+        assert pipeline.psnr(out16, out32) > 30.0
+    finally:
+        c.close()

@@ -276,3 +276,58 @@ def test_finest_level_700x700x64_ten_iterations_matches_the_committed_golden(pkg
     crcs = [zlib.crc32(np.ascontiguousarray(v).tobytes()) for v in (ga, gad, gb, gbd)]
     assert crcs == [int(v) for v in g["pm700_crc"]]
     assert ev == int(g["pm700_evals"].sum())
+
+
+@pytest.mark.parametrize("Cn,ah,aw,bh,bw,iters,rs", [(64, 41, 37, 39, 44, 4, 8), (128, 33, 35, 30, 31, 3, 4), (256, 20, 24, 22, 19, 3, 32),
+                                                     (512, 12, 13, 11, 14, 10, 2), (64, 96, 96, 96, 96, 10, 32)])
+def test_fp16_feature_store_is_bit_exact_against_the_oracle_on_rounded_volumes(pkg, ctx, dev, Cn, ah, aw, bh, bw, iters, rs):
+    """Throughput mode beyond the reference: the PatchMatch volumes stored as FP16.  nct_l2norm_f16 = the
+    canonical normalisation rounded to nearest-even half; the kernels convert every half to FP32 exactly and keep their
+    arithmetic, so NNF, distances and evaluation counters equal the ORACLE run on the rounded volumes, bit for bit."""
+    import torch
+
+    a = synth.feature_volume(51, ah, aw, Cn)
+    b = synth.feature_volume(52, bh, bw, Cn)
+    na16, nb16 = ctx.norm_f16(to_dev(a, dev)), ctx.norm_f16(to_dev(b, dev))
+    ctx.synchronize()
+    oa16 = oracle.l2norm_hwc(a).astype(np.float16)
+    ob16 = oracle.l2norm_hwc(b).astype(np.float16)
+    assert np.array_equal(na16.cpu().numpy().view(np.uint16), oa16.view(np.uint16))
+    assert np.array_equal(nb16.cpu().numpy().view(np.uint16), ob16.view(np.uint16))
+    ann = torch.empty(ah * aw, dtype=torch.int32, device=dev)
+    bnn = torch.empty(bh * bw, dtype=torch.int32, device=dev)
+    annd = torch.empty(ah * aw, dtype=torch.float32, device=dev)
+    bnnd = torch.empty(bh * bw, dtype=torch.float32, device=dev)
+    ctx.init_ann(ann, ah, aw, bh, bw)
+    ctx.init_ann(bnn, bh, bw, ah, aw)
+    ctx.count_evals(True)
+    ctx.patchmatch_bidir(na16, nb16, ann, annd, bnn, bnnd, pkg.make_params(Cn, ah, aw, bh, bw, iters=iters, rs_max=rs))
+    ev, _ = ctx.patchmatch_stats()
+    ctx.count_evals(False)
+    fa, fb = oa16.astype(np.float32), ob16.astype(np.float32)
+    o_ann, o_annd, st_a = oracle.patchmatch(fa, fb, oracle.nnf_init(ah, aw, bh, bw), oracle.make_params(Cn, ah, aw, bh, bw, iters=iters, rs_max=rs))
+    o_bnn, o_bnnd, st_b = oracle.patchmatch(fb, fa, oracle.nnf_init(bh, bw, ah, aw), oracle.make_params(Cn, bh, bw, ah, aw, iters=iters, rs_max=rs))
+    assert np.array_equal(ann.cpu().numpy().view(np.uint32), o_ann) and np.array_equal(bnn.cpu().numpy().view(np.uint32), o_bnn)
+    assert np.array_equal(annd.cpu().numpy().view(np.uint32), o_annd.view(np.uint32))
+    assert np.array_equal(bnnd.cpu().numpy().view(np.uint32), o_bnnd.view(np.uint32))
+    assert ev == st_a[1] + st_b[1]
+    # single direction through its own entry point
+    ann1 = torch.empty(ah * aw, dtype=torch.int32, device=dev)
+    annd1 = torch.empty(ah * aw, dtype=torch.float32, device=dev)
+    ctx.init_ann(ann1, ah, aw, bh, bw)
+    ctx.patchmatch_single(na16, nb16, ann1, annd1, pkg.make_params(Cn, ah, aw, bh, bw, iters=iters, rs_max=rs))
+    ctx.synchronize()
+    assert np.array_equal(ann1.cpu().numpy().view(np.uint32), o_ann)
+
+
+def test_fp16_feature_store_rejects_what_it_does_not_cover(pkg, ctx, dev):
+    import torch
+
+    t = torch.zeros((16, 16, 32), dtype=torch.float16, device=dev)
+    ann = torch.zeros(256, dtype=torch.int32, device=dev)
+    annd = torch.zeros(256, dtype=torch.float32, device=dev)
+    with pytest.raises(pkg.NctError):
+        ctx.patchmatch_single(t, t, ann, annd, pkg.make_params(32, 16, 16, 16, 16))            # C < 64
+    t64 = torch.zeros((16, 16, 64), dtype=torch.float16, device=dev)
+    with pytest.raises(pkg.NctError):
+        ctx.patchmatch_single(t64, t64, ann, annd, pkg.make_params(64, 16, 16, 16, 16, iters=0))  # iters = 0

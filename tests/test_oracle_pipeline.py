@@ -1,5 +1,6 @@
 """CPU test: the composed oracle pipeline (oracle/pipeline.py) runs BASELINE config 1's plumbing at a small size."""
 import numpy as np
+import pytest
 
 from oracle import pipeline, synth
 
@@ -113,3 +114,31 @@ def test_fullsize_golden_fixture_is_self_consistent():
     assert g["pm700_ann_s97"].shape == ((700 * 700 + 96) // 97,) and g["pm700_crc"].shape == (4,)
     cnt, stl = synth.pair(*[int(v) for v in g["e2e700_cfg"]])
     assert cnt.shape == (700, 700, 3)  # the pair bench.py's first context runs
+
+
+def test_fp16_feature_store_mode_of_the_oracle_changes_only_the_patchmatch_inputs():
+    """oracle/pipeline.py feature_store="f16": level 0 of a small pair -- the NNF comes from the FP16-rounded volumes (it
+    equals a direct oracle PatchMatch call on them), the mode is deterministic, and the image stays close to the FP32 one."""
+    import oracle
+
+    w = synth.vgg19_weights(19)
+    cnt, stl = synth.pair(3, 64, 64)
+    got = {}
+
+    def grab(l, d):
+        got[l] = d
+
+    a = pipeline.transfer_pair(cnt, stl, w, stop_after_level=0, feature_store="f16", on_level=grab)
+    d = got[0]
+    nC16 = d["nC"].astype(np.float16).astype(np.float32)
+    nS16 = d["nS"].astype(np.float16).astype(np.float32)
+    ah, aw, Cn = nC16.shape
+    bh, bw, _ = nS16.shape
+    ann, _, _ = oracle.patchmatch(nC16, nS16, oracle.nnf_init(ah, aw, bh, bw), oracle.make_params(Cn, ah, aw, bh, bw, 10, max(64, 64) // 16))
+    assert np.array_equal(ann, d["ann"])
+    b = pipeline.transfer_pair(cnt, stl, w, stop_after_level=0, feature_store="f16")
+    assert np.array_equal(a, b)
+    c = pipeline.transfer_pair(cnt, stl, w, stop_after_level=0)
+    assert pipeline.psnr(a, c) > 30.0
+    with pytest.raises(ValueError):
+        pipeline.transfer_pair(cnt, stl, w, stop_after_level=0, feature_store="bf16")
