@@ -371,7 +371,7 @@ def run_ours(args):
     # measured while the other P - 1 pairs co-run.  Separate from the region above because the stage events slow the profiled
     # context (round 2: context 0 took 1.9x as long per pair as its five neighbours and set the end of the whole region).
     n_prof = min(K, 4)
-    c0.profile(True)
+    c0.profile(int(os.environ.get("NCT_BENCH_PROFILE_LEVEL", "2")))   # 2 = PatchMatch spans only
     run_steps(n_prof, "dev")
     torch.cuda.synchronize(dev)
     prof = c0.profile_report()

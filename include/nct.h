@@ -60,7 +60,9 @@ void nct_reset_launch_count(nct_ctx *ctx);
 
 /* Stage timing of nct_transfer_pair* (CUDA events recorded on the ctx stream around each stage; the spans are
  * resolved when nct_profile_get is called, which synchronises).  Stages: 0 vgg, 1 patchmatch, 2 bds, 3 knn,
- * 4 nonlocal_cg, 5 wls, 6 misc, 7 kmeans.  ms_out = accumulated device milliseconds, spans_out = timed spans. */
+ * 4 nonlocal_cg, 5 wls, 6 misc, 7 kmeans.  ms_out = accumulated device milliseconds, spans_out = timed spans.
+ * enable: 0 = off, 1 = every stage, 2 = the PatchMatch stage only.  A measuring aid: a profiled context runs slower than
+ * its neighbours when several contexts share a GPU (bench.py keeps it out of the headline region). */
 int nct_profile_enable(nct_ctx *ctx, int enable);
 int nct_profile_reset(nct_ctx *ctx);
 int nct_profile_get(nct_ctx *ctx, int stage, double *ms_out, long long *spans_out);
@@ -192,6 +194,17 @@ int nct_solve_ls_cg(nct_ctx *ctx, int size, int constraints, const double *A, co
 int nct_upsample_coefficients(nct_ctx *ctx, const double *a_lvl_dev, const double *b_lvl_dev, int h, int w,
                               const uint8_t *cnt_lab_full_dev, int H, int W, double *a_full_dev, double *b_full_dev,
                               double *rough_dev);
+
+/* solve_direct_cpu(aRes, bRes, nonZeroNum, eleNum, oneBased, A, rowIndex, columns, Ba0, Xa0, ..., Bb2, Xb2)
+ * (CT/SparseSolver_CPU.h:35-43, CT/SparseSolver_CPU.cpp:104-286: MKL PARDISO, real SPD, UPPER triangle in CSR, six right-hand
+ * sides) with the same numerical arguments: host arrays, one-based CSR when one_based != 0, B[k] / X[k] = the six
+ * right-hand sides / solutions (a0 a1 a2 b0 b1 b2).  Any SPD matrix in that format: Jacobi-preconditioned CG in FP64 on the
+ * GPU to the relative residual rel_tol (<= 0: 1e-10; PARDISO is exact to rounding).  The pipeline does not use it: for the WLS
+ * system nct_solve_wls (multigrid, matrix-free) is ~40x faster; this is for callers that keep the reference's assembly
+ * (CT/ColorTransfer.cpp:951-1099). */
+int nct_solve_direct(nct_ctx *ctx, int nnz, int n, int one_based, const double *A, const int *row_index, const int *columns,
+                     const double *const B[6], double *const X[6], double rel_tol, int max_iters, int *iters_out,
+                     double *rel_res_out);
 
 /* solve_WLS_roughness_cpu + solve_direct_cpu (CT/ColorTransfer.cpp:951-1125, CT/SparseSolver_CPU.cpp:104-286):
  * (diag(rough) + L_g) x = diag(rough) x0 for the six maps, in place.  rel_tol <= 0 -> 1e-10, max_iters <= 0 -> default.

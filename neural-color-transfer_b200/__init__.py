@@ -79,6 +79,7 @@ ABI = {
     "nct_vgg19_set_weights": (_i, [c_ctx_p, _i, _p, _p]),
     "nct_vgg19_set_engine": (_i, [c_ctx_p, _i]),
     "nct_conv3x3_fixedpoint": (_i, [c_ctx_p, _p, _p, _p, _p, _p, _i, _i, _i, _i]),
+    "nct_solve_direct": (_i, [c_ctx_p, _i, _i, _i, _p, _p, _p, C.POINTER(_p), C.POINTER(_p), _d, _i, C.POINTER(_i), C.POINTER(_d)]),
     "nct_probe_read_bandwidth": (_i, [c_ctx_p, C.c_size_t, _i, C.POINTER(C.c_double)]),
     "nct_vgg19_level_dims": (_i, [_i, _i, C.POINTER(_i * 3)]),
     "nct_vgg19_features": (_i, [c_ctx_p, _p, _i, _i, _i, C.POINTER(_p)]),
@@ -259,7 +260,8 @@ class Context:
         self.lib.nct_reset_launch_count(self.h)
 
     def profile(self, enable=True):
-        self._check(self.lib.nct_profile_enable(self.h, 1 if enable else 0))
+        """stage events on the context's stream: True / 1 = every stage, 2 = the PatchMatch stage only, False = off"""
+        self._check(self.lib.nct_profile_enable(self.h, int(enable)))
         self._check(self.lib.nct_profile_reset(self.h))
 
     def profile_report(self):
@@ -455,6 +457,24 @@ class Context:
         self._check(fn(self.h, _ptr(a), _ptr(b), _ptr(rough), _ptr(cnt_lab_full), H, W, lam, alpha,
                                            rel_tol, max_iters, C.byref(it), C.byref(res)))
         return it.value, res.value
+
+    def solve_direct(self, A, row_index, columns, B, one_based=True, rel_tol=0.0, max_iters=0):
+        """solve_direct_cpu (CT/SparseSolver_CPU.h:35-43): upper-triangular CSR of an SPD matrix (numpy host arrays), B = six
+        right-hand sides (6, n).  Returns (X (6, n), iterations, relative residual)."""
+        import numpy as np
+        A = np.ascontiguousarray(A, np.float64)
+        ri = np.ascontiguousarray(row_index, np.int32)
+        co = np.ascontiguousarray(columns, np.int32)
+        B = np.ascontiguousarray(B, np.float64)
+        n = ri.size - 1
+        X = np.empty((6, n), np.float64)
+        bp = (_p * 6)(*[B[k].ctypes.data for k in range(6)])
+        xp = (_p * 6)(*[X[k].ctypes.data for k in range(6)])
+        it, res = _i(0), _d(0.0)
+        self._check(self.lib.nct_solve_direct(self.h, int(A.size), n, 1 if one_based else 0, A.ctypes.data_as(C.c_void_p),
+                                              ri.ctypes.data_as(C.c_void_p), co.ctypes.data_as(C.c_void_p), bp, xp, rel_tol, max_iters,
+                                              C.byref(it), C.byref(res)))
+        return X, it.value, res.value
 
     def apply_coefficients(self, cnt_lab_full, a, b, want_lab=False):
         import torch

@@ -187,6 +187,7 @@ void nct_graphs_free(nct_ctx *ctx)
 NctStageTimer::NctStageTimer(nct_ctx *c, int stage) : ctx(c)
 {
     if (!c || !c->profile) return;
+    if (c->profile == 2 && stage != ST_PM) return;   // level 2: PatchMatch spans only (the roofline kernel)
     nct_ctx::ProfSpan sp;
     sp.stage = stage;
     auto get = [&]() {
@@ -212,7 +213,7 @@ extern "C" {
 int nct_profile_enable(nct_ctx *ctx, int enable)
 {
     NCT_ENTER(ctx);
-    ctx->profile = enable ? 1 : 0;
+    ctx->profile = enable == 2 ? 2 : (enable ? 1 : 0);   // 1 = every stage, 2 = the PatchMatch stage only
     if (enable) {
         // events for ~4 pairs up front: creating them inside the measured region (cudaEventCreate takes driver-wide locks the
         // other contexts' launching threads contend for) slowed the profiled context measurably

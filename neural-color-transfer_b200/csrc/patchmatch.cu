@@ -706,8 +706,19 @@ struct StepLauncher {
         if constexpr (C >= 64) {
             const int tile = pm_tile_size(s.nq_total, 148);
             const int blocks = nct_div_up(nct_div_up(s.nq_total, tile), 4);  // 4 warps per block, `tile` queries per warp
-            if (f16) pm_step_t_kernel<C, UseHalfWarp<C>::value, __half><<<blocks, 128, 0, st>>>(s, tile);
-            else pm_step_t_kernel<C, UseHalfWarp<C>::value, float><<<blocks, 128, 0, st>>>(s, tile);
+            // experiment knob: NCT_PM_SMEM_PAD=<bytes> of unused dynamic shared memory per CTA caps the resident CTAs per SM
+            // (e.g. 60000 -> 3 instead of 4), leaving registers for other streams' kernels to co-reside
+            static const int pad = getenv("NCT_PM_SMEM_PAD") ? atoi(getenv("NCT_PM_SMEM_PAD")) : 0;
+            if (pad > 48 * 1024) {
+                static bool set[2] = {false, false};
+                if (!set[f16 ? 1 : 0]) {
+                    if (f16) cudaFuncSetAttribute(pm_step_t_kernel<C, UseHalfWarp<C>::value, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+                    else cudaFuncSetAttribute(pm_step_t_kernel<C, UseHalfWarp<C>::value, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+                    set[f16 ? 1 : 0] = true;
+                }
+            }
+            if (f16) pm_step_t_kernel<C, UseHalfWarp<C>::value, __half><<<blocks, 128, pad, st>>>(s, tile);
+            else pm_step_t_kernel<C, UseHalfWarp<C>::value, float><<<blocks, 128, pad, st>>>(s, tile);
         } else {
             const int blocks = nct_div_up(s.nq_total, PM_TPB / 32);
             pm_step_kernel<C><<<blocks, PM_TPB, 0, st>>>(s);

@@ -255,3 +255,40 @@ def test_wls_converged_start_returns_immediately(ctx, dev):
     its, res = ctx.solve_wls(ga, gb, to_dev(np.ones((H, W)), dev), to_dev(lab, dev), 0.5, 1.2, rel_tol=1e-8)
     assert its == 0 and res <= 1e-8
     assert np.array_equal(ga.cpu().numpy(), a) and np.array_equal(gb.cpu().numpy(), b)
+
+
+@pytest.mark.parametrize("one_based", [True, False])
+def test_solve_direct_with_the_reference_argument_list(ctx, one_based):
+    """nct_solve_direct = solve_direct_cpu's own numerical arguments (CT/SparseSolver_CPU.h:35-43): host arrays, UPPER
+    triangle of the SPD matrix in CSR (one-based as the reference builds it, CT/ColorTransfer.cpp:951-1099), six
+    right-hand sides.  (1) The WLS system the reference assembles, against scipy's direct solve (standing in for PARDISO);
+    (2) an unrelated random sparse SPD matrix: the entry point does not depend on the 5-point structure."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    rng = np.random.default_rng(7)
+    H, W = 40, 36
+    cnt, _ = synth.pair(4, H, W)
+    lab = color.bgr2lab_u8(cnt)
+    rough = np.where(rng.random((H, W)) < 0.1, 1e-6, 1.0)
+    M1 = color.wls_matrix(rough, lab[..., 0] / 255.0, 1.5, 1.2).tocsr()
+    n2 = 500
+    R = sp.random(n2, n2, density=0.01, random_state=3, format="csr")
+    M2 = (R @ R.T + sp.identity(n2) * 0.5).tocsr()
+    for M in (M1, M2):
+        n = M.shape[0]
+        U = sp.triu(M, format="csr")
+        U.sort_indices()
+        base = 1 if one_based else 0
+        B = rng.standard_normal((6, n))
+        X, its, res = ctx.solve_direct(U.data, U.indptr + base, U.indices + base, B, one_based=one_based, rel_tol=1e-11)
+        ref = spla.splu(M.tocsc()).solve(B.T).T
+        err = np.abs(X - ref).max() / np.abs(ref).max()
+        print(f"nct_solve_direct n={n} nnz(upper)={U.nnz}: {its} iterations, rel.res {res:.1e}, max rel. error vs direct solve {err:.1e}")
+        assert res <= 1e-11 and err < 1e-8
+
+
+def test_solve_direct_rejects_a_matrix_that_is_not_upper_triangular(pkg, ctx):
+    A = np.array([1.0, 0.5, 1.0])
+    with pytest.raises(pkg.NctError):
+        ctx.solve_direct(A, np.array([0, 1, 3]), np.array([0, 0, 1]), np.zeros((6, 2)), one_based=False)   # entry (1, 0) is below the diagonal
