@@ -129,18 +129,35 @@ __global__ void km_count_kernel(const int *__restrict__ belongs, int n, const Km
     if (i < n) atomicAdd(&count[belongs[i]], 1);
 }
 
+// member lists of the clusters in ascending point order (one warp per cluster: ballot + prefix count), so that the centre
+// sums below walk ~n / k points instead of testing all n
+__global__ void km_members_kernel(const int *__restrict__ belongs, int n, int k, const KmState *st, int *__restrict__ members)
+{
+    if (st->done) return;
+    const int c = blockIdx.x, lane = threadIdx.x;
+    int off = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const bool m = i < n && belongs[i] == c;
+        const unsigned b = __ballot_sync(0xffffffffu, m);
+        if (m) members[(size_t)c * n + off + __popc(b & ((1u << lane) - 1u))] = i;
+        off += __popc(b);
+    }
+}
+
 // new centres: double sums in point-index order (one thread per (cluster, dim))
-__global__ void km_centers_kernel(const float *__restrict__ f, int n, int dim, int k, const int *__restrict__ belongs,
+__global__ void km_centers_kernel(const float *__restrict__ f, int n, int dim, int k, const int *__restrict__ members,
                                   const int *__restrict__ count, const KmState *st, double *__restrict__ dc)
 {
     if (st->done) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= k * dim) return;
     const int c = t / dim, d = t % dim;
+    const int m = count[c];
+    const int *list = members + (size_t)c * n;
     double s = 0.0;
-    for (int i = 0; i < n; ++i)
-        if (belongs[i] == c) s = __dadd_rn(s, (double)f[(size_t)i * dim + d]);
-    dc[t] = __ddiv_rn(s, (double)count[c]);
+    for (int j = 0; j < m; ++j) s = __dadd_rn(s, (double)f[(size_t)list[j] * dim + d]);
+    dc[t] = __ddiv_rn(s, (double)m);
 }
 
 __global__ void km_reset_kernel(const KmState *st, unsigned *__restrict__ radius_bits, int *__restrict__ count, int k)
@@ -361,7 +378,8 @@ int nct_cluster_features(nct_ctx *ctx, const float *feat_norm_hwc_dev, int h, in
     char *misc = (char *)nct_scratch(ctx, "km_misc", 4096);
     double *dc = (double *)nct_scratch(ctx, "km_centers", sizeof(double) * (size_t)k * C);
     float *dist = (float *)nct_scratch(ctx, "km_dist", sizeof(float) * (size_t)n * k);
-    if (!d_shuf || !misc || !dc || !dist) return NCT_ERR_NOMEM;
+    int *members = (int *)nct_scratch(ctx, "km_members", sizeof(int) * (size_t)n * k);
+    if (!d_shuf || !misc || !dc || !dist || !members) return NCT_ERR_NOMEM;
     KmState *st = (KmState *)misc;
     int *centers = (int *)(misc + 64);
     unsigned *radius = (unsigned *)(misc + 256);
@@ -376,7 +394,9 @@ int nct_cluster_features(nct_ctx *ctx, const float *feat_norm_hwc_dev, int h, in
     NCT_CHECK_LAUNCH(ctx);
     for (int it = 0; it <= iterations; ++it) {
         if (it > 0) {
-            km_centers_kernel<<<nct_div_up(k * C, 128), 128, 0, ctx->stream>>>(feat_norm_hwc_dev, n, C, k, labels_dev, count, st, dc);
+            km_members_kernel<<<k, 32, 0, ctx->stream>>>(labels_dev, n, k, st, members);
+            NCT_CHECK_LAUNCH(ctx);
+            km_centers_kernel<<<nct_div_up(k * C, 128), 128, 0, ctx->stream>>>(feat_norm_hwc_dev, n, C, k, members, count, st, dc);
             NCT_CHECK_LAUNCH(ctx);
         }
         km_reset_kernel<<<1, 32, 0, ctx->stream>>>(st, radius, count, k);

@@ -533,8 +533,9 @@ struct TQueryState {
     float dbest;
 };
 
-template <int C, bool HALF, typename E>
-__global__ void __launch_bounds__(128, HALF ? 4 : 2) pm_step_t_kernel(const PMStep s, const int tile)
+// MINB = resident CTAs per SM the register allocation aims at (half-warp kernels; 4 -> 127 registers, 5 -> 96, 6 -> 80)
+template <int C, bool HALF, typename E, int MINB = 4>
+__global__ void __launch_bounds__(128, HALF ? MINB : 2) pm_step_t_kernel(const PMStep s, const int tile)
 {
     using T = UTraits<C, HALF>;
     __shared__ TQueryState st_all[4][32];
@@ -706,19 +707,23 @@ struct StepLauncher {
         if constexpr (C >= 64) {
             const int tile = pm_tile_size(s.nq_total, 148);
             const int blocks = nct_div_up(nct_div_up(s.nq_total, tile), 4);  // 4 warps per block, `tile` queries per warp
-            // experiment knob: NCT_PM_SMEM_PAD=<bytes> of unused dynamic shared memory per CTA caps the resident CTAs per SM
-            // (e.g. 60000 -> 3 instead of 4), leaving registers for other streams' kernels to co-reside
-            static const int pad = getenv("NCT_PM_SMEM_PAD") ? atoi(getenv("NCT_PM_SMEM_PAD")) : 0;
-            if (pad > 48 * 1024) {
-                static bool set[2] = {false, false};
-                if (!set[f16 ? 1 : 0]) {
-                    if (f16) cudaFuncSetAttribute(pm_step_t_kernel<C, UseHalfWarp<C>::value, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-                    else cudaFuncSetAttribute(pm_step_t_kernel<C, UseHalfWarp<C>::value, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-                    set[f16 ? 1 : 0] = true;
+            if constexpr (UseHalfWarp<C>::value) {
+                // NCT_PM_MINB = 4 / 5 / 6 selects the register budget of the half-warp kernels (A/B knob).  Measured (B200, 700^2
+                // level shapes, profiles/r2_pm_tuning.md): C = 64: 28.1 / 28.6 / 30.6 ms, C = 128: 15.3 / 14.7 / 15.9 ms
+                static const int minb = getenv("NCT_PM_MINB") ? atoi(getenv("NCT_PM_MINB")) : (C == 128 ? 5 : 4);
+                if (f16) {
+                    if (minb >= 6) pm_step_t_kernel<C, true, __half, 6><<<blocks, 128, 0, st>>>(s, tile);
+                    else if (minb == 5) pm_step_t_kernel<C, true, __half, 5><<<blocks, 128, 0, st>>>(s, tile);
+                    else pm_step_t_kernel<C, true, __half, 4><<<blocks, 128, 0, st>>>(s, tile);
+                } else {
+                    if (minb >= 6) pm_step_t_kernel<C, true, float, 6><<<blocks, 128, 0, st>>>(s, tile);
+                    else if (minb == 5) pm_step_t_kernel<C, true, float, 5><<<blocks, 128, 0, st>>>(s, tile);
+                    else pm_step_t_kernel<C, true, float, 4><<<blocks, 128, 0, st>>>(s, tile);
                 }
+            } else {
+                if (f16) pm_step_t_kernel<C, false, __half><<<blocks, 128, 0, st>>>(s, tile);
+                else pm_step_t_kernel<C, false, float><<<blocks, 128, 0, st>>>(s, tile);
             }
-            if (f16) pm_step_t_kernel<C, UseHalfWarp<C>::value, __half><<<blocks, 128, pad, st>>>(s, tile);
-            else pm_step_t_kernel<C, UseHalfWarp<C>::value, float><<<blocks, 128, pad, st>>>(s, tile);
         } else {
             const int blocks = nct_div_up(s.nq_total, PM_TPB / 32);
             pm_step_kernel<C><<<blocks, PM_TPB, 0, st>>>(s);
