@@ -27,9 +27,7 @@ namespace {
 
 constexpr int TPB = 256;
 constexpr int MAX_LEVELS = 14;
-#ifndef MG_FUSED_MIN_N_DEFAULT
-#define MG_FUSED_MIN_N_DEFAULT 0   // tile-fused V-cycle legs: off until measured (NCT_MG_FUSED_MIN_N)
-#endif
+
 // tunable through NCT_MG_OMEGA / NCT_MG_EDGE_SCALE for experiments; the defaults are the measured optimum on the
 // 700x700 workload (profiles/r1_wls_tuning.md)
 __constant__ float c_omega = 0.55f;
@@ -55,7 +53,6 @@ struct MgHierarchy {
     int bottom;  // first level handled by the single-block kernel
     int mid;     // first level handled by the cluster kernel (== bottom: no such level)
     int bottom_smem_bytes;  // > 0: the bottom levels run out of shared memory (mg_bottom_smem_kernel)
-    int fused_min_n;        // > 0: grid levels with at least this many nodes use the tile-fused legs
 };
 
 // the FP64 operator of the outer CG
@@ -745,213 +742,6 @@ __global__ void __launch_bounds__(TPB) pcg_update_kernel(int n, double *__restri
     }
 }
 
-// ---- tile-fused legs of the V-cycle for the large levels
-// The unfused down leg of a level is three streaming kernels (presmooth2: b -> x; residual: b, x -> t; restrict: t -> coarse b)
-// and the up leg two (prolong_smooth: x, coarse x, b -> t; smooth: t, b -> x): 348 bytes per node of vector traffic per cycle.
-// Here a thread block owns a tile of FT_X x FT_Y fine nodes and keeps the intermediates of the tile plus a halo in shared
-// memory: down = x on the tile + 2, t on the tile + 1, then the tile's coarse right-hand side; up = y = x + P xc on the
-// tile + 2, the first sweep on the tile + 1, the second on the tile.  Only b, x (once) and the coarse vectors touch global
-// memory: ~185 bytes per node per cycle, and 2 launches per level instead of 5.  Every node value is computed with the
-// arithmetic of the unfused ops (same neighbour order, same damping), halo values redundantly by the neighbouring tiles.
-// Vectors: down reads b, writes the pre-smoothed x into the level's t vector and the coarse b; up reads that t vector (with
-// halo), the coarse x and b, and writes the level's x -- no vector is both read across tiles and written in one launch.
-constexpr int FT_X = 64, FT_Y = 16, FT_TPB = 256;
-constexpr int FT_XRW = FT_X + 4, FT_XRH = FT_Y + 4;   // region with a halo of 2
-constexpr int FT_TRW = FT_X + 2, FT_TRH = FT_Y + 2;   // region with a halo of 1
-constexpr int FT_SMEM = (FT_XRW * FT_XRH + FT_TRW * FT_TRH) * 6 * (int)sizeof(T);
-
-__device__ __forceinline__ void sld6(const T *p, T (&o)[6])
-{
-    const float2 a = reinterpret_cast<const float2 *>(p)[0], b = reinterpret_cast<const float2 *>(p)[1], c = reinterpret_cast<const float2 *>(p)[2];
-    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y;
-}
-__device__ __forceinline__ void sst6(T *p, const T (&o)[6])
-{
-    reinterpret_cast<float2 *>(p)[0] = make_float2(o[0], o[1]);
-    reinterpret_cast<float2 *>(p)[1] = make_float2(o[2], o[3]);
-    reinterpret_cast<float2 *>(p)[2] = make_float2(o[4], o[5]);
-}
-
-// nbr_sum with the neighbour given as an offset (same order and weights as nbr_sum)
-template <class Get>
-__device__ __forceinline__ void nbr_sum_xy(const MgLevel &L, int i, int x, int y, Get get, T (&s)[6])
-{
-#pragma unroll
-    for (int k = 0; k < 6; ++k) s[k] = 0;
-    auto add = [&](int dx, int dy, T w) {
-        T xj[6];
-        get(dx, dy, xj);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) s[k] += w * xj[k];
-    };
-    if (x + 1 < L.W) add(1, 0, L.wx[i]);
-    if (x > 0) add(-1, 0, L.wx[i - 1]);
-    if (y + 1 < L.H) add(0, 1, L.wy[i]);
-    if (y > 0) add(0, -1, L.wy[i - L.W]);
-}
-
-__global__ void __launch_bounds__(FT_TPB) mg_down_fused_kernel(MgLevel F, MgLevel Cc, const PcgScalars *sc)
-{
-    if (sc->done) return;
-    extern __shared__ __align__(16) unsigned char ft_raw[];
-    T *sx = reinterpret_cast<T *>(ft_raw);          // x on the tile + 2: [FT_XRH][FT_XRW][6]
-    T *st = sx + FT_XRW * FT_XRH * 6;               // t on the tile + 1: [FT_TRH][FT_TRW][6]
-    const int fx0 = blockIdx.x * FT_X, fy0 = blockIdx.y * FT_Y;
-    // x = S2(b): two damped-Jacobi sweeps from a zero guess (op_presmooth2)
-    for (int idx = threadIdx.x; idx < FT_XRW * FT_XRH; idx += FT_TPB) {
-        const int lx = idx % FT_XRW, ly = idx / FT_XRW;
-        const int gx = fx0 - 2 + lx, gy = fy0 - 2 + ly;
-        if (gx < 0 || gy < 0 || gx >= F.W || gy >= F.H) continue;
-        const int i = gy * F.W + gx;
-        T bi[6], s[6], o[6];
-        ld6(F.b, i, F.n, bi);
-        nbr_sum_xy(F, i, gx, gy, [&](int dx, int dy, T (&xj)[6]) {
-            const int j = i + dy * F.W + dx;
-            ld6(F.b, j, F.n, xj);
-            const T f = OMEGA * F.invd[j];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) xj[k] *= f;
-        }, s);
-        const T f = OMEGA * F.invd[i], f2 = OMEGA2 * F.invd[i];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) o[k] = f * bi[k] + f2 * ((T(1) - OMEGA) * bi[k] + s[k]);
-        sst6(sx + idx * 6, o);
-        // the pre-smoothed x goes to the level's t vector: the up leg reads it there (halo included) and writes the final x
-        // into the x vector -- reading and writing the same vector across tiles of one launch would race
-        if (lx >= 2 && lx < 2 + FT_X && ly >= 2 && ly < 2 + FT_Y) st6(F.t, i, F.n, o);
-    }
-    __syncthreads();
-    // t = b - M x (op_residual_to_t) on the tile + 1
-    for (int idx = threadIdx.x; idx < FT_TRW * FT_TRH; idx += FT_TPB) {
-        const int lx = idx % FT_TRW, ly = idx / FT_TRW;
-        const int gx = fx0 - 1 + lx, gy = fy0 - 1 + ly;
-        if (gx < 0 || gy < 0 || gx >= F.W || gy >= F.H) continue;
-        const int i = gy * F.W + gx;
-        const T *xc = sx + ((ly + 1) * FT_XRW + (lx + 1)) * 6;
-        T bi[6], xi[6], s[6], r[6];
-        ld6(F.b, i, F.n, bi);
-        sld6(xc, xi);
-        nbr_sum_xy(F, i, gx, gy, [&](int dx, int dy, T (&xj)[6]) { sld6(xc + (dy * FT_XRW + dx) * 6, xj); }, s);
-        const T d = T(1) / F.invd[i];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) r[k] = bi[k] - d * xi[k] + s[k];
-        sst6(st + idx * 6, r);
-    }
-    __syncthreads();
-    // coarse right-hand side = P^T t (op_restrict) for the tile's aggregates
-    for (int idx = threadIdx.x; idx < (FT_X / 2) * (FT_Y / 2); idx += FT_TPB) {
-        const int J = fx0 / 2 + idx % (FT_X / 2), I = fy0 / 2 + idx / (FT_X / 2);
-        if (J >= Cc.W || I >= Cc.H) continue;
-        T acc[6] = {0, 0, 0, 0, 0, 0};
-        for (int y = 2 * I - 1; y <= 2 * I + 2; ++y) {
-            if (y < 0 || y >= F.H) continue;
-            const T wy = pw(y, I, Cc.H);
-            if (wy == T(0)) continue;
-            for (int x = 2 * J - 1; x <= 2 * J + 2; ++x) {
-                if (x < 0 || x >= F.W) continue;
-                const T w = wy * pw(x, J, Cc.W);
-                if (w == T(0)) continue;
-                T r[6];
-                sld6(st + ((y - (fy0 - 1)) * FT_TRW + (x - (fx0 - 1))) * 6, r);
-#pragma unroll
-                for (int k = 0; k < 6; ++k) acc[k] += w * r[k];
-            }
-        }
-        st6(Cc.b, I * Cc.W + J, Cc.n, acc);
-    }
-}
-
-// up leg: y = x + P xc ; t = y + w1 D^-1 (b - M y) ; x = t + w2 D^-1 (b - M t) ; RZ: level 0, fused r.z (see mg_smooth_rz_kernel)
-template <bool RZ>
-__global__ void __launch_bounds__(FT_TPB) mg_up_fused_kernel(MgLevel F, MgLevel Cc, PcgScalars *sc, double *partials, unsigned *counter)
-{
-    __shared__ double red[6 * TPB / 32];
-    if (sc->done) return;
-    extern __shared__ __align__(16) unsigned char ft_raw[];
-    T *sy = reinterpret_cast<T *>(ft_raw);          // y on the tile + 2
-    T *st = sy + FT_XRW * FT_XRH * 6;               // t on the tile + 1
-    const int fx0 = blockIdx.x * FT_X, fy0 = blockIdx.y * FT_Y;
-    for (int idx = threadIdx.x; idx < FT_XRW * FT_XRH; idx += FT_TPB) {
-        const int gx = fx0 - 2 + idx % FT_XRW, gy = fy0 - 2 + idx / FT_XRW;
-        if (gx < 0 || gy < 0 || gx >= F.W || gy >= F.H) continue;
-        const int i = gy * F.W + gx;
-        T yj[6], pc[6];
-        ld6(F.t, i, F.n, yj);   // the pre-smoothed x of the down leg (see mg_down_fused_kernel)
-        prolong_at(F, Cc, i, pc);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) yj[k] += pc[k];
-        sst6(sy + idx * 6, yj);
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < FT_TRW * FT_TRH; idx += FT_TPB) {
-        const int lx = idx % FT_TRW, ly = idx / FT_TRW;
-        const int gx = fx0 - 1 + lx, gy = fy0 - 1 + ly;
-        if (gx < 0 || gy < 0 || gx >= F.W || gy >= F.H) continue;
-        const int i = gy * F.W + gx;
-        const T *yc = sy + ((ly + 1) * FT_XRW + (lx + 1)) * 6;
-        T yi[6], bi[6], s[6], o[6];
-        sld6(yc, yi);
-        ld6(F.b, i, F.n, bi);
-        nbr_sum_xy(F, i, gx, gy, [&](int dx, int dy, T (&xj)[6]) { sld6(yc + (dy * FT_XRW + dx) * 6, xj); }, s);
-        const T invd = F.invd[i], d = T(1) / invd;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) o[k] = yi[k] + OMEGA * invd * (bi[k] - d * yi[k] + s[k]);
-        sst6(st + idx * 6, o);
-    }
-    __syncthreads();
-    double dots[6] = {0, 0, 0, 0, 0, 0};
-    for (int idx = threadIdx.x; idx < FT_X * FT_Y; idx += FT_TPB) {
-        const int lx = idx % FT_X, ly = idx / FT_X;
-        const int gx = fx0 + lx, gy = fy0 + ly;
-        if (gx >= F.W || gy >= F.H) continue;
-        const int i = gy * F.W + gx;
-        const T *tc = st + ((ly + 1) * FT_TRW + (lx + 1)) * 6;
-        T ti[6], bi[6], s[6], o[6];
-        sld6(tc, ti);
-        ld6(F.b, i, F.n, bi);
-        nbr_sum_xy(F, i, gx, gy, [&](int dx, int dy, T (&xj)[6]) { sld6(tc + (dy * FT_TRW + dx) * 6, xj); }, s);
-        const T invd = F.invd[i], d = T(1) / invd;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) o[k] = ti[k] + OMEGA2 * invd * (bi[k] - d * ti[k] + s[k]);
-        st6(F.x, i, F.n, o);
-        if (RZ) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) dots[k] += (double)bi[k] * (double)o[k];
-        }
-    }
-    if (RZ) {
-        // blocks are numbered row-major over the tile grid; partial sums per block in block order, as everywhere
-        double *my_partials = partials;
-        // grid_reduce indexes partials by blockIdx.x and compares against gridDim.x: flatten the 2-D grid
-        __shared__ bool last;
-        block_reduce<6>(dots, red);
-        const unsigned nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) my_partials[(size_t)bid * 6 + k] = dots[k];
-            __threadfence();
-            last = (atomicAdd(counter, 1u) == nblocks - 1);
-        }
-        __syncthreads();
-        if (!last) return;
-        __threadfence();
-        double acc[6] = {0, 0, 0, 0, 0, 0};
-        for (unsigned b = threadIdx.x; b < nblocks; b += FT_TPB) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) acc[k] += __ldcg(&my_partials[(size_t)b * 6 + k]);
-        }
-        block_reduce<6>(acc, red);
-        if (threadIdx.x == 0) {
-            *counter = 0;
-            for (int k = 0; k < 6; ++k) {
-                sc->rz_old[k] = sc->rz[k];
-                sc->rz[k] = acc[k];
-                sc->beta[k] = sc->rz_old[k] > 0.0 ? acc[k] / sc->rz_old[k] : 0.0;
-            }
-        }
-    }
-}
-
 // optional in-stream trace of one PCG iteration (NCT_WLS_TRACE=1): an event after every launch, printed per kernel
 struct TraceRec { const char *name; int n; cudaEvent_t e; };
 static thread_local std::vector<TraceRec> g_tr;  // (one context per host thread; the trace is a single-thread dev aid)
@@ -969,20 +759,8 @@ static thread_local bool g_tr_on = false;
 // z (level-0 x) = B r32 (level-0 b); rz and beta come out of its last kernel
 int vcycle(nct_ctx *ctx, const MgHierarchy &h, PcgScalars *sc, double *partials, unsigned *counter)
 {
-    // tile-fused legs for the levels with at least h.fused_min_n nodes (NCT_MG_FUSED_MIN_N; 0 = never); smaller grid levels
-    // keep the unfused kernels (a 64 x 16 tile grid would not fill the GPU there)
-    const int fused_min_n = h.fused_min_n;
-    auto fused = [&](const MgLevel &L) { return fused_min_n > 0 && L.n >= fused_min_n; };
     for (int k = 0; k < h.mid; ++k) {
         const MgLevel &L = h.lv[k];
-        if (fused(L)) {
-            const MgLevel &Cc = h.lv[k + 1];
-            dim3 grid(nct_div_up(L.W, FT_X), nct_div_up(L.H, FT_Y));
-            mg_down_fused_kernel<<<grid, FT_TPB, FT_SMEM, ctx->stream>>>(L, Cc, sc);
-            NCT_CHECK_LAUNCH(ctx);
-            TR("down_fused", L.n);
-            continue;
-        }
         mg_presmooth2_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L, sc);
         NCT_CHECK_LAUNCH(ctx);
         TR("presmooth2", L.n);
@@ -1002,14 +780,6 @@ int vcycle(nct_ctx *ctx, const MgHierarchy &h, PcgScalars *sc, double *partials,
     for (int k = h.mid - 1; k >= 0; --k) {
         const MgLevel &L = h.lv[k];
         const MgLevel &Cc = h.lv[k + 1];
-        if (fused(L)) {
-            dim3 grid(nct_div_up(L.W, FT_X), nct_div_up(L.H, FT_Y));
-            if (k == 0) mg_up_fused_kernel<true><<<grid, FT_TPB, FT_SMEM, ctx->stream>>>(L, Cc, sc, partials, counter);
-            else mg_up_fused_kernel<false><<<grid, FT_TPB, FT_SMEM, ctx->stream>>>(L, Cc, sc, partials, counter);
-            NCT_CHECK_LAUNCH(ctx);
-            TR("up_fused", L.n);
-            continue;
-        }
         mg_prolong_smooth_kernel<<<nct_div_up(L.n, TPB), TPB, 0, ctx->stream>>>(L, Cc, sc);
         NCT_CHECK_LAUNCH(ctx);
         TR("prolong_smooth", L.n);
@@ -1101,14 +871,10 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
     } else {
         constexpr int kSmemCap = 220 * 1024;  // of the 227 KB a block may use on sm_100
         NCT_CUDA(ctx, cudaFuncSetAttribute(mg_bottom_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCap));  // per device, cheap
-        NCT_CUDA(ctx, cudaFuncSetAttribute(mg_down_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
-        NCT_CUDA(ctx, cudaFuncSetAttribute(mg_up_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
-        NCT_CUDA(ctx, cudaFuncSetAttribute(mg_up_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
         for (int k = 1; k < nl; ++k)
             if (bottom_smem_bytes(h, k) <= (size_t)kSmemCap) { h.bottom = k; break; }
         h.bottom_smem_bytes = (int)bottom_smem_bytes(h, h.bottom);
     }
-    h.fused_min_n = getenv("NCT_MG_FUSED_MIN_N") ? atoi(getenv("NCT_MG_FUSED_MIN_N")) : MG_FUSED_MIN_N_DEFAULT;
     static const int mid_n = getenv("NCT_MG_MID_N") ? atoi(getenv("NCT_MG_MID_N")) : 0;
     h.mid = h.bottom;
     for (int k = 1; k < h.bottom; ++k)
@@ -1180,8 +946,7 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
                                                (unsigned long long)(uintptr_t)dcoef, (unsigned long long)(uintptr_t)coef,
                                                (unsigned long long)(uintptr_t)vec, (unsigned long long)(uintptr_t)dvec,
                                                (unsigned long long)(uintptr_t)partials, (unsigned long long)(uintptr_t)misc,
-                                               (unsigned long long)h.bottom, (unsigned long long)h.mid, (unsigned long long)h.bottom_smem_bytes,
-                                               (unsigned long long)h.fused_min_n};
+                                               (unsigned long long)h.bottom, (unsigned long long)h.mid, (unsigned long long)h.bottom_smem_bytes};
         if (!nct_graph_cached(ctx, gname, key)) {
             cudaGraphConditionalHandle handle = 0;
             int rc = nct_graph_begin(ctx, gname, key, mode == 2 ? &handle : nullptr);

@@ -292,31 +292,3 @@ def test_solve_direct_rejects_a_matrix_that_is_not_upper_triangular(pkg, ctx):
     A = np.array([1.0, 0.5, 1.0])
     with pytest.raises(pkg.NctError):
         ctx.solve_direct(A, np.array([0, 1, 3]), np.array([0, 0, 1]), np.zeros((6, 2)), one_based=False)   # entry (1, 0) is below the diagonal
-
-
-@pytest.mark.parametrize("H,W,lam", [(175, 160, 1.5), (350, 280, 0.4), (97, 131, 6.07)])
-def test_solve_wls_tile_fused_vcycle_legs_agree_with_the_unfused_kernels(ctx, dev, H, W, lam, monkeypatch):
-    """NCT_MG_FUSED_MIN_N: the down leg (presmooth2 + residual + restrict) and the up leg (prolong + two sweeps) of the large
-    V-cycle levels as ONE shared-memory-tiled kernel each.  Every node value is computed with the unfused ops' arithmetic;
-    only the block order of the fused r.z reduction differs, so the solves agree to rounding (iteration counts within 1) and
-    both match the direct solve."""
-    rng = np.random.default_rng(H)
-    cnt, _ = synth.pair(7, H, W)
-    lab = color.bgr2lab_u8(cnt)
-    a = 1.0 + 0.5 * rng.standard_normal((H, W, 3))
-    b = 0.2 * rng.standard_normal((H, W, 3))
-    rough = np.where(rng.random((H, W)) < 0.1, 1e-6, 1.0)
-    res = {}
-    for fused in ("0", "1"):    # 1 = every grid level fused, ragged tiles and tiny levels included
-        monkeypatch.setenv("NCT_MG_FUSED_MIN_N", fused)
-        ga, gb = to_dev(a, dev), to_dev(b, dev)
-        its, r = ctx.solve_wls(ga, gb, to_dev(rough, dev), to_dev(lab, dev), lam, 1.2, rel_tol=1e-9)
-        ctx.synchronize()
-        res[fused] = (its, ga.cpu().numpy().copy(), gb.cpu().numpy().copy())
-        assert r <= 1e-9
-    oa, ob = color.solve_wls(a, b, rough, lab[..., 0] / 255.0, lam, 1.2)
-    for fused in ("0", "1"):
-        assert relerr(res[fused][1], oa) < 1e-7 and relerr(res[fused][2], ob) < 1e-7
-    assert abs(res["0"][0] - res["1"][0]) <= 1
-    print(f"WLS {H}x{W}: {res['0'][0]} iterations unfused, {res['1'][0]} fused; max rel. diff of the solutions {relerr(res['1'][1], res['0'][1]):.1e}")
-    assert relerr(res["1"][1], res["0"][1]) < 1e-7
