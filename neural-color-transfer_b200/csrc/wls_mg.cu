@@ -91,44 +91,60 @@ __device__ __forceinline__ void st6(double *__restrict__ v, int i, int n, const 
     q[2 * (size_t)n + i] = make_double2(o[4], o[5]);
 }
 
-// sum_e w_e * X_j over the 4 neighbours, X given by a functor
+// sum_e w_e * X_j over the 4 neighbours, X given by a functor.  Straight-line: a missing neighbour (image border) is
+// replaced by the node itself with weight 0, so the four neighbour fetches are issued together instead of one dependent
+// load per conditional block (these kernels are latency-bound at every level, profiles/r2_wls_ncu.md); a zero-weight term
+// adds exactly 0, the order of the four terms is unchanged.
 template <class GetX>
 __device__ __forceinline__ void nbr_sum(const MgLevel &L, int i, GetX getx, T (&s)[6])
 {
     const int x = i % L.W, y = i / L.W;
+    const bool r = x + 1 < L.W, l = x > 0, d = y + 1 < L.H, u = y > 0;
+    const int jr = r ? i + 1 : i, jl = l ? i - 1 : i, jd = d ? i + L.W : i, ju = u ? i - L.W : i;
+    const T wr = r ? L.wx[i] : T(0), wl = l ? L.wx[jl] : T(0), wd = d ? L.wy[i] : T(0), wu = u ? L.wy[ju] : T(0);
+    T xr[6], xl[6], xd[6], xu[6];
+    getx(jr, xr);
+    getx(jl, xl);
+    getx(jd, xd);
+    getx(ju, xu);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) s[k] = 0;
-    auto add = [&](int j, T w) {
-        T xj[6];
-        getx(j, xj);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) s[k] += w * xj[k];
-    };
-    if (x + 1 < L.W) add(i + 1, L.wx[i]);
-    if (x > 0) add(i - 1, L.wx[i - 1]);
-    if (y + 1 < L.H) add(i + L.W, L.wy[i]);
-    if (y > 0) add(i - L.W, L.wy[i - L.W]);
+    for (int k = 0; k < 6; ++k) {
+        T acc = T(0);
+        acc += wr * xr[k];
+        acc += wl * xl[k];
+        acc += wd * xd[k];
+        acc += wu * xu[k];
+        s[k] = acc;
+    }
 }
 
-// FP64 version on the fine operator; also returns the diagonal
+// FP64 version on the fine operator; also returns the diagonal (same straight-line form)
 template <class GetX>
 __device__ __forceinline__ double nbr_sum64(const FineOp &F, int i, GetX getx, double (&s)[6])
 {
     const int x = i % F.W, y = i / F.W;
+    const bool r = x + 1 < F.W, l = x > 0, d = y + 1 < F.H, u = y > 0;
+    const int jr = r ? i + 1 : i, jl = l ? i - 1 : i, jd = d ? i + F.W : i, ju = u ? i - F.W : i;
+    const double wr = r ? F.wx[i] : 0.0, wl = l ? F.wx[jl] : 0.0, wd = d ? F.wy[i] : 0.0, wu = u ? F.wy[ju] : 0.0;
+    double xr[6], xl[6], xd[6], xu[6];
+    getx(jr, xr);
+    getx(jl, xl);
+    getx(jd, xd);
+    getx(ju, xu);
     double diag = F.rough[i];
+    diag += wr;
+    diag += wl;
+    diag += wd;
+    diag += wu;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) s[k] = 0.0;
-    auto add = [&](int j, double w) {
-        double xj[6];
-        getx(j, xj);
-        diag += w;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) s[k] += w * xj[k];
-    };
-    if (x + 1 < F.W) add(i + 1, F.wx[i]);
-    if (x > 0) add(i - 1, F.wx[i - 1]);
-    if (y + 1 < F.H) add(i + F.W, F.wy[i]);
-    if (y > 0) add(i - F.W, F.wy[i - F.W]);
+    for (int k = 0; k < 6; ++k) {
+        double acc = 0.0;
+        acc += wr * xr[k];
+        acc += wl * xl[k];
+        acc += wd * xd[k];
+        acc += wu * xu[k];
+        s[k] = acc;
+    }
     return diag;
 }
 
@@ -174,24 +190,36 @@ __device__ __forceinline__ T pw(int x, int J, int nc)
     return (Jp == J ? T(0.75) : T(0)) + (Jn == J ? T(0.25) : T(0));
 }
 
-// coarse right-hand side = P^T r: gather of the 4 x 4 fine residuals around the aggregate with weights pw(y) * pw(x)
+// coarse right-hand side = P^T r: gather of the 4 x 4 fine residuals around the aggregate with weights pw(y) * pw(x).
+// All sixteen loads are issued up front (fully unrolled, out-of-range positions read a clamped address with weight 0): the
+// loop with early `continue`s serialised sixteen dependent-latency loads per thread and cost ~8 us at EVERY level, however
+// small (profiles/r2_wls_ncu.md).  Same accumulation order (y outer, x inner); a zero-weight term adds exactly 0.
 __device__ __forceinline__ void op_restrict(const MgLevel &F, const MgLevel &Cc, int c)
 {
     const int J = c % Cc.W, I = c / Cc.W;
-    T acc[6] = {0, 0, 0, 0, 0, 0};
-    for (int y = 2 * I - 1; y <= 2 * I + 2; ++y) {
-        if (y < 0 || y >= F.H) continue;
-        const T wy = pw(y, I, Cc.H);
-        if (wy == T(0)) continue;
-        for (int x = 2 * J - 1; x <= 2 * J + 2; ++x) {
-            if (x < 0 || x >= F.W) continue;
-            const T w = wy * pw(x, J, Cc.W);
-            if (w == T(0)) continue;
-            T r[6];
-            ld6(F.t, y * F.W + x, F.n, r);
+    T wgt[16];
+    int idx[16];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) acc[k] += w * r[k];
+    for (int dy = 0; dy < 4; ++dy) {
+        const int y = 2 * I - 1 + dy;
+        const bool oky = y >= 0 && y < F.H;
+        const T wy = oky ? pw(y, I, Cc.H) : T(0);
+        const int yc = min(max(y, 0), F.H - 1);
+#pragma unroll
+        for (int dx = 0; dx < 4; ++dx) {
+            const int x = 2 * J - 1 + dx;
+            const bool okx = x >= 0 && x < F.W;
+            wgt[dy * 4 + dx] = okx ? wy * pw(x, J, Cc.W) : T(0);
+            idx[dy * 4 + dx] = yc * F.W + min(max(x, 0), F.W - 1);
         }
+    }
+    T acc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        T r[6];
+        ld6(F.t, idx[q], F.n, r);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[k] += wgt[q] * r[k];
     }
     st6(Cc.b, c, Cc.n, acc);
 }
