@@ -41,7 +41,7 @@ int main(int argc, char **argv)
     int gpu_id = 0, ngpu = 1, inflight = 1, engine = 3, resume = 0, vis = 0;
     std::vector<Param> params = {
         {"m", "Directory of network models.", 0, &model_dir},
-        {"i", "Input directory of content and style images and pairs.txt.", 0, &input_dir},
+        {"i", "Input directory of content and style images (PNG) and pairs.txt.", 0, &input_dir},
         {"o", "Output directory of result images.", 0, &output_dir},
         {"g", "GPU ID (default: 0).", 1, &gpu_id},
         {"bds", "Weight of reverse color in BDS voting (default: 2.0).", 2, &cfg.bds_weight},
