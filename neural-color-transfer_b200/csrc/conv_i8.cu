@@ -35,6 +35,7 @@ constexpr int NTHREADS = 192;
 constexpr int NXD = 4, NWD = 3;                                // digit planes of activations / weights
 constexpr int SMEM_LIMIT = 227 * 1024;
 
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -285,6 +286,196 @@ conv3x3_i8_kernel(const __grid_constant__ ConvMapsI8 maps, const float *__restri
     }
 }
 
+// ------------------------------------------------------------------ persistent variant
+// One CTA per SM walks the (pixel tile, N tile) list with a stride of gridDim.x.  What the one-tile-per-CTA kernel pays per
+// tile -- barrier set-up, TMEM allocation, the first TMA round trip with an empty pipeline, the epilogue with the tensor
+// pipe idle, CTA teardown and relaunch -- is paid once, and across tiles the three roles overlap: the TMA warp runs ahead
+// into the next tile's stages while the epilogue drains the current one, and with NBUF = 2 accumulator sets in TMEM
+// (4 x BN x 2 <= 512 columns, i.e. BN = 64) the MMA warp starts the next tile while the epilogue warps still read the
+// previous set.  Shallow layers (K = 576: conv1_2, conv2_1) are epilogue-bound in the one-tile kernel (25 - 37 % tensor
+// pipe, profiles/r2_conv_i8_ncu.md); results are bit-identical (same integer sums, same epilogue).
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN, int KB, int STAGES, int NBUF>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv3x3_i8_persistent_kernel(const __grid_constant__ ConvMapsI8 maps, const float *__restrict__ bias, const int *__restrict__ wexp,
+                             const uint32_t *__restrict__ in_max_bits, float *__restrict__ out, uint32_t *__restrict__ out_max_bits,
+                             int *__restrict__ dbg_acc, int H, int W, int Cin, int Cout, int tiles_x, int total_tiles)
+{
+    using Cfg = I8Cfg<BN, KB>;
+    constexpr int A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr int OFF_B = NXD * A_BYTES;
+    constexpr int TMEM_COLS = NBUF * 4 * BN;
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two <= 512 columns");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + STAGES * STAGE_BYTES;   // full[STAGES], empty[STAGES], tfull[NBUF], tempty[NBUF], tmem_ptr
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + NBUF + b); };
+    const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 2 * NBUF);
+    uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * NBUF));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pix_tiles = total_tiles / (Cout / BN);
+    const int kchunks = Cin / KB;
+    const int NKB = 9 * kchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < NBUF; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 4);   // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp == 0) {
+        // ===== TMA producer: the stage ring runs on across tile boundaries =====
+        if (lane == 0) {
+            int g = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int pt = t % pix_tiles, n0 = (t / pix_tiles) * BN;   // pixel tile fastest: concurrent CTAs share the weight tile
+                const int tile_y0 = (pt / tiles_x) * TILE_H, tile_x0 = (pt % tiles_x) * TILE_W;
+                for (int kb = 0; kb < NKB; ++kb, ++g) {
+                    const int s = g % STAGES;
+                    if (g >= STAGES) mbar_wait(empty_bar(s), (uint32_t)(((g / STAGES) - 1) & 1));
+                    const int tap = kb / kchunks, kc = (kb % kchunks) * KB;
+                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                    const uint32_t st = base + s * STAGE_BYTES;
+                    mbar_expect_tx(full_bar(s), (uint32_t)STAGE_BYTES);
+#pragma unroll
+                    for (int i = 0; i < NXD; ++i) tma_load_3d(st + i * A_BYTES, &maps.a[i], full_bar(s), kc, tile_x0 + dx, tile_y0 + dy);
+#pragma unroll
+                    for (int j = 0; j < NWD; ++j) tma_load_2d(st + OFF_B + j * B_BYTES, &maps.b[j], full_bar(s), tap * Cin + kc, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc_u = make_idesc_i8(BM, BN, 0, 1);
+            constexpr uint32_t idesc_s = make_idesc_i8(BM, BN, 1, 1);
+            int g = 0, it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int buf = it % NBUF;
+                if (it >= NBUF) {   // the epilogue has drained this accumulator set
+                    mbar_wait(tempty_bar(buf), (uint32_t)(((it / NBUF) - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * 4 * BN);
+                for (int kb = 0; kb < NKB; ++kb, ++g) {
+                    const int s = g % STAGES;
+                    mbar_wait(full_bar(s), (uint32_t)((g / STAGES) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * STAGE_BYTES;
+                    uint64_t ad[NXD], bd[NWD];
+#pragma unroll
+                    for (int i = 0; i < NXD; ++i) ad[i] = make_desc<KB>(st + i * A_BYTES);
+#pragma unroll
+                    for (int j = 0; j < NWD; ++j) bd[j] = make_desc<KB>(st + OFF_B + j * B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < KB / 32; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                        const uint32_t acc = (kb | k) != 0;
+                        umma_i8(tacc + 0 * BN, ad[0] + adv, bd[0] + adv, idesc_u, acc);
+                        umma_i8(tacc + 1 * BN, ad[0] + adv, bd[1] + adv, idesc_u, acc);
+                        umma_i8(tacc + 1 * BN, ad[1] + adv, bd[0] + adv, idesc_s, 1u);
+                        umma_i8(tacc + 2 * BN, ad[0] + adv, bd[2] + adv, idesc_u, acc);
+                        umma_i8(tacc + 2 * BN, ad[1] + adv, bd[1] + adv, idesc_s, 1u);
+                        umma_i8(tacc + 2 * BN, ad[2] + adv, bd[0] + adv, idesc_s, 1u);
+                        umma_i8(tacc + 3 * BN, ad[1] + adv, bd[2] + adv, idesc_s, acc);
+                        umma_i8(tacc + 3 * BN, ad[2] + adv, bd[1] + adv, idesc_s, 1u);
+                        umma_i8(tacc + 3 * BN, ad[3] + adv, bd[0] + adv, idesc_s, 1u);
+                    }
+                    umma_commit(empty_bar(s));
+                    if (kb == NKB - 1) umma_commit(tfull_bar(buf));
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: 4 warps, warp (id % 4) owns TMEM lanes [32*(id%4), +32) =====
+        const int lg = warp & 3;
+        const int E = q_exponent_bits(__ldg(in_max_bits));
+        const int m = lg * 32 + lane;
+        float vmax = 0.f;
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int buf = it % NBUF;
+            const int pt = t % pix_tiles, n0 = (t / pix_tiles) * BN;
+            const int tile_y0 = (pt / tiles_x) * TILE_H, tile_x0 = (pt % tiles_x) * TILE_W;
+            const int x = tile_x0 + (m % TILE_W), y = tile_y0 + (m / TILE_W);
+            const bool valid = x < W && y < H;
+            const size_t off = ((size_t)y * W + x) * Cout + n0;
+            mbar_wait(tfull_bar(buf), (uint32_t)((it / NBUF) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                int32_t a0[16], a1[16], a2[16], a3[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 4 * BN + c0);
+                tmem_ld16(taddr + 0 * BN, a0);
+                tmem_ld16(taddr + 1 * BN, a1);
+                tmem_ld16(taddr + 2 * BN, a2);
+                tmem_ld16(taddr + 3 * BN, a3);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (valid) {
+                    if (dbg_acc) {
+                        const size_t plane = (size_t)H * W * Cout;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            dbg_acc[0 * plane + off + c0 + j] = a0[j];
+                            dbg_acc[1 * plane + off + c0 + j] = a1[j];
+                            dbg_acc[2 * plane + off + c0 + j] = a2[j];
+                            dbg_acc[3 * plane + off + c0 + j] = a3[j];
+                        }
+                    }
+                    float o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const long long S = ((long long)a0[j] << 24) + ((long long)a1[j] << 16) + ((long long)a2[j] << 8) + (long long)a3[j];
+                        const int e = E + __ldg(wexp + n0 + c0 + j) - 37;
+                        const double scale = __longlong_as_double((long long)(e + 1023) << 52);
+                        const float v = __double2float_rn(__ll2double_rn(S) * scale);
+                        o[j] = fmaxf(__fadd_rn(v, __ldg(bias + n0 + c0 + j)), 0.f);
+                        vmax = fmaxf(vmax, o[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4 *>(out + off + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                }
+            }
+            // this warp has read its lanes of the accumulator set: hand it back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+        uint32_t mb = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));
+        if (lane == 0 && out_max_bits) atomicMax(out_max_bits, mb);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------ activation digit planes
 __device__ __forceinline__ void q_digits(float v, double s, int &d0, int &d1, int &d2, int &d3)
 {
@@ -416,6 +607,8 @@ int encode_wgt(nct_ctx *ctx, EncodeTiledFn encode, CUtensorMap *m, const int8_t 
     return NCT_OK;
 }
 
+int env_int(const char *name, int dflt);
+
 template <int BN, int KB>
 int launch(nct_ctx *ctx, const ConvMapsI8 &maps, const float *bias, const int *wexp, const uint32_t *in_max, float *out, uint32_t *out_max,
            int *dbg, int H, int W, int Cin, int Cout)
@@ -423,6 +616,21 @@ int launch(nct_ctx *ctx, const ConvMapsI8 &maps, const float *bias, const int *w
     using Cfg = I8Cfg<BN, KB>;
     constexpr int STAGES = Cfg::STAGES;
     const int tiles_x = nct_div_up(W, TILE_W), tiles_y = nct_div_up(H, TILE_H);
+    // persistent tile loop for the shallow layers (K = 9 Cin <= 1152: conv1_2 ... conv3_1), where the one-tile kernel is
+    // epilogue-bound; the deep layers are tensor-bound either way and measured 5 - 10 % slower with the single accumulator set
+    // they can afford (profiles/r2_conv_i8_ncu.md).  NCT_I8_PERSIST=0 / 1 forces one kernel for every layer (A/B, tests).
+    const int persist = env_int("NCT_I8_PERSIST", -1);
+    if (persist == 1 || (persist < 0 && Cin <= 128)) {
+        constexpr int NBUF = (BN == 64) ? 2 : 1;   // two accumulator sets fit TMEM's 512 columns only at BN = 64
+        const int total = tiles_x * tiles_y * (Cout / BN);
+        const int grid = total < ctx->num_sms ? total : ctx->num_sms;
+        const size_t smem_p = (size_t)STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 2 * NBUF + 1) + 1024;
+        NCT_CUDA(ctx, cudaFuncSetAttribute(conv3x3_i8_persistent_kernel<BN, KB, STAGES, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+        conv3x3_i8_persistent_kernel<BN, KB, STAGES, NBUF><<<grid, NTHREADS, smem_p, ctx->stream>>>(maps, bias, wexp, in_max, out, out_max, dbg, H, W,
+                                                                                                 Cin, Cout, tiles_x, total);
+        NCT_CHECK_LAUNCH(ctx);
+        return NCT_OK;
+    }
     dim3 grid(tiles_x * tiles_y, Cout / BN);
     const size_t smem = (size_t)STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 2) + 1024;
     NCT_CUDA(ctx, cudaFuncSetAttribute(conv3x3_i8_kernel<BN, KB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

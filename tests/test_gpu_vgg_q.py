@@ -140,3 +140,23 @@ def test_pipeline_end_to_end_with_the_tensor_core_engine_against_independent_ora
     ndiff = int((out != ref).sum())
     print(f"engine 3 end-to-end vs independent fixed-point oracle ({ch}x{cw} / {sh}x{sw}): PSNR {ps:.1f} dB, {ndiff} of {out.size} bytes differ")
     assert ps >= 50.0
+
+
+@pytest.mark.parametrize("persist", ["0", "1"])
+def test_one_tile_and_persistent_kernels_give_the_same_bits(qctx, dev, weights, persist, monkeypatch):
+    """conv3x3_i8_kernel (one tile per CTA) and conv3x3_i8_persistent_kernel (one CTA per SM walking the tile list, two
+    accumulator sets in TMEM at BN = 64) compute the same integer sums: forcing either for EVERY layer reproduces the default
+    mix (persistent for the shallow layers only) bit for bit."""
+    img, _ = synth.pair(13, 112, 96)
+    t = to_dev(img, dev)
+    base = qctx.predict(t, 0)
+    qctx.synchronize()
+    base = [f.cpu().numpy() for f in base]
+    monkeypatch.setenv("NCT_I8_PERSIST", persist)
+    got = qctx.predict(t, 0)
+    qctx.synchronize()
+    for l in range(5):
+        assert np.array_equal(base[l].view(np.uint32), got[l].cpu().numpy().view(np.uint32))
+    ref = vgg.features_fixedpoint(img, weights, 0)
+    for l in range(5):
+        assert np.array_equal(got[l].cpu().numpy().view(np.uint32), ref[l].view(np.uint32))
