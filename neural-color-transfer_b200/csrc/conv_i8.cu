@@ -276,7 +276,7 @@ conv3x3_i8_kernel(const __grid_constant__ ConvMapsI8 maps, const float *__restri
         }
         // tensor maximum for the next layer's quantisation (non-negative floats order like their bit patterns)
         uint32_t mb = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));
-        if (lane == 0 && out_max_bits) atomicMax(out_max_bits, mb);
+        if (lane == 0 && out_max_bits && mb > *reinterpret_cast<volatile uint32_t *>(out_max_bits)) atomicMax(out_max_bits, mb);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
@@ -466,7 +466,7 @@ conv3x3_i8_persistent_kernel(const __grid_constant__ ConvMapsI8 maps, const floa
             if (lane == 0) mbar_arrive(tempty_bar(buf));
         }
         uint32_t mb = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));
-        if (lane == 0 && out_max_bits) atomicMax(out_max_bits, mb);
+        if (lane == 0 && out_max_bits && mb > *reinterpret_cast<volatile uint32_t *>(out_max_bits)) atomicMax(out_max_bits, mb);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();

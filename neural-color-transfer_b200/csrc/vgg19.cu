@@ -81,10 +81,9 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float *__restrict
     __syncthreads();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int p = t >> 2, cg = (t & 3) * 16;
-    if (p >= H * W) {   // (whole warps stay alive for the maximum reduction below)
-        if (max_bits) __reduce_max_sync(0xFFFFFFFFu, 0u);
-        return;
-    }
+    __shared__ uint32_t smax[8];
+    float vmax = 0.f;
+    if (p < H * W) {   // (every thread stays alive for the block-wide maximum below)
     const int x = p % W, y = p / W;
     float acc[16];
 #pragma unroll
@@ -105,7 +104,6 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float *__restrict
             }
         }
     float4 *op = reinterpret_cast<float4 *>(out + (size_t)p * 64 + cg);
-    float vmax = 0.f;
 #pragma unroll
     for (int o = 0; o < 16; o += 4) {
         const float4 r = make_float4(fmaxf(acc[o] + sb[cg + o], 0.f), fmaxf(acc[o + 1] + sb[cg + o + 1], 0.f),
@@ -113,9 +111,20 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float *__restrict
         op[o / 4] = r;
         vmax = fmaxf(fmaxf(vmax, fmaxf(r.x, r.y)), fmaxf(r.z, r.w));
     }
-    if (max_bits) {   // tensor maximum for the fixed-point engine's quantisation of the next layer's input
+    }
+    if (max_bits) {
+        // tensor maximum for the fixed-point engine's quantisation of the next layer's input: ONE atomic per block, and only
+        // if it can raise the value -- one atomicMax per warp on a single address (61 000 of them at 700 x 700) serialised in L2
+        // and was most of this kernel's time
         const uint32_t mb = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));
-        if ((threadIdx.x & 31) == 0) atomicMax(max_bits, mb);
+        if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mb;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t m = smax[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) m = max(m, smax[i]);
+            if (m > *reinterpret_cast<volatile uint32_t *>(max_bits)) atomicMax(max_bits, m);
+        }
     }
 }
 
