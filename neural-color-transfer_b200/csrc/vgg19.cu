@@ -69,53 +69,87 @@ __global__ void preprocess_kernel(const uint8_t *__restrict__ bgr, float *__rest
 }
 
 // ------------------------------------------------------------------ conv1_1: Cin = 3 (K = 27), direct
-// one thread = one pixel x 16 output channels; weights [27][64] in shared memory
 __global__ void __launch_bounds__(256) conv_first_kernel(const float *__restrict__ in, const float *__restrict__ wt,
                                                          const float *__restrict__ bias, float *__restrict__ out, int H, int W,
                                                          uint32_t *__restrict__ max_bits)
 {
-    __shared__ float sw[27 * 64];
+    // weights in shared memory as [27][o4 = 0..3][group = 0..3] float4: the four channel groups a warp's lanes belong to read
+    // ONE contiguous 64-byte line per instruction (the plain [27][64] layout put groups 0 / 2 and 1 / 3 on the same banks:
+    // 2-way conflicts, 27.7 M of them per launch, and the kernel was shared-memory bound at 96 % L1 throughput)
+    __shared__ float4 sw4[27 * 16];
     __shared__ float sb[64];
-    for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = wt[i];
+    for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
+        const int tc = i / 64, o = i % 64;            // source: wt[tap * 3 + c][cout]
+        const int g = o / 16, o4 = (o % 16) / 4, e = o % 4;
+        reinterpret_cast<float *>(sw4)[((tc * 4 + o4) * 4 + g) * 4 + e] = wt[i];
+    }
     if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
+    // one thread = TWO horizontally adjacent pixels x 16 output channels: every weight vector read from shared memory feeds
+    // eight FMAs instead of four (the kernel is shared-memory-bandwidth bound); per output the FMA sequence is unchanged
+    // (tap-major, channel-minor, out-of-image taps skipped)
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int p = t >> 2, cg = (t & 3) * 16;
+    const int pairs_x = (W + 1) >> 1;
+    const int pp = t >> 2, cg = (t & 3) * 16;
     __shared__ uint32_t smax[8];
     float vmax = 0.f;
-    if (p < H * W) {   // (every thread stays alive for the block-wide maximum below)
-    const int x = p % W, y = p / W;
-    float acc[16];
+    if (pp < H * pairs_x) {   // (every thread stays alive for the block-wide maximum below)
+        const int x0 = (pp % pairs_x) * 2, y = pp / pairs_x;
+        const bool has1 = x0 + 1 < W;
+        float acc[2][16];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) acc[o] = 0.f;
+        for (int q = 0; q < 2; ++q)
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+            for (int o = 0; o < 16; ++o) acc[q][o] = 0.f;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int yy = y + ky - 1, xx = x + kx - 1;
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const float *ip = in + ((size_t)yy * W + xx) * 3;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = y + ky - 1;
+            if (yy < 0 || yy >= H) continue;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float v = ip[c];
-                const float *wp = sw + ((ky * 3 + kx) * 3 + c) * 64 + cg;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xa = x0 + kx - 1, xb = xa + 1;
+                const bool oka = xa >= 0 && xa < W, okb = has1 && xb < W;   // (xb >= 0 always)
+                const float *ipa = in + ((size_t)yy * W + (oka ? xa : 0)) * 3;
+                const float *ipb = in + ((size_t)yy * W + (okb ? xb : 0)) * 3;
 #pragma unroll
-                for (int o = 0; o < 16; ++o) acc[o] = __fmaf_rn(v, wp[o], acc[o]);
+                for (int c = 0; c < 3; ++c) {
+                    const float va = ipa[c], vb = ipb[c];
+                    const float4 *wp = sw4 + ((ky * 3 + kx) * 3 + c) * 16 + (cg >> 4);
+#pragma unroll
+                    for (int o4 = 0; o4 < 4; ++o4) {
+                        const float4 wv = wp[o4 * 4];
+                        if (oka) {
+                            acc[0][o4 * 4 + 0] = __fmaf_rn(va, wv.x, acc[0][o4 * 4 + 0]);
+                            acc[0][o4 * 4 + 1] = __fmaf_rn(va, wv.y, acc[0][o4 * 4 + 1]);
+                            acc[0][o4 * 4 + 2] = __fmaf_rn(va, wv.z, acc[0][o4 * 4 + 2]);
+                            acc[0][o4 * 4 + 3] = __fmaf_rn(va, wv.w, acc[0][o4 * 4 + 3]);
+                        }
+                        if (okb) {
+                            acc[1][o4 * 4 + 0] = __fmaf_rn(vb, wv.x, acc[1][o4 * 4 + 0]);
+                            acc[1][o4 * 4 + 1] = __fmaf_rn(vb, wv.y, acc[1][o4 * 4 + 1]);
+                            acc[1][o4 * 4 + 2] = __fmaf_rn(vb, wv.z, acc[1][o4 * 4 + 2]);
+                            acc[1][o4 * 4 + 3] = __fmaf_rn(vb, wv.w, acc[1][o4 * 4 + 3]);
+                        }
+                    }
+                }
             }
         }
-    float4 *op = reinterpret_cast<float4 *>(out + (size_t)p * 64 + cg);
 #pragma unroll
-    for (int o = 0; o < 16; o += 4) {
-        const float4 r = make_float4(fmaxf(acc[o] + sb[cg + o], 0.f), fmaxf(acc[o + 1] + sb[cg + o + 1], 0.f),
-                                     fmaxf(acc[o + 2] + sb[cg + o + 2], 0.f), fmaxf(acc[o + 3] + sb[cg + o + 3], 0.f));
-        op[o / 4] = r;
-        vmax = fmaxf(fmaxf(vmax, fmaxf(r.x, r.y)), fmaxf(r.z, r.w));
-    }
+        for (int q = 0; q < 2; ++q) {
+            if (q == 1 && !has1) break;
+            float4 *op = reinterpret_cast<float4 *>(out + ((size_t)y * W + x0 + q) * 64 + cg);
+#pragma unroll
+            for (int o = 0; o < 16; o += 4) {
+                const float4 r = make_float4(fmaxf(acc[q][o] + sb[cg + o], 0.f), fmaxf(acc[q][o + 1] + sb[cg + o + 1], 0.f),
+                                             fmaxf(acc[q][o + 2] + sb[cg + o + 2], 0.f), fmaxf(acc[q][o + 3] + sb[cg + o + 3], 0.f));
+                op[o / 4] = r;
+                vmax = fmaxf(fmaxf(vmax, fmaxf(r.x, r.y)), fmaxf(r.z, r.w));
+            }
+        }
     }
     if (max_bits) {
         // tensor maximum for the fixed-point engine's quantisation of the next layer's input: ONE atomic per block, and only
-        // if it can raise the value -- one atomicMax per warp on a single address (61 000 of them at 700 x 700) serialised in L2
-        // and was most of this kernel's time
+        // if it can raise the value
         const uint32_t mb = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(vmax));
         if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mb;
         __syncthreads();
@@ -379,7 +413,7 @@ int nct_vgg19_features(nct_ctx *ctx, const uint8_t *bgr_dev, int h, int w, int d
             if (L.level < 0) flip ^= 1;
             if (dst == cur) return nct_fail(ctx, NCT_ERR_STATE, "internal: aliasing activation buffers");
             if (i == 0) {
-                conv_first_kernel<<<nct_div_up(H * W * 4, 256), 256, 0, ctx->stream>>>(cur, v->w[0], v->b[0], dst, H, W, v->max_slots + 0);
+                conv_first_kernel<<<nct_div_up(H * ((W + 1) / 2) * 4, 256), 256, 0, ctx->stream>>>(cur, v->w[0], v->b[0], dst, H, W, v->max_slots + 0);
                 NCT_CHECK_LAUNCH(ctx);
             } else {
                 int rc;
@@ -456,7 +490,7 @@ int nct_vgg19_features(nct_ctx *ctx, const uint8_t *bgr_dev, int h, int w, int d
         if (L.level < 0) flip ^= 1;
         if (dst == cur) return nct_fail(ctx, NCT_ERR_STATE, "internal: aliasing activation buffers");
         if (i == 0) {
-            conv_first_kernel<<<nct_div_up(H * W * 4, 256), 256, 0, ctx->stream>>>(cur, v->w[0], v->b[0], dst, H, W, nullptr);
+            conv_first_kernel<<<nct_div_up(H * ((W + 1) / 2) * 4, 256), 256, 0, ctx->stream>>>(cur, v->w[0], v->b[0], dst, H, W, nullptr);
         } else if (v->engine >= 1) {
             int rc = nct_conv3x3_tensorcore(ctx, x3 ? cur_hi : cur, x3 ? cur_lo : nullptr, x3 ? v->wk_hi[i] : v->wk[i],
                                             x3 ? v->wk_lo[i] : nullptr, v->b[i], dst, dst_hi, dst_lo, H, W, L.cin, L.cout);
