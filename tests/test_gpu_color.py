@@ -292,3 +292,24 @@ def test_solve_direct_rejects_a_matrix_that_is_not_upper_triangular(pkg, ctx):
     A = np.array([1.0, 0.5, 1.0])
     with pytest.raises(pkg.NctError):
         ctx.solve_direct(A, np.array([0, 1, 3]), np.array([0, 0, 1]), np.zeros((6, 2)), one_based=False)   # entry (1, 0) is below the diagonal
+
+
+@pytest.mark.parametrize("mode", ["2", "1", "0"])
+def test_wls_iteration_budget_is_enforced_on_the_device(pkg, ctx, dev, mode, monkeypatch):
+    """max_iters is checked by the kernels themselves (PcgScalars::done): with a budget far below what the system needs the
+    solve stops after exactly that many iterations -- in particular the device-side WHILE loop terminates -- and reports
+    the failure instead of returning an unconverged result as if it were one."""
+    monkeypatch.setenv("NCT_WLS_LOOP", mode)
+    rng = np.random.default_rng(1)
+    H, W = 96, 112
+    cnt, _ = synth.pair(9, H, W)
+    lab = color.bgr2lab_u8(cnt)
+    a = 1.0 + 0.5 * rng.standard_normal((H, W, 3))
+    b = 0.2 * rng.standard_normal((H, W, 3))
+    ga, gb = to_dev(a, dev), to_dev(b, dev)
+    with pytest.raises(pkg.NctError, match="did not reach"):
+        ctx.solve_wls(ga, gb, to_dev(np.ones((H, W)), dev), to_dev(lab, dev), 3.0, 1.2, rel_tol=1e-12, max_iters=5)
+    # the context is still usable and the next solve converges
+    ga, gb = to_dev(a, dev), to_dev(b, dev)
+    its, res = ctx.solve_wls(ga, gb, to_dev(np.ones((H, W)), dev), to_dev(lab, dev), 3.0, 1.2, rel_tol=1e-8)
+    assert res <= 1e-8 and its > 5
