@@ -766,28 +766,55 @@ int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1
     uint32_t *tmp[2] = {tmp0, tmp1};
     // last-change steps, double buffered like the field: [buffer][direction 0 | direction 1]
     const size_t nq = (size_t)s.nq_total;
-    NCT_CUDA(ctx, cudaMemsetAsync(lc, 0xff, nq, ctx->stream));
     int8_t *lcbuf[2][2] = {{lc, lc + s.nq0}, {lc + nq, lc + nq + s.nq0}};
-    int step = 0;
-    for (int iter = 0; iter < iters; ++iter)
-        for (int jump = 8; jump > 0; jump /= 2, ++step) {
-            s.iter = iter;
-            s.jump = jump;
-            s.t = step;
-            s.first = (step == 0);
-            s.do_random = (jump == 1);
-            for (int d = 0; d < ndir; ++d) {
-                // even steps read the caller's buffer and write scratch; odd steps the reverse.
-                // 4*iters steps is even, so the final NNF lands in the caller's buffer.
-                s.d[d].nnf_in = (step & 1) ? tmp[d] : user[d];
-                s.d[d].nnf_out = (step & 1) ? user[d] : tmp[d];
-                s.d[d].lc_in = lcbuf[step & 1][d];
-                s.d[d].lc_out = lcbuf[(step & 1) ^ 1][d];
+    auto steps = [&]() -> int {
+        NCT_CUDA(ctx, cudaMemsetAsync(lc, 0xff, nq, ctx->stream));
+        int step = 0;
+        for (int iter = 0; iter < iters; ++iter)
+            for (int jump = 8; jump > 0; jump /= 2, ++step) {
+                s.iter = iter;
+                s.jump = jump;
+                s.t = step;
+                s.first = (step == 0);
+                s.do_random = (jump == 1);
+                for (int d = 0; d < ndir; ++d) {
+                    // even steps read the caller's buffer and write scratch; odd steps the reverse.
+                    // 4*iters steps is even, so the final NNF lands in the caller's buffer.
+                    s.d[d].nnf_in = (step & 1) ? tmp[d] : user[d];
+                    s.d[d].nnf_out = (step & 1) ? user[d] : tmp[d];
+                    s.d[d].lc_in = lcbuf[step & 1][d];
+                    s.d[d].lc_out = lcbuf[(step & 1) ^ 1][d];
+                }
+                StepLauncher<C>::go(s, ctx->stream, f16);
+                NCT_CHECK_LAUNCH(ctx);
             }
-            StepLauncher<C>::go(s, ctx->stream, f16);
-            NCT_CHECK_LAUNCH(ctx);
-        }
-    return NCT_OK;
+        return NCT_OK;
+    };
+    // The 4 * iters step launches of a level as ONE replayed graph per level shape (the pipeline calls with the same buffers
+    // for every pair, so a pair re-captures nothing); NCT_PM_GRAPH=0: plain stream launches.
+    const bool use_graph = !(getenv("NCT_PM_GRAPH") && atoi(getenv("NCT_PM_GRAPH")) == 0);
+    if (!use_graph) return steps();
+    auto P = [](const void *q) { return (unsigned long long)(uintptr_t)q; };
+    std::vector<unsigned long long> key = {(unsigned long long)C, (unsigned long long)f16, (unsigned long long)iters, (unsigned long long)ndir,
+                                           P(tmp0), P(tmp1), P(lc), P(s.counters), (unsigned long long)s.nq0, (unsigned long long)s.nq_total};
+    for (int d = 0; d < ndir; ++d) {
+        const PMDir &D = s.d[d];
+        const unsigned long long part[] = {P(D.a), P(D.b), P(D.nnf_out), P(D.nnd), P(D.rng), (unsigned long long)D.ah, (unsigned long long)D.aw,
+                                           (unsigned long long)D.bh, (unsigned long long)D.bw, (unsigned long long)D.rs_start,
+                                           (unsigned long long)D.n_mag, (unsigned long long)D.ndraws};
+        key.insert(key.end(), part, part + sizeof(part) / sizeof(part[0]));
+    }
+    char gname[64];
+    snprintf(gname, sizeof(gname), "pm_steps_c%d_%dx%d_%d", C, s.d[0].ah, s.d[0].aw, ndir);
+    if (!nct_graph_cached(ctx, gname, key)) {
+        int rc = nct_graph_begin(ctx, gname, key, nullptr);
+        if (rc) return rc;
+        rc = steps();
+        if (rc) return rc;
+        rc = nct_graph_end(ctx, gname);
+        if (rc) return rc;
+    }
+    return nct_graph_launch(ctx, gname);
 }
 
 int fill_dir(nct_ctx *ctx, PMDir &D, const void *a, const void *b, uint32_t *ann, float *annd, int ah, int aw,
