@@ -163,6 +163,25 @@ int nct_graph_end(nct_ctx *ctx, const char *name)
     return NCT_OK;
 }
 
+int nct_graph_abort(nct_ctx *ctx, const char *name, int rc)
+{
+    // leave the stream usable (a stream left in capture mode fails every later synchronise / copy on it) and keep the
+    // message of the call that failed
+    cudaGraph_t dead = nullptr;
+    cudaStreamEndCapture(ctx->stream, &dead);
+    auto it = ctx->graphs.find(name);
+    if (it != ctx->graphs.end()) {
+        if (dead && !it->second.graph) cudaGraphDestroy(dead);   // (a WHILE body belongs to its parent graph)
+        graph_release(it->second);
+        ctx->launches = it->second.launches_at_begin;
+        ctx->graphs.erase(it);
+    } else if (dead) {
+        cudaGraphDestroy(dead);
+    }
+    cudaGetLastError();
+    return rc;
+}
+
 int nct_graph_launch(nct_ctx *ctx, const char *name)
 {
     auto it = ctx->graphs.find(name);

@@ -89,6 +89,7 @@ void *nct_scratch(nct_ctx *ctx, const char *name, size_t bytes);
 bool nct_graph_cached(nct_ctx *ctx, const char *name, const std::vector<unsigned long long> &key);
 int nct_graph_begin(nct_ctx *ctx, const char *name, const std::vector<unsigned long long> &key, cudaGraphConditionalHandle *while_handle);
 int nct_graph_end(nct_ctx *ctx, const char *name);
+int nct_graph_abort(nct_ctx *ctx, const char *name, int rc);   // a launch failed while capturing: ends the capture, drops the graph, returns rc
 int nct_graph_launch(nct_ctx *ctx, const char *name);   // adds the sequence's launch count to ctx->launches once
 long long nct_graph_nodes(nct_ctx *ctx, const char *name);
 void nct_graphs_free(nct_ctx *ctx);

@@ -810,7 +810,7 @@ int launch_pm(nct_ctx *ctx, PMStep &s, int iters, uint32_t *tmp0, uint32_t *tmp1
         int rc = nct_graph_begin(ctx, gname, key, nullptr);
         if (rc) return rc;
         rc = steps();
-        if (rc) return rc;
+        if (rc) return nct_graph_abort(ctx, gname, rc);
         rc = nct_graph_end(ctx, gname);
         if (rc) return rc;
     }

@@ -674,7 +674,7 @@ int nct_solve_nonlocal(nct_ctx *ctx, double *a_dev, double *b_dev, const double 
             if (rc) return rc;
             for (int q = 0; q < kBlock; ++q) {
                 rc = iteration();
-                if (rc) return rc;
+                if (rc) return nct_graph_abort(ctx, gname, rc);
             }
             rc = nct_graph_end(ctx, gname);
             if (rc) return rc;

@@ -37,6 +37,7 @@ __constant__ float c_omega2 = 1.7f;  // damping of the second sweep of each pair
 #define OMEGA2 c_omega2
 
 typedef float T;  // precision of the preconditioner
+constexpr float kDepthThr = 0.96f;  // default of NCT_WLS_DEPTH (see mg_depth_kernel; 0 = always descend to one node)
 
 struct MgLevel {
     int H, W, n;
@@ -336,6 +337,7 @@ struct PcgScalars {
                      // of an iteration returns at once when it is set, so queued / captured iterations past the
                      // stopping point cost a few empty launches and the result does not depend on how many were queued
     int converged;
+    int bottom_last;  // last level the single-block bottom kernel descends to (mg_depth_kernel; nlevels - 1 = full depth)
 };
 
 // rr_k <= tol^2 bb_k for all six right-hand sides (bb_k = 0: only an exactly zero residual counts)
@@ -447,7 +449,7 @@ __device__ __forceinline__ void bottom_body(const MgLevel *lv, int bottom, int n
 __global__ void __launch_bounds__(1024) mg_bottom_kernel(MgHierarchy h, const PcgScalars *sc)
 {
     if (sc->done) return;
-    bottom_body(h.lv, h.bottom, h.nlevels);
+    bottom_body(h.lv, h.bottom, sc->bottom_last + 1);
 }
 
 // The same bottom of the V-cycle with every vector and coefficient of its levels staged in SHARED memory: a sweep
@@ -459,11 +461,12 @@ __global__ void __launch_bounds__(1024) mg_bottom_smem_kernel(MgHierarchy h, con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ MgLevel lv[MAX_LEVELS];
     if (sc->done) return;
+    const int nlev = sc->bottom_last + 1;  // levels past bottom_last are neither staged nor visited
     T *sp = reinterpret_cast<T *>(smem_raw);
     if (threadIdx.x == 0) {
         T *tbuf = sp;
         T *q = sp + (size_t)h.lv[h.bottom].n * 6;
-        for (int k = h.bottom; k < h.nlevels; ++k) {
+        for (int k = h.bottom; k < nlev; ++k) {
             MgLevel L = h.lv[k];
             const int n2 = (L.n + 1) & ~1;  // keep every array 8-byte aligned
             L.x = q; q += (size_t)n2 * 6;
@@ -477,7 +480,7 @@ __global__ void __launch_bounds__(1024) mg_bottom_smem_kernel(MgHierarchy h, con
         }
     }
     __syncthreads();
-    for (int k = h.bottom; k < h.nlevels; ++k) {
+    for (int k = h.bottom; k < nlev; ++k) {
         const MgLevel &G = h.lv[k];
         const MgLevel &S = lv[k];
         T *sinvd = S.invd, *swx = const_cast<T *>(S.wx), *swy = const_cast<T *>(S.wy);
@@ -497,7 +500,7 @@ __global__ void __launch_bounds__(1024) mg_bottom_smem_kernel(MgHierarchy h, con
         }
     }
     __syncthreads();
-    bottom_body(lv, h.bottom, h.nlevels);
+    bottom_body(lv, h.bottom, nlev);
     {
         const MgLevel &G = h.lv[h.bottom];
         const MgLevel &S = lv[h.bottom];
@@ -545,7 +548,7 @@ __global__ void __cluster_dims__(MID_CTAS, 1, 1) __launch_bounds__(MID_TPB) mg_m
         for (int c = tid; c < Cc.n; c += nthreads) op_restrict(L, Cc, c);
         cluster_sync();
     }
-    if (rank == 0) bottom_body(h.lv, h.bottom, h.nlevels);
+    if (rank == 0) bottom_body(h.lv, h.bottom, sc->bottom_last + 1);
     cluster_sync();
     for (int k = h.bottom - 1; k >= mid; --k) {
         const MgLevel &L = h.lv[k];
@@ -598,6 +601,42 @@ __global__ void mg_diag_kernel(MgLevel L)
     if (y + 1 < L.H) d += L.wy[i];
     if (y > 0) d += L.wy[i - L.W];
     L.invd[i] = T(1) / d;
+}
+
+// How deep the single-block bottom kernel has to go.  The screening (data) term of a level grows 4x per coarsening, the
+// edge weights 1x, so from some level on a node's diagonal is mostly data term and the two damped-Jacobi sweeps the
+// coarsest level gets anyway leave nothing for the levels below it to correct: the PCG iteration counts are the same
+// (profiles/r2_wls_tuning.md, hierarchy depth).  bottom_last = the first level >= h.bottom whose MEAN off-diagonal share
+// sum_j |a_ij| / a_ii is <= thr (nlevels - 1 if none, and for thr <= 0).  One block, shares quantised to 2^-20 and summed
+// as integers: the decision does not depend on a floating-point summation order.
+__global__ void __launch_bounds__(1024) mg_depth_kernel(MgHierarchy h, PcgScalars *sc, float thr)
+{
+    __shared__ unsigned long long part[32];
+    __shared__ int found;
+    if (threadIdx.x == 0) found = -1;
+    __syncthreads();
+    if (thr > 0.f) {
+        const unsigned long long thr_q = (unsigned long long)(thr * 1048576.f);
+        for (int k = h.bottom; k < h.nlevels - 1; ++k) {
+            const MgLevel &L = h.lv[k];
+            unsigned long long acc = 0;
+            for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
+                const float share = 1.f - L.rsum[i] * L.invd[i];
+                acc += (unsigned long long)(fminf(fmaxf(share, 0.f), 1.f) * 1048576.f + 0.5f);
+            }
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long tot = 0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
+                if (tot <= thr_q * (unsigned long long)L.n) found = k;
+            }
+            __syncthreads();
+            if (found >= 0) break;
+        }
+    }
+    if (threadIdx.x == 0) sc->bottom_last = found >= 0 ? found : h.nlevels - 1;
 }
 
 // fine-level edge weights in FP64 (the operator CG solves with) plus FP32 copies for the preconditioner
@@ -926,6 +965,11 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
         mg_diag_kernel<<<nct_div_up(h.lv[k].n, TPB), TPB, 0, ctx->stream>>>(h.lv[k]);
         NCT_CHECK_LAUNCH(ctx);
     }
+    // NCT_WLS_DEPTH = mean off-diagonal share below which the bottom kernel stops descending (0 = always to one node)
+    const char *depth_env = getenv("NCT_WLS_DEPTH");   // read per solve (tests switch it)
+    const float depth_thr = depth_env ? (float)atof(depth_env) : kDepthThr;
+    mg_depth_kernel<<<1, 1024, 0, ctx->stream>>>(h, sc, depth_thr);
+    NCT_CHECK_LAUNCH(ctx);
     pack6_kernel<<<blocks0, TPB, 0, ctx->stream>>>(a_dev, b_dev, n0, x);
     NCT_CHECK_LAUNCH(ctx);
     NCT_CUDA(ctx, cudaMemsetAsync(p0, 0, sizeof(double) * 6 * (size_t)n0, ctx->stream));
@@ -980,9 +1024,9 @@ int nct_solve_wls(nct_ctx *ctx, double *a_dev, double *b_dev, const double *roug
             int rc = nct_graph_begin(ctx, gname, key, mode == 2 ? &handle : nullptr);
             if (rc) return rc;
             rc = iteration(p0, p1, 0);
-            if (rc) return rc;
+            if (rc) return nct_graph_abort(ctx, gname, rc);
             rc = iteration(p1, p0, handle);
-            if (rc) return rc;
+            if (rc) return nct_graph_abort(ctx, gname, rc);
             rc = nct_graph_end(ctx, gname);
             if (rc) return rc;
         }

@@ -213,6 +213,31 @@ def test_solve_wls_matches_direct_solve(ctx, dev, H, W, lam):
           f"max rel.err a {max(relerr(ga.cpu().numpy()[..., c], oa[..., c]) for c in range(3)):.2e}")
 
 
+@pytest.mark.parametrize("H,W,lam", [(700, 700, 6.144), (700, 700, 1.536), (700, 700, 0.384), (700, 700, 0.096), (350, 280, 0.096), (96, 80, 6.07)])
+def test_wls_adaptive_bottom_depth(ctx, dev, H, W, lam, monkeypatch):
+    """NCT_WLS_DEPTH = t: the single-block bottom of the V-cycle stops at the first level whose mean off-diagonal share is
+    <= t instead of descending to one node.  Same solution to the tolerance, iteration count within 2 of the full depth."""
+    rng = np.random.default_rng(H + W)
+    cnt, _ = synth.pair(6, H, W)
+    lab = color.bgr2lab_u8(cnt)
+    a = 1.0 + 0.5 * rng.standard_normal((H, W, 3))
+    b = 0.2 * rng.standard_normal((H, W, 3))
+    rough = np.where(rng.random((H, W)) < 0.1, 1e-6, 1.0)
+    got = {}
+    for thr in ("0", "0.96", "0.96"):
+        monkeypatch.setenv("NCT_WLS_DEPTH", thr)
+        ga, gb = to_dev(a, dev), to_dev(b, dev)
+        its, res = ctx.solve_wls(ga, gb, to_dev(rough, dev), to_dev(lab, dev), lam, 1.2, rel_tol=1e-8)
+        assert res <= 1e-8
+        r = (its, ga.cpu().numpy().copy(), gb.cpu().numpy().copy())
+        if thr in got:   # deterministic: the depth decision is integer arithmetic
+            assert r[0] == got[thr][0] and np.array_equal(r[1].view(np.uint64), got[thr][1].view(np.uint64))
+        got[thr] = r
+    print(f"WLS {H}x{W} lam={lam}: {got['0'][0]} iterations at full depth, {got['0.96'][0]} with the adaptive bottom")
+    assert abs(got["0.96"][0] - got["0"][0]) <= 2
+    assert relerr(got["0.96"][1], got["0"][1]) < 1e-6 and relerr(got["0.96"][2], got["0"][2]) < 1e-6
+
+
 @pytest.mark.parametrize("H,W,lam", [(128, 128, 0.096), (350, 280, 1.5), (96, 80, 6.07)])
 def test_solve_wls_loop_modes_are_bit_identical(ctx, dev, H, W, lam, monkeypatch):
     """The stopping test runs on the device after every iteration, so the solution and the iteration count do not depend on
