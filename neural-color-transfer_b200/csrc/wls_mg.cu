@@ -606,31 +606,43 @@ __global__ void mg_diag_kernel(MgLevel L)
 // How deep the single-block bottom kernel has to go.  The screening (data) term of a level grows 4x per coarsening, the
 // edge weights 1x, so from some level on a node's diagonal is mostly data term and the two damped-Jacobi sweeps the
 // coarsest level gets anyway leave nothing for the levels below it to correct: the PCG iteration counts are the same
-// (profiles/r2_wls_tuning.md, hierarchy depth).  bottom_last = the first level >= h.bottom whose MEAN off-diagonal share
-// sum_j |a_ij| / a_ii is <= thr (nlevels - 1 if none, and for thr <= 0).  One block, shares quantised to 2^-20 and summed
-// as integers: the decision does not depend on a floating-point summation order.
+// (profiles/r2_wls_tuning.md, hierarchy depth).  bottom_last = the first level >= h.bottom whose off-diagonal share
+// sum_j |a_ij| / a_ii has MEAN <= thr and MAX <= kDepthMax (nlevels - 1 if none, and for thr <= 0).  The maximum is what
+// keeps the full depth for an image with a contiguous low-roughness region (out-of-range colours: roughness 1e-6): its
+// coarse nodes keep a share of ~1 at every level and need the global coupling of the deep levels, whatever the mean says.
+// One block, shares quantised to 2^-20, integer sum and maximum: the decision does not depend on a summation order.
+constexpr float kDepthMax = 0.99f;
 __global__ void __launch_bounds__(1024) mg_depth_kernel(MgHierarchy h, PcgScalars *sc, float thr)
 {
     __shared__ unsigned long long part[32];
+    __shared__ unsigned pmax[32];
     __shared__ int found;
     if (threadIdx.x == 0) found = -1;
     __syncthreads();
     if (thr > 0.f) {
         const unsigned long long thr_q = (unsigned long long)(thr * 1048576.f);
+        const unsigned max_q = (unsigned)(kDepthMax * 1048576.f);
         for (int k = h.bottom; k < h.nlevels - 1; ++k) {
             const MgLevel &L = h.lv[k];
             unsigned long long acc = 0;
+            unsigned mx = 0;
             for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
                 const float share = 1.f - L.rsum[i] * L.invd[i];
-                acc += (unsigned long long)(fminf(fmaxf(share, 0.f), 1.f) * 1048576.f + 0.5f);
+                const unsigned q = (unsigned)(fminf(fmaxf(share, 0.f), 1.f) * 1048576.f + 0.5f);
+                acc += q;
+                mx = max(mx, q);
             }
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+            for (int o = 16; o > 0; o >>= 1) {
+                acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            if ((threadIdx.x & 31) == 0) { part[threadIdx.x >> 5] = acc; pmax[threadIdx.x >> 5] = mx; }
             __syncthreads();
             if (threadIdx.x == 0) {
                 unsigned long long tot = 0;
-                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
-                if (tot <= thr_q * (unsigned long long)L.n) found = k;
+                unsigned m = 0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { tot += part[w]; m = max(m, pmax[w]); }
+                if (tot <= thr_q * (unsigned long long)L.n && m <= max_q) found = k;
             }
             __syncthreads();
             if (found >= 0) break;

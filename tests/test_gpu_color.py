@@ -213,16 +213,21 @@ def test_solve_wls_matches_direct_solve(ctx, dev, H, W, lam):
           f"max rel.err a {max(relerr(ga.cpu().numpy()[..., c], oa[..., c]) for c in range(3)):.2e}")
 
 
-@pytest.mark.parametrize("H,W,lam", [(700, 700, 6.144), (700, 700, 1.536), (700, 700, 0.384), (700, 700, 0.096), (350, 280, 0.096), (96, 80, 6.07)])
-def test_wls_adaptive_bottom_depth(ctx, dev, H, W, lam, monkeypatch):
-    """NCT_WLS_DEPTH = t: the single-block bottom of the V-cycle stops at the first level whose mean off-diagonal share is
-    <= t instead of descending to one node.  Same solution to the tolerance, iteration count within 2 of the full depth."""
+@pytest.mark.parametrize("H,W,lam,hole", [(700, 700, 6.144, 0), (700, 700, 1.536, 0), (700, 700, 0.384, 0), (700, 700, 0.096, 0), (350, 280, 0.096, 0),
+                                          (96, 80, 6.07, 0), (700, 700, 0.096, 380), (700, 700, 0.384, 560), (350, 280, 0.096, 150)])
+def test_wls_adaptive_bottom_depth(ctx, dev, H, W, lam, hole, monkeypatch):
+    """NCT_WLS_DEPTH = t: the single-block bottom of the V-cycle stops at the first level whose off-diagonal share has
+    mean <= t and maximum <= 0.99 instead of descending to one node.  Same solution to the tolerance, iteration count
+    within 2 of the full depth -- also with a contiguous hole x hole region of roughness 1e-6 (out-of-range colours),
+    which needs the deep levels and must keep them (a mean-only criterion costs 8-15 iterations there)."""
     rng = np.random.default_rng(H + W)
     cnt, _ = synth.pair(6, H, W)
     lab = color.bgr2lab_u8(cnt)
     a = 1.0 + 0.5 * rng.standard_normal((H, W, 3))
     b = 0.2 * rng.standard_normal((H, W, 3))
     rough = np.where(rng.random((H, W)) < 0.1, 1e-6, 1.0)
+    if hole:
+        rough[H // 8:H // 8 + hole, W // 10:W // 10 + hole] = 1e-6
     got = {}
     for thr in ("0", "0.96", "0.96"):
         monkeypatch.setenv("NCT_WLS_DEPTH", thr)
@@ -233,7 +238,7 @@ def test_wls_adaptive_bottom_depth(ctx, dev, H, W, lam, monkeypatch):
         if thr in got:   # deterministic: the depth decision is integer arithmetic
             assert r[0] == got[thr][0] and np.array_equal(r[1].view(np.uint64), got[thr][1].view(np.uint64))
         got[thr] = r
-    print(f"WLS {H}x{W} lam={lam}: {got['0'][0]} iterations at full depth, {got['0.96'][0]} with the adaptive bottom")
+    print(f"WLS {H}x{W} lam={lam} hole={hole}: {got['0'][0]} iterations at full depth, {got['0.96'][0]} with the adaptive bottom")
     assert abs(got["0.96"][0] - got["0"][0]) <= 2
     assert relerr(got["0.96"][1], got["0"][1]) < 1e-6 and relerr(got["0.96"][2], got["0"][2]) < 1e-6
 
